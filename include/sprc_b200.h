@@ -1,0 +1,137 @@
+/* libsprc_b200 — C ABI of the B200-native composed-image-retrieval inference path.
+ *
+ * The reference (chunmeifeng/SPRC) has no FFI layer: its boundary is the Python module surface
+ * `lavis.models.load_model_and_preprocess` -> `Blip2QformerCirAlignPrompt.{extract_target_features,
+ * inference, inference_rerank}` plus `validate_blip.compute_*`.  This header is the
+ * C boundary underneath our Python mirror of that surface (sprc_b200/model.py binds it with ctypes);
+ * every entry point names the reference function it replaces (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *   - return 0 on success, a negative errno-style code on failure; `sprc_last_error()` returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - all `const void*` / `void*` tensor arguments are DEVICE pointers unless the name ends in `_host`;
+ *     the caller owns every input and output buffer, the handle owns weights and workspace;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation
+ *     except in the `*_host` convenience calls, which synchronise the stream before returning;
+ *   - one handle per GPU / process, not re-entrant.
+ */
+#ifndef SPRC_B200_H_
+#define SPRC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPRC_ABI_VERSION 1
+
+#define SPRC_NUM_QUERY_TOKENS 32 /* blip2_qformer_cir_align_prompt.py:52  num_query_token */
+#define SPRC_MAX_TXT_LEN 32      /* blip2_qformer_cir_align_prompt.py:55  max_txt_len */
+#define SPRC_EMBED_DIM 256       /* blip2_qformer_cir_align_prompt.py:54  embed_dim */
+#define SPRC_VIT_TOKENS 257      /* (224/14)^2 + cls; eva_vit.py:324-331, clip_vit.py:171-178 */
+#define SPRC_QF_HIDDEN 768       /* BertConfig bert-base-uncased; blip2.py:47-61 */
+
+typedef struct sprc_handle sprc_handle;
+
+enum sprc_vit_kind {
+  SPRC_VIT_EVA_G = 0, /* eva_vit.py:428-441   create_eva_vit_g : 1408 x 39 blocks, 16 heads x 88, mlp 6144 */
+  SPRC_VIT_CLIP_L = 1 /* clip_vit.py:242-250  create_clip_vit_L: 1024 x 23 blocks, 16 heads x 64, mlp 4096 */
+};
+
+enum sprc_dtype { SPRC_F32 = 0, SPRC_F16 = 1, SPRC_BF16 = 2, SPRC_I64 = 3, SPRC_I32 = 4 };
+
+typedef struct sprc_config {
+  int vit_kind;    /* enum sprc_vit_kind */
+  int vit_depth;   /* 0 = the reference's depth for vit_kind; smaller values build truncated test models */
+  int qf_layers;   /* 0 = 12 (BERT-base); smaller values for tests */
+  int max_images;  /* largest B accepted by sprc_encode_gallery (workspace is sized for it) */
+  int max_queries; /* largest Bq accepted by sprc_encode_query */
+  int max_pairs;   /* largest R*T accepted by sprc_rerank (0 = rerank workspace not allocated) */
+  int device;      /* CUDA device ordinal */
+} sprc_config;
+
+/* One tensor of the reference checkpoint (`ckpt["Blip2QformerCirAlignPrompt"]`, utils.py:208-222),
+ * under its reference state-dict key, fp32 or fp16, host or device memory. */
+typedef struct sprc_tensor_desc {
+  const char* name;
+  int dtype; /* enum sprc_dtype */
+  int ndim;
+  int64_t shape[4];
+  const void* data;
+} sprc_tensor_desc;
+
+int sprc_abi_version(void);
+const char* sprc_last_error(void);
+
+/* Blip2QformerCirAlignPrompt.__init__ / from_config (blip2_qformer_cir_align_prompt.py:44-92,502-529). */
+int sprc_create(const sprc_config* cfg, sprc_handle** out);
+void sprc_destroy(sprc_handle* h);
+
+/* model.load_state_dict(ckpt[...], strict=False) (blip_validate.py:107-109).  Unknown keys are ignored
+ * (the LM head, temp, prompt_tokens); `*n_missing` receives how many required tensors are still unset. */
+int sprc_load_weights(sprc_handle* h, const sprc_tensor_desc* tensors, int n, int* n_missing);
+/* Name of the i-th still-missing required tensor, or NULL. */
+const char* sprc_missing_weight(sprc_handle* h, int i);
+
+/* extract_target_features (blip2_qformer_cir_align_prompt.py:364-386): images fp32 [B,3,224,224] ->
+ * feats [B,32,256] (unit-norm rows) and raws = ln_vision(ViT(images)) [B,257,Dv].  Any output may be NULL. */
+int sprc_encode_gallery(sprc_handle* h, const float* images, int B, float* feats_f32, void* feats_bf16,
+                        float* raws_f32, void* raws_bf16, void* stream);
+
+/* The fusion half of `inference` (blip2_qformer_cir_align_prompt.py:312-350): reference embeds
+ * [Bq,257,Dv] (fp32 or bf16, `ref_dtype`) + token ids / attention mask [Bq,32] int64 (tokenisation stays
+ * on the host, :323-329) -> fusion_feats [Bq,256] fp32 unit-norm.  `ref_rows` (optional, int32 [Bq])
+ * gathers the reference rows out of a resident raw-embed table instead of a packed [Bq,...] tensor. */
+int sprc_encode_query(sprc_handle* h, const void* ref_raws, int ref_dtype, const int32_t* ref_rows,
+                      const int64_t* input_ids, const int64_t* attention_mask, int Bq, float* fusion_f32,
+                      void* fusion_bf16, void* stream);
+
+/* The similarity half of `inference` (:353-358) fused with the ranking of validate_blip.py:44-46,253-255:
+ * sim[q,n] = max_t <query[q], gallery[n,t]>, top-k by (sim desc, row asc).  gallery is bf16 [N,32,256],
+ * queries bf16 [Q,256].  out_full (optional) receives the whole fp32 [Q,N] matrix (what `inference`
+ * returns); out_score/out_idx (optional, [Q,k]) the ranking, idx = row_offset + local row. */
+int sprc_sim_topk(sprc_handle* h, const void* queries_bf16, int Q, const void* gallery_bf16, int64_t N,
+                  int64_t row_offset, int k, float* out_score, int32_t* out_idx, float* out_full, void* stream);
+
+/* Merge P candidate lists per query (the per-shard top-k after the NCCL all-gather):
+ * cand_* are [P,Q,k]; output [Q,k] sorted by (score desc, idx asc). */
+int sprc_topk_merge(sprc_handle* h, const float* cand_score, const int32_t* cand_idx, int P, int Q, int k,
+                    float* out_score, int32_t* out_idx, void* stream);
+
+/* sim of selected (query, row) pairs — CIRR subset members (validate_blip.py:268-271): rows int32 [Q,m]
+ * (negative = skip, score -inf) -> out [Q,m]. */
+int sprc_gather_scores(sprc_handle* h, const void* queries_bf16, int Q, const void* gallery_bf16, int64_t N,
+                       const int32_t* rows, int m, float* out, void* stream);
+
+/* inference_rerank (blip2_qformer_cir_rerank.py:399-445): for each of R queries, T candidates;
+ * ref rows int32 [R], candidate rows int32 [R*T] index a resident bf16 raw-embed table [*,257,Dv];
+ * p[R*T] = softmax(mean_q itm_head(h))[:, 1]. */
+int sprc_rerank(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
+                const int64_t* input_ids, const int64_t* attention_mask, int R, int T, float* p, void* stream);
+
+/* End-to-end query step with HOST buffers (what generate_*_val_predictions + compute_* do per batch,
+ * validate_blip.py:386-408,253-255): H2D of ids/mask/ref_rows, fusion, scan, top-k, D2H of [Bq,k]. */
+int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
+                         const int32_t* ref_rows_host, const int64_t* input_ids_host,
+                         const int64_t* attention_mask_host, int Bq, int k, float* out_score_host,
+                         int32_t* out_idx_host, void* stream);
+
+/* Number of kernels this library has launched on behalf of the calling process (bench `gpu_launches`). */
+int64_t sprc_launch_count(void);
+
+/* ---- single-op entry points (tests and micro-benchmarks) ------------------------------------- */
+/* C = act(A[M,K] W[N,K]^T + bias) (+ residual); impl 0 = tcgen05 product kernel, 1 = CUDA-core checker. */
+int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
+                 int grp_stride, const float* bias, const float* residual, float* out_f32, void* out_bf16,
+                 int ldc, int act, int impl, void* stream);
+int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
+                      int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream);
+int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int B, int H, int dh, int Lq,
+                      int Lk, int ldq, int ldk, int ldv, int ldo, int q_batch_rows, int kv_batch_rows,
+                      const float* key_mask, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRC_B200_H_ */

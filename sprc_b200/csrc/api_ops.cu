@@ -1,0 +1,68 @@
+// C-ABI: library-level queries and the single-op entry points declared at the bottom of
+// include/sprc_b200.h (used by tests/ and micro-benchmarks to check each kernel in isolation).
+#include "../../include/sprc_b200.h"
+#include "common.h"
+#include "ops.h"
+
+using namespace sprc;
+
+extern "C" {
+
+int sprc_abi_version(void) { return SPRC_ABI_VERSION; }
+const char* sprc_last_error(void) { return last_error(); }
+int64_t sprc_launch_count(void) { return launch_count(); }
+
+int sprc_op_gemm(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int grp_rows, int grp_stride,
+                 const float* bias, const float* residual, float* out_f32, void* out_bf16, int ldc, int act,
+                 int impl, void* stream) {
+  GemmDesc d;
+  d.A = static_cast<const bf16*>(A);
+  d.W = static_cast<const bf16*>(W);
+  d.M = M;
+  d.N = N;
+  d.K = K;
+  d.lda = lda;
+  d.ldw = ldw;
+  d.grp_rows = grp_rows;
+  d.grp_stride = grp_stride;
+  d.bias = bias;
+  d.residual = residual;
+  d.out_f32 = out_f32;
+  d.out_bf16 = static_cast<bf16*>(out_bf16);
+  d.ldc = ldc;
+  d.act = act;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return impl == 0 ? gemm_bf16_tcgen05(d, st) : gemm_bf16_simt(d, st);
+}
+
+int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
+                      int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream) {
+  return layernorm(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32, static_cast<bf16*>(out_bf16),
+                   static_cast<cudaStream_t>(stream));
+}
+
+int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int B, int H, int dh, int Lq, int Lk,
+                      int ldq, int ldk, int ldv, int ldo, int q_batch_rows, int kv_batch_rows,
+                      const float* key_mask, float scale, void* stream) {
+  AttnDesc a;
+  a.Q = static_cast<const bf16*>(Q);
+  a.K = static_cast<const bf16*>(K);
+  a.V = static_cast<const bf16*>(V);
+  a.O = static_cast<bf16*>(O);
+  a.B = B;
+  a.H = H;
+  a.dh = dh;
+  a.Lq = Lq;
+  a.Lk = Lk;
+  a.ldq = ldq;
+  a.ldk = ldk;
+  a.ldv = ldv;
+  a.ldo = ldo;
+  a.q_batch_rows = q_batch_rows;
+  a.kv_batch_rows = kv_batch_rows;
+  a.key_mask = key_mask;
+  a.scale = scale;
+  return attention(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// Host-side plumbing shared by all translation units of libsprc_b200: error reporting
+// (thread-local message + negative errno-style codes, see include/sprc_b200.h), CUDA
+// error checking and the descriptors the kernels' host launchers take.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace sprc {
+
+typedef __nv_bfloat16 bf16;
+
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define SPRC_CUDA(expr)                                                                               \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return ::sprc::set_error(-5, "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                 \
+                               cudaGetErrorString(_e));                                               \
+  } while (0)
+
+#define SPRC_TRY(expr)        \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+#define SPRC_REQUIRE(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) return ::sprc::set_error(-22, __VA_ARGS__);      \
+  } while (0)
+
+int device_sm_count();
+
+// ------------------------------------------------------------------------------------------------
+// GEMM:  C[M,N] = epilogue( A[M,K] (bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw) )
+// ------------------------------------------------------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICKGELU = 2 };
+
+struct GemmDesc {
+  const bf16* A = nullptr;
+  const bf16* W = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0;
+  // Row grouping: logical row m lives at physical row (m / grp_rows) * grp_stride + (m % grp_rows)
+  // of A (relative to the A pointer) and of the output/residual (relative to their pointers).
+  // grp_rows == 0 means "no grouping" (dense rows).  Used for the Q-Former's "first 32 rows of
+  // every 64-row sample" operands (Qformer.py:436,466 row slices) without any gather copies.
+  int grp_rows = 0, grp_stride = 0;
+  const float* bias = nullptr;      // [N] fp32
+  const float* residual = nullptr;  // fp32, pitch ldc (may alias out_f32)
+  float* out_f32 = nullptr;         // exactly one of out_f32 / out_bf16
+  bf16* out_bf16 = nullptr;
+  int ldc = 0;
+  int act = ACT_NONE;
+};
+
+int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)
+int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st);     // CUDA-core checker used by tests only
+
+}  // namespace sprc

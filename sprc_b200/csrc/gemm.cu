@@ -1,0 +1,367 @@
+// tcgen05 GEMM for sm_100a:  C = epilogue(A[M,K] * W[N,K]^T), bf16 operands, fp32 accumulate in TMEM.
+//
+// This one kernel carries every dense contraction of the hot path (SURVEY.md §2.3 K1,K3,K5,K6,K7,
+// K10-K13): ViT patch-embed / QKV / proj / fc1 / fc2 (eva_vit.py:55-59,122-146, clip_vit.py:118-122),
+// the Q-Former's linear layers (Qformer.py:133-139,287,358,373) and the ITC heads
+// (blip2_qformer_cir_align_prompt.py:80-81).
+//
+// Structure (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) into a STAGES-deep ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators
+//               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
+//               128-bit global stores (fp32 residual stream or bf16 activations)
+#include "common.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace sprc {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+
+struct GemmKernelParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int a_grp_rows;  // 0: dense (coords k, m0, 0); else (k, 0, m0 / a_grp_rows)
+  int grp_rows, grp_stride;
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  bf16* out_bf16;
+  int ldc;
+  int act;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int RING_BYTES = STAGES * (A_BYTES + B_BYTES);
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmKernelParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_blocks) * BM;
+        const int n0 = (tile % p.num_n_blocks) * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
+          if (p.a_grp_rows == 0)
+            tma_load_3d(&tmA, &full_bar[stage], sA + stage * L::A_BYTES, kb * BK, m0, 0, kEvictNormal);
+          else
+            tma_load_3d(&tmA, &full_bar[stage], sA + stage * L::A_BYTES, kb * BK, 0, m0 / p.a_grp_rows,
+                        kEvictNormal);
+          tma_load_2d(&tmB, &full_bar[stage], sB + stage * L::B_BYTES, kb * BK, n0, kEvictLast);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_blocks) * BM;
+      const int n0 = (tile % p.num_n_blocks) * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      long long orow = m;
+      if (p.grp_rows > 0) orow = static_cast<long long>(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int n = n0 + c * 32;
+        if (row_ok && n < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          }
+          const size_t off = static_cast<size_t>(orow) * p.ldc + n;
+          if (p.residual) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = r4[j];
+              v[4 * j + 0] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// bf16 tensor [d2][d1][d0] with d0 contiguous; strides in elements; box {b0,b1,b2}; 128B swizzle.
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                   uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(-38, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (rank == 3 && (strides[1] & 15)))
+    return set_error(-22, "TMA operand must be 16-byte aligned (ptr %p, pitches %llu/%llu B)", ptr,
+                     (unsigned long long)strides[0], (unsigned long long)strides[1]);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-22, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
+  using L = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  if (d.grp_rows > 0) {
+    const int groups = d.M / d.grp_rows;
+    SPRC_TRY(make_tmap_bf16(&tmA, d.A, d.K, d.grp_rows, groups, d.lda, (uint64_t)d.grp_stride * d.lda, BK,
+                            d.grp_rows, BM / d.grp_rows, 3));
+  } else {
+    SPRC_TRY(make_tmap_bf16(&tmA, d.A, d.K, d.M, 1, d.lda, (uint64_t)d.M * d.lda, BK, BM, 1, 3));
+  }
+  SPRC_TRY(make_tmap_bf16(&tmB, d.W, d.K, d.N, 1, d.ldw, 0, BK, BN, 1, 2));
+
+  GemmKernelParams p;
+  p.M = d.M;
+  p.N = d.N;
+  p.K = d.K;
+  p.num_m_blocks = (d.M + BM - 1) / BM;
+  p.num_n_blocks = (d.N + BN - 1) / BN;
+  p.num_k_blocks = (d.K + BK - 1) / BK;
+  p.a_grp_rows = d.grp_rows;
+  p.grp_rows = d.grp_rows;
+  p.grp_stride = d.grp_stride;
+  p.bias = d.bias;
+  p.residual = d.residual;
+  p.out_f32 = d.out_f32;
+  p.out_bf16 = d.out_bf16;
+  p.ldc = d.ldc;
+  p.act = d.act;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPRC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, STAGES>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, p);
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
+  SPRC_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem %dx%dx%d", d.M, d.N, d.K);
+  SPRC_REQUIRE(d.N % 32 == 0, "gemm: N=%d must be a multiple of 32", d.N);
+  SPRC_REQUIRE(d.K % 8 == 0 && d.lda % 8 == 0 && d.ldw % 8 == 0 && d.ldc % 8 == 0,
+               "gemm: K/lda/ldw/ldc must be multiples of 8 (K=%d lda=%d ldw=%d ldc=%d)", d.K, d.lda, d.ldw, d.ldc);
+  SPRC_REQUIRE((d.out_f32 != nullptr) != (d.out_bf16 != nullptr), "gemm: exactly one output pointer");
+  SPRC_REQUIRE(d.grp_rows == 0 || (BM % d.grp_rows == 0 && d.M % d.grp_rows == 0 && d.grp_stride >= d.grp_rows),
+               "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
+  const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
+  if (d.N % 256 == 0 && tiles256 >= device_sm_count()) return launch_gemm<256, 4>(d, st);
+  return launch_gemm<128, 6>(d, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core checker (tests only): one thread per output element, same epilogue semantics.
+// ------------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W, GemmKernelParams p,
+                                 int lda, int ldw) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= p.N || m >= p.M) return;
+  long long prow = m;
+  if (p.grp_rows > 0) prow = (long long)(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows);
+  const bf16* a = A + prow * lda;
+  const bf16* w = W + (size_t)n * ldw;
+  float acc = 0.f;
+  for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+  if (p.bias) acc += p.bias[n];
+  if (p.act == ACT_GELU) acc = gelu_erf(acc);
+  if (p.act == ACT_QUICKGELU) acc = quick_gelu(acc);
+  const size_t off = (size_t)prow * p.ldc + n;
+  if (p.residual) acc += p.residual[off];
+  if (p.out_f32)
+    p.out_f32[off] = acc;
+  else
+    p.out_bf16[off] = __float2bfloat16(acc);
+}
+
+int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st) {
+  GemmKernelParams p = {};
+  p.M = d.M;
+  p.N = d.N;
+  p.K = d.K;
+  p.grp_rows = d.grp_rows;
+  p.grp_stride = d.grp_stride;
+  p.bias = d.bias;
+  p.residual = d.residual;
+  p.out_f32 = d.out_f32;
+  p.out_bf16 = d.out_bf16;
+  p.ldc = d.ldc;
+  p.act = d.act;
+  dim3 grid((d.N + 127) / 128, d.M);
+  gemm_simt_kernel<<<grid, 128, 0, st>>>(d.A, d.W, p, d.lda, d.ldw);
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sprc
