@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_loader.py) on the seeded synthetic checkpoints / inputs
+of oracle/synth.py.  Run in the build container only:  `python -m oracle.make_golden [case ...]`.
+
+Each golden file holds the case description (so tests regenerate identical weights and inputs from
+the seeds) and the reference's outputs at the stage boundaries of SURVEY.md §7 step 1:
+  raws_rows  image_embeds_frozen[:, [0,1,128,256], :]   (ln_vision(ViT(x)), align_prompt.py:367-368)
+  feats      image_features [B,32,256]                  (align_prompt.py:385)
+  sim        inference(...) [Bq,N]                      (align_prompt.py:312-361)
+  fusion     fusion_feats [Bq,256]                      (align_prompt.py:348-350; recomputed from the
+                                                         reference's own sub-modules, same statements)
+  rerank_p   inference_rerank(...) [R*T]                (rerank.py:399-445)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+from . import ref_loader, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: vit, vit_depth (None = full), qf_layers, n_images, n_queries
+    "tiny_L": dict(vit="clip_L", vit_depth=2, qf_layers=2, n_images=5, n_queries=3),
+    "tiny_g": dict(vit="eva_clip_g", vit_depth=2, qf_layers=4, n_images=4, n_queries=3),
+    "full_L": dict(vit="clip_L", vit_depth=None, qf_layers=12, n_images=4, n_queries=4),
+    "full_g": dict(vit="eva_clip_g", vit_depth=None, qf_layers=12, n_images=3, n_queries=3),
+}
+RAW_ROWS = [0, 1, 128, 256]
+
+
+def reference_fusion_feats(model, reference_embeds, ids, mask):
+    """The first half of the reference's `inference`, statement for statement (align_prompt.py:314-350),
+    executed on the reference's own sub-modules; `inference` itself only returns the similarity."""
+    import torch.nn.functional as F
+
+    image_atts = torch.ones(reference_embeds.size()[:-1], dtype=torch.long)
+    query_tokens = model.query_tokens.expand(reference_embeds.shape[0], -1, -1)
+    query_atts = torch.ones(query_tokens.size()[:-1], dtype=torch.long)
+    attention_mask = torch.cat([query_atts, mask], dim=1)
+    fusion_output = model.Qformer.bert(ids, query_embeds=query_tokens, attention_mask=attention_mask,
+                                       encoder_hidden_states=reference_embeds, encoder_attention_mask=image_atts,
+                                       return_dict=True)
+    text_output = model.Qformer.bert(ids, query_embeds=fusion_output.last_hidden_state[:, :32, :],
+                                     attention_mask=attention_mask, return_dict=True)
+    return F.normalize(model.text_proj(text_output.last_hidden_state[:, 32, :]), dim=-1)
+
+
+def run_case(name, cfg, check_keys=True):
+    t0 = time.time()
+    sd = synth.make_state_dict(cfg["vit"], cfg["vit_depth"], cfg["qf_layers"], seed=0)
+    model = ref_loader.build_reference_model(cfg["vit"], seed=0, vit_depth=cfg["vit_depth"],
+                                             qf_layers=cfg["qf_layers"])
+    ref_keys = {k for k in model.state_dict() if not k.startswith("Qformer.cls.") and "position_ids" not in k}
+    if check_keys:
+        assert ref_keys == set(sd), (sorted(ref_keys - set(sd))[:5], sorted(set(sd) - ref_keys)[:5])
+        for k, v in model.state_dict().items():
+            if k in sd:
+                assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys
+    images = synth.make_images(cfg["n_images"])
+    ids, mask = synth.make_token_ids(cfg["n_queries"])
+    ref_rows = torch.arange(cfg["n_queries"]) % cfg["n_images"]
+    with torch.no_grad():
+        feats, raws = model.extract_target_features(images)
+        ref_embeds = raws[ref_rows]
+        sim = ref_loader.call_inference(model, ref_embeds, feats, ids, mask)
+        fusion = reference_fusion_feats(model, ref_embeds, ids, mask)
+        # rerank: reference class shares every statement of the fusion pass; use the rerank model class
+        # only for tiny cases (it instantiates a second Q-Former)
+    out = dict(case=dict(cfg, name=name, seed=0), raw_rows=RAW_ROWS, raws_rows=raws[:, RAW_ROWS].clone(),
+               feats=feats.clone(), sim=sim.reshape(cfg["n_queries"], -1).clone(), fusion=fusion.clone(),
+               ref_rows=ref_rows, input_ids=ids, attention_mask=mask)
+    if name.startswith("tiny"):
+        out["rerank_p"] = run_rerank(cfg, sd, raws, ids, mask)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"[golden] {name}: feats {tuple(feats.shape)} sim {tuple(sim.shape)} in {time.time()-t0:.1f}s", flush=True)
+    return out
+
+
+def run_rerank(cfg, sd, raws, ids, mask):
+    """inference_rerank of the reference's rerank class with the same Q-Former / itm_head weights:
+    R = 2 references x T = 2 candidates."""
+    model = ref_loader.build_reference_model(cfg["vit"], seed=0, vit_depth=cfg["vit_depth"],
+                                             qf_layers=cfg["qf_layers"], kind="rerank")
+    model.load_state_dict(sd, strict=False)
+    R, T = 2, 2
+    ref = raws[[0, 1]]
+    tgt = raws[[2, 3, 1, 2]]
+    with torch.no_grad():
+        p = model.inference_rerank(ref, tgt, ref_loader.TokenBatch(ids[:R], mask[:R]))
+    return dict(R=R, T=T, ref_rows=torch.tensor([0, 1]), cand_rows=torch.tensor([2, 3, 1, 2]), p=p.clone())
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run_case(n, CASES[n])

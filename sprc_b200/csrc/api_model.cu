@@ -1,42 +1,157 @@
 // C-ABI: model-level entry points (handle, weights, gallery/query encoders, scan, rerank).
+// Each function documents, in include/sprc_b200.h, the reference function it stands in for.
+#include <new>
+
 #include "../../include/sprc_b200.h"
 #include "common.h"
+#include "model.h"
 #include "ops.h"
 
 using namespace sprc;
 
-#define SPRC_TODO(name) return set_error(-38, name ": not implemented yet")
+struct sprc_handle {
+  Model m;
+};
+
+namespace {
+// scan workspace for handle-less calls (scan-only tools); grows on demand, freed at process exit
+void* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+int ensure_global_ws(size_t bytes) {
+  if (bytes <= g_ws_bytes) return 0;
+  if (g_ws) cudaFree(g_ws);
+  g_ws = nullptr;
+  g_ws_bytes = 0;
+  if (cudaMalloc(&g_ws, bytes) != cudaSuccess) return set_error(-12, "cudaMalloc of %zu bytes failed", bytes);
+  g_ws_bytes = bytes;
+  return 0;
+}
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+}  // namespace
 
 extern "C" {
 
-int sprc_create(const sprc_config*, sprc_handle**) { SPRC_TODO("sprc_create"); }
-void sprc_destroy(sprc_handle*) {}
-int sprc_load_weights(sprc_handle*, const sprc_tensor_desc*, int, int*) { SPRC_TODO("sprc_load_weights"); }
-const char* sprc_missing_weight(sprc_handle*, int) { return nullptr; }
-int sprc_encode_gallery(sprc_handle*, const float*, int, float*, void*, float*, void*, void*) {
-  SPRC_TODO("sprc_encode_gallery");
+int sprc_create(const sprc_config* cfg, sprc_handle** out) {
+  if (!cfg || !out) return set_error(-22, "sprc_create: null argument");
+  *out = nullptr;
+  sprc_handle* h = new (std::nothrow) sprc_handle();
+  if (!h) return set_error(-12, "sprc_create: out of host memory");
+  int rc = h->m.init(cfg->vit_kind, cfg->vit_depth, cfg->qf_layers, cfg->max_images, cfg->max_queries,
+                     cfg->max_pairs, cfg->device);
+  if (rc != 0) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
 }
-int sprc_encode_query(sprc_handle*, const void*, int, const int32_t*, const int64_t*, const int64_t*, int, float*,
-                      void*, void*) {
-  SPRC_TODO("sprc_encode_query");
+
+void sprc_destroy(sprc_handle* h) { delete h; }
+
+int sprc_load_weights(sprc_handle* h, const sprc_tensor_desc* t, int n, int* n_missing) {
+  if (!h || (!t && n > 0)) return set_error(-22, "sprc_load_weights: null argument");
+  SPRC_CUDA(cudaSetDevice(h->m.device));
+  for (int i = 0; i < n; ++i) {
+    if (!t[i].name || !t[i].data) return set_error(-22, "sprc_load_weights: tensor %d has a null name or pointer", i);
+    int rc = h->m.load_tensor(t[i].name, t[i].dtype, t[i].ndim, t[i].shape, t[i].data);
+    if (rc < 0) return rc;
+  }
+  const int miss = h->m.count_missing();
+  if (n_missing) *n_missing = miss;
+  return 0;
 }
-int sprc_sim_topk(sprc_handle*, const void*, int, const void*, int64_t, int64_t, int, float*, int32_t*, float*,
-                  void*) {
-  SPRC_TODO("sprc_sim_topk");
+
+const char* sprc_missing_weight(sprc_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->m.missing_cache.size()) return nullptr;
+  return h->m.missing_cache[i].c_str();
 }
-int sprc_topk_merge(sprc_handle*, const float*, const int32_t*, int, int, int, float*, int32_t*, void*) {
-  SPRC_TODO("sprc_topk_merge");
+
+int sprc_encode_gallery(sprc_handle* h, const float* images, int B, float* feats_f32, void* feats_bf16,
+                        float* raws_f32, void* raws_bf16, void* stream) {
+  if (!h || !images) return set_error(-22, "sprc_encode_gallery: null argument");
+  if (h->m.count_missing() != 0)
+    return set_error(-61, "sprc_encode_gallery: %d weights missing (first: %s)", (int)h->m.missing_cache.size(),
+                     h->m.missing_cache[0].c_str());
+  return h->m.encode_gallery(images, B, feats_f32, static_cast<bf16*>(feats_bf16), raws_f32,
+                             static_cast<bf16*>(raws_bf16), S(stream));
 }
-int sprc_gather_scores(sprc_handle*, const void*, int, const void*, int64_t, const int32_t*, int, float*, void*) {
-  SPRC_TODO("sprc_gather_scores");
+
+int sprc_encode_query(sprc_handle* h, const void* ref_raws, int ref_dtype, const int32_t* ref_rows,
+                      const int64_t* input_ids, const int64_t* attention_mask, int Bq, float* fusion_f32,
+                      void* fusion_bf16, void* stream) {
+  if (!h || !ref_raws || !input_ids || !attention_mask) return set_error(-22, "sprc_encode_query: null argument");
+  if (h->m.count_missing() != 0)
+    return set_error(-61, "sprc_encode_query: %d weights missing (first: %s)", (int)h->m.missing_cache.size(),
+                     h->m.missing_cache[0].c_str());
+  return h->m.encode_query(ref_raws, ref_dtype, ref_rows, input_ids, attention_mask, Bq, fusion_f32,
+                           static_cast<bf16*>(fusion_bf16), S(stream));
 }
-int sprc_rerank(sprc_handle*, const void*, const int32_t*, const int32_t*, const int64_t*, const int64_t*, int, int,
-                float*, void*) {
-  SPRC_TODO("sprc_rerank");
+
+int sprc_sim_topk(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N, int64_t row_offset,
+                  int k, float* out_score, int32_t* out_idx, float* out_full, void* stream) {
+  if (!queries || !gallery) return set_error(-22, "sprc_sim_topk: null argument");
+  const bool want_topk = out_score || out_idx;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  if (want_topk) {
+    const size_t need = sim_topk_workspace_bytes(Q, N, k, out_full != nullptr);
+    if (h) {
+      SPRC_TRY(h->m.ensure_scan_ws(need));
+      ws = h->m.scan_ws;
+      ws_bytes = h->m.scan_ws_bytes;
+    } else {
+      SPRC_TRY(ensure_global_ws(need));
+      ws = g_ws;
+      ws_bytes = g_ws_bytes;
+    }
+  }
+  return sim_topk(static_cast<const bf16*>(queries), Q, static_cast<const bf16*>(gallery), N, row_offset, k,
+                  out_score, out_idx, out_full, ws, ws_bytes, S(stream));
 }
-int sprc_query_topk_host(sprc_handle*, const void*, const void*, int64_t, const int32_t*, const int64_t*,
-                         const int64_t*, int, int, float*, int32_t*, void*) {
-  SPRC_TODO("sprc_query_topk_host");
+
+int sprc_topk_merge(sprc_handle*, const float* cand_score, const int32_t* cand_idx, int P, int Q, int k,
+                    float* out_score, int32_t* out_idx, void* stream) {
+  if (!cand_score || !cand_idx) return set_error(-22, "sprc_topk_merge: null argument");
+  return topk_merge(cand_score, cand_idx, P, Q, k, out_score, out_idx, S(stream));
+}
+
+int sprc_gather_scores(sprc_handle*, const void* queries, int Q, const void* gallery, int64_t N,
+                       const int32_t* rows, int m, float* out, void* stream) {
+  if (!queries || !gallery || !rows || !out) return set_error(-22, "sprc_gather_scores: null argument");
+  return gather_scores(static_cast<const bf16*>(queries), Q, static_cast<const bf16*>(gallery), N, rows, m, out,
+                       S(stream));
+}
+
+int sprc_rerank(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
+                const int64_t* input_ids, const int64_t* attention_mask, int R, int T, float* p, void* stream) {
+  if (!h || !raws_bf16 || !ref_rows || !cand_rows || !input_ids || !attention_mask || !p)
+    return set_error(-22, "sprc_rerank: null argument");
+  for (const char* nm : {"itm_head.weight", "itm_head.bias"})
+    if (!h->m.slots[nm].loaded) return set_error(-61, "sprc_rerank: %s was never loaded", nm);
+  if (h->m.count_missing() != 0) return set_error(-61, "sprc_rerank: weights missing");
+  return h->m.rerank(static_cast<const bf16*>(raws_bf16), ref_rows, cand_rows, input_ids, attention_mask, R, T, p,
+                     S(stream));
+}
+
+int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
+                         const int32_t* ref_rows_host, const int64_t* ids_host, const int64_t* mask_host, int Bq,
+                         int k, float* out_score_host, int32_t* out_idx_host, void* stream) {
+  if (!h || !raws_bf16 || !gallery_bf16 || !ref_rows_host || !ids_host || !mask_host || !out_score_host ||
+      !out_idx_host)
+    return set_error(-22, "sprc_query_topk_host: null argument");
+  Model& m = h->m;
+  SPRC_REQUIRE(Bq > 0 && Bq <= m.max_queries, "sprc_query_topk_host: Bq=%d outside (0, %d]", Bq, m.max_queries);
+  SPRC_REQUIRE(k > 0 && k <= 256, "sprc_query_topk_host: k=%d outside [1, 256]", k);
+  cudaStream_t st = S(stream);
+  SPRC_CUDA(cudaMemcpyAsync(m.d_ids, ids_host, (size_t)Bq * 32 * 8, cudaMemcpyHostToDevice, st));
+  SPRC_CUDA(cudaMemcpyAsync(m.d_mask, mask_host, (size_t)Bq * 32 * 8, cudaMemcpyHostToDevice, st));
+  SPRC_CUDA(cudaMemcpyAsync(m.d_rows, ref_rows_host, (size_t)Bq * 4, cudaMemcpyHostToDevice, st));
+  SPRC_TRY(sprc_encode_query(h, raws_bf16, SPRC_BF16, m.d_rows, m.d_ids, m.d_mask, Bq, nullptr, m.d_fusion, stream));
+  SPRC_TRY(sprc_sim_topk(h, m.d_fusion, Bq, gallery_bf16, N, 0, k, m.d_topk_score, m.d_topk_idx, nullptr, stream));
+  SPRC_CUDA(cudaMemcpyAsync(out_score_host, m.d_topk_score, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
+  SPRC_CUDA(cudaMemcpyAsync(out_idx_host, m.d_topk_idx, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
+  SPRC_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 }  // extern "C"

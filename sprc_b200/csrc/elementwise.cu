@@ -164,7 +164,7 @@ int vit_assemble_tokens(const float* patch_out, const float* cls, const float* p
 // Q-Former embeddings (pre-LayerNorm rows), width fixed at 768 = 192 float4
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(192)
-qformer_embed_kernel(const float4* __restrict__ qe, int q_batch_rows, const int64_t* __restrict__ ids,
+qformer_embed_kernel(const float4* __restrict__ qe, int q_batch_rows, const int64_t* __restrict__ ids, int ids_div,
                      const float4* __restrict__ word, const float4* __restrict__ pos, int vocab, int S,
                      float4* __restrict__ out) {
   const int r = blockIdx.x;  // row over B*S
@@ -174,7 +174,7 @@ qformer_embed_kernel(const float4* __restrict__ qe, int q_batch_rows, const int6
   if (s < 32) {
     v = q_batch_rows == 0 ? __ldg(qe + (size_t)s * 192 + c) : qe[((size_t)b * q_batch_rows + s) * 192 + c];
   } else {
-    long long id = ids[(size_t)b * 32 + (s - 32)];
+    long long id = ids[(size_t)(b / ids_div) * 32 + (s - 32)];
     if (id < 0) id = 0;
     if (id >= vocab) id = vocab - 1;
     const float4 w = __ldg(word + (size_t)id * 192 + c);
@@ -184,11 +184,12 @@ qformer_embed_kernel(const float4* __restrict__ qe, int q_batch_rows, const int6
   out[(size_t)r * 192 + c] = v;
 }
 
-int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_t* ids, const float* word_emb,
-                       const float* pos_emb, int vocab, int B, float* out, cudaStream_t st) {
+int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_t* ids, int ids_div,
+                       const float* word_emb, const float* pos_emb, int vocab, int B, float* out, cudaStream_t st) {
+  if (ids_div < 1) ids_div = 1;
   if (B <= 0) return 0;
   const int S = ids ? 64 : 32;
-  qformer_embed_kernel<<<B * S, 192, 0, st>>>(reinterpret_cast<const float4*>(query_embeds), q_batch_rows, ids,
+  qformer_embed_kernel<<<B * S, 192, 0, st>>>(reinterpret_cast<const float4*>(query_embeds), q_batch_rows, ids, ids_div,
                                               reinterpret_cast<const float4*>(word_emb),
                                               reinterpret_cast<const float4*>(pos_emb), vocab, S,
                                               reinterpret_cast<float4*>(out));
@@ -197,16 +198,17 @@ int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_
   return 0;
 }
 
-__global__ void qformer_key_mask_kernel(const int64_t* __restrict__ am, int B, float* __restrict__ out) {
+__global__ void qformer_key_mask_kernel(const int64_t* __restrict__ am, int div, int B, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 64) return;
   const int b = i >> 6, j = i & 63;
-  out[i] = j < 32 ? 0.f : (1.0f - (float)am[b * 32 + (j - 32)]) * -10000.0f;
+  out[i] = j < 32 ? 0.f : (1.0f - (float)am[(size_t)(b / div) * 32 + (j - 32)]) * -10000.0f;
 }
 
-int qformer_key_mask(const int64_t* attention_mask, int B, float* out, cudaStream_t st) {
+int qformer_key_mask(const int64_t* attention_mask, int div, int B, float* out, cudaStream_t st) {
   if (B <= 0) return 0;
-  qformer_key_mask_kernel<<<(B * 64 + 255) / 256, 256, 0, st>>>(attention_mask, B, out);
+  if (div < 1) div = 1;
+  qformer_key_mask_kernel<<<(B * 64 + 255) / 256, 256, 0, st>>>(attention_mask, div, B, out);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

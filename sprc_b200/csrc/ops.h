@@ -26,11 +26,13 @@ int vit_assemble_tokens(const float* patch_out, const float* cls, const float* p
 // Q-Former embedding rows before LayerNorm (Qformer.py:98-110): rows [0,32) of each sample = query
 // embeds (broadcast [32,768] when q_batch_rows == 0, else sample b starts at row b*q_batch_rows),
 // rows [32,64) = word[ids] + pos[0..31].  ids == nullptr -> only the 32 query rows (S = 32).
-int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_t* ids, const float* word_emb,
-                       const float* pos_emb, int vocab, int B, float* out, cudaStream_t st);
+// Sample b reads token ids row b / ids_div (rerank repeats each caption T times, rerank.py:418-419).
+int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_t* ids, int ids_div,
+                       const float* word_emb, const float* pos_emb, int vocab, int B, float* out, cudaStream_t st);
 
 // additive self-attention mask (Qformer.py:807): out[b, j] = 0 for j < 32, (1 - mask[b, j-32]) * -10000 after
-int qformer_key_mask(const int64_t* attention_mask, int B, float* out, cudaStream_t st);
+// (sample b reads attention_mask row b / div)
+int qformer_key_mask(const int64_t* attention_mask, int div, int B, float* out, cudaStream_t st);
 
 int convert_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);
 int convert_f16_to_bf16(const void* in, bf16* out, size_t n, cudaStream_t st);
@@ -75,7 +77,7 @@ int attention(const AttnDesc& a, cudaStream_t st);
 int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t row_offset, int k,
              float* out_score, int32_t* out_idx, float* out_full, void* workspace, size_t workspace_bytes,
              cudaStream_t st);
-size_t sim_topk_workspace_bytes(int Q, int k);
+size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full);
 int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, int k, float* out_score,
                int32_t* out_idx, cudaStream_t st);
 int gather_scores(const bf16* queries, int Q, const bf16* gallery, int64_t N, const int32_t* rows, int m,

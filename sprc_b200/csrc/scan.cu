@@ -1,0 +1,481 @@
+// Similarity scan + top-k:
+//   sim[q, n] = max_{t<32} < query[q, :], gallery[n, t, :] >        blip2_qformer_cir_align_prompt.py:353-358
+//   ranking   = argsort(1 - sim)[:, :k]  (ties: lower gallery row)   validate_blip.py:44-46,253-255
+//
+// The reference expands the gallery Bq times and sorts all N scores per query.  Here one persistent
+// kernel streams the bf16 gallery [N*32, 256] from HBM exactly once per 128-query tile:
+//   warp 0      TMA producer: 64 gallery tokens (2 images) x 256 dims per stage, 3-stage ring
+//   warp 1      tcgen05.mma issuer: D[128 queries, 64 tokens] = Qtile[128,256] * G[64,256]^T, fp32 in TMEM
+//               (queries on TMEM lanes so that the max over an image's 32 tokens is a per-thread max
+//               over 32 accumulator columns - no shuffles)
+//   warps 2..5  epilogue: one thread per query; keeps that query's running top-k as a binary min-heap in
+//               shared memory (slot-major layout -> bank-conflict free for any mix of heap positions)
+// CTAs = query tiles x gallery splits; per-(split, query) heaps go to a scratch buffer and a second
+// small kernel merges them (the same kernel merges per-GPU candidates after the NCCL all-gather).
+// Bytes per gallery pass: N*32*256*2 (819.2 MB at N = 50k); the scan is HBM-bound for Q <= 128.
+#include <float.h>
+
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace sprc {
+
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                   uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank);
+
+static constexpr int SQ = 128;        // queries per CTA (UMMA M)
+static constexpr int ST = 64;         // gallery tokens per stage (UMMA N) = 2 images
+static constexpr int SSTAGES = 3;
+static constexpr int KCAP = 64;       // heap capacity (fused path handles k <= 64)
+static constexpr int SEG = 4096;      // segment width of the large-k path
+static constexpr int A_BYTES = SQ * 256 * 2;   // 64 KB
+static constexpr int B_BYTES = ST * 256 * 2;   // 32 KB
+static constexpr int HEAP_BYTES = KCAP * SQ * 8;  // 64 KB
+static constexpr int SCAN_SMEM = A_BYTES + SSTAGES * B_BYTES + HEAP_BYTES + 256 + 1024;
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 make_key(float score, uint32_t idx) {
+  uint32_t f = __float_as_uint(score);
+  f = (f & 0x80000000u) ? ~f : (f | 0x80000000u);  // monotone float -> uint
+  return (static_cast<u64>(f) << 32) | static_cast<u64>(0xFFFFFFFFu - idx);  // larger key = better
+}
+__device__ __forceinline__ void decode_key(u64 key, float& score, int32_t& idx) {
+  const uint32_t hi = static_cast<uint32_t>(key >> 32);
+  if (hi == 0) {  // never filled
+    score = -INFINITY;
+    idx = -1;
+    return;
+  }
+  const uint32_t f = (hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi;
+  score = __uint_as_float(f);
+  idx = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu));
+}
+
+struct ScanParams {
+  int Q;
+  long long N;
+  long long row_offset;
+  int k;
+  int qtiles, splits;
+  long long imgs_per_split;  // even
+  float* out_full;           // [Q, N] or null
+  u64* cand;                 // [splits][k][qtiles*128] or null
+};
+
+__global__ void __launch_bounds__(192, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                 const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + A_BYTES;
+  u64* heap = reinterpret_cast<u64*>(smem + A_BYTES + SSTAGES * B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + SSTAGES * B_BYTES + HEAP_BYTES);
+  uint64_t* full_bar = bars;                  // [SSTAGES]
+  uint64_t* empty_bar = bars + SSTAGES;       // [SSTAGES]
+  uint64_t* tfull_bar = bars + 2 * SSTAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint64_t* q_bar = tempty_bar + 2;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.qtiles;
+  const int sp = blockIdx.x / p.qtiles;
+  const long long n_begin = static_cast<long long>(sp) * p.imgs_per_split;
+  long long n_end = n_begin + p.imgs_per_split;
+  if (n_end > p.N) n_end = p.N;
+  const int stages_total = n_end > n_begin ? static_cast<int>((n_end - n_begin + 1) / 2) : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmG);
+    for (int s = 0; s < SSTAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    mbar_init(q_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // query tile: 4 K-blocks of [128 rows x 64 cols]
+      mbar_expect_tx(q_bar, A_BYTES);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tmQ, q_bar, sA + kb * (SQ * 128), kb * 64, qt * SQ, kEvictLast);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < stages_total; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], B_BYTES);
+        const long long row0 = (n_begin + 2LL * it) * 32;
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(&tmG, &full_bar[stage], sB + stage * B_BYTES + kb * (ST * 128), kb * 64,
+                      static_cast<int>(row0), p.qtiles > 1 ? kEvictNormal : kEvictFirst);
+        if (++stage == SSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(SQ, ST);
+    mbar_wait(q_bar, 0);
+    tc_fence_after();
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int it = 0; it < stages_total; ++it) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * ST);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * (SQ * 128)));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES + kb * (ST * 128)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[as]);
+      }
+      __syncwarp();
+      if (++stage == SSTAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per query =====================
+    const int qw = warp & 3;
+    const int ql = qw * 32 + lane;         // query row inside the tile = TMEM lane
+    const int q = qt * SQ + ql;
+    const bool q_ok = q < p.Q;
+    const int k = p.k;
+    u64* myheap = heap + ql;               // slot j at myheap[j * SQ]
+    for (int j = 0; j < k; ++j) myheap[j * SQ] = static_cast<u64>(j);  // distinct sub-minimal keys, valid min-heap
+    u64 root = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int it = 0; it < stages_total; ++it) {
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + static_cast<uint32_t>(as * ST);
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);  // accumulator is in registers: release TMEM early
+      float s0 = __uint_as_float(r0[0]), s1 = __uint_as_float(r1[0]);
+#pragma unroll
+      for (int j = 1; j < 32; ++j) {
+        s0 = fmaxf(s0, __uint_as_float(r0[j]));
+        s1 = fmaxf(s1, __uint_as_float(r1[j]));
+      }
+      const long long n0 = n_begin + 2LL * it;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long n = n0 + e;
+        const float s = e == 0 ? s0 : s1;
+        if (q_ok && n < n_end) {
+          if (p.out_full) p.out_full[static_cast<size_t>(q) * p.N + n] = s;
+          if (p.cand) {
+            const u64 key = make_key(s, static_cast<uint32_t>(p.row_offset + n));
+            if (key > root) {
+              // replace the heap minimum and sift down
+              int i = 0;
+              while (true) {
+                const int l = 2 * i + 1;
+                if (l >= k) break;
+                const u64 kl = myheap[l * SQ];
+                const u64 kr = (l + 1 < k) ? myheap[(l + 1) * SQ] : ~0ull;
+                const int c = kr < kl ? l + 1 : l;
+                const u64 kc = kr < kl ? kr : kl;
+                if (kc >= key) break;
+                myheap[i * SQ] = kc;
+                i = c;
+              }
+              myheap[i * SQ] = key;
+              root = myheap[0];
+            }
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (p.cand && q_ok) {
+      const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
+      for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = myheap[j * SQ];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bitonic helpers (descending order of u64 keys) on a shared-memory array of n = power of two
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_desc(u64* s, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const u64 a = s[lo], b = s[hi];
+        if ((a < b) == desc) {
+          s[lo] = b;
+          s[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// merge: for each query, P*k candidates -> top-k sorted.  Candidates are either packed keys laid out
+// [P][k][qpad] (from scan_topk_kernel / row_topk_kernel) or (score, idx) pairs [P][Q][k] (C ABI).
+__global__ void __launch_bounds__(1024)
+topk_merge_kernel(const u64* __restrict__ cand_keys, size_t qpad, const float* __restrict__ cand_score,
+                  const int32_t* __restrict__ cand_idx, int P, int Q, int k, int npow2, float* __restrict__ out_score,
+                  int32_t* __restrict__ out_idx) {
+  extern __shared__ u64 skeys[];
+  const int q = blockIdx.x;
+  const int total = P * k;
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    u64 key = 0;
+    if (i < total) {
+      const int pp = i / k, j = i % k;
+      if (cand_keys) {
+        key = cand_keys[(static_cast<size_t>(pp) * k + j) * qpad + q];
+      } else {
+        const size_t o = (static_cast<size_t>(pp) * Q + q) * k + j;
+        const int32_t idx = cand_idx[o];
+        key = idx < 0 ? 0 : make_key(cand_score[o], static_cast<uint32_t>(idx));
+      }
+    }
+    skeys[i] = key;
+  }
+  bitonic_sort_desc(skeys, npow2);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    float sc;
+    int32_t ix;
+    decode_key(j < npow2 ? skeys[j] : 0, sc, ix);
+    if (out_score) out_score[static_cast<size_t>(q) * k + j] = sc;
+    if (out_idx) out_idx[static_cast<size_t>(q) * k + j] = ix;
+  }
+}
+
+// large-k path: top-k of each 4096-wide segment of a full score row
+__global__ void __launch_bounds__(1024)
+row_topk_kernel(const float* __restrict__ full, long long N, long long row_offset, int k, size_t qpad,
+                u64* __restrict__ cand) {
+  __shared__ u64 skeys[SEG];
+  const int seg = blockIdx.x, q = blockIdx.y;
+  const long long n0 = static_cast<long long>(seg) * SEG;
+  for (int i = threadIdx.x; i < SEG; i += blockDim.x) {
+    const long long n = n0 + i;
+    skeys[i] = n < N ? make_key(full[static_cast<size_t>(q) * N + n], static_cast<uint32_t>(row_offset + n)) : 0;
+  }
+  bitonic_sort_desc(skeys, SEG);
+  for (int j = threadIdx.x; j < k; j += blockDim.x)
+    cand[(static_cast<size_t>(seg) * k + j) * qpad + q] = j < SEG ? skeys[j] : 0;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int32_t* ci, int P, int Q, int k,
+                        float* out_score, int32_t* out_idx, cudaStream_t st) {
+  const int np2 = next_pow2(P * k < 2 ? 2 : P * k);
+  const size_t smem = static_cast<size_t>(np2) * 8;
+  SPRC_REQUIRE(smem <= 200 * 1024, "topk_merge: %d candidates per query exceed the merge capacity", P * k);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SPRC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, P, Q, k, np2, out_score, out_idx);
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, int k, float* out_score,
+               int32_t* out_idx, cudaStream_t st) {
+  SPRC_REQUIRE(P > 0 && Q > 0 && k > 0, "topk_merge: empty problem");
+  return launch_merge(nullptr, 0, cand_score, cand_idx, P, Q, k, out_score, out_idx, st);
+}
+
+// workspace: candidate keys of the fused path, or [full matrix +] segment candidates of the large-k path
+static void scan_plan(int Q, long long N, int k, int& qtiles, int& splits, long long& ips) {
+  qtiles = (Q + SQ - 1) / SQ;
+  const int sms = device_sm_count();
+  splits = sms / qtiles;
+  if (splits < 1) splits = 1;
+  const long long max_splits = (N + 1) / 2;  // at least one stage (2 images) per split
+  if (splits > max_splits) splits = static_cast<int>(max_splits > 0 ? max_splits : 1);
+  // keep the merge within capacity (splits * k <= 16384)
+  while (static_cast<long long>(splits) * k > 16384 && splits > 1) --splits;
+  ips = (N + splits - 1) / splits;
+  if (ips & 1) ++ips;
+  if (ips < 2) ips = 2;
+  splits = static_cast<int>((N + ips - 1) / ips);
+  if (splits < 1) splits = 1;
+}
+
+size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full) {
+  const size_t qpad = static_cast<size_t>((Q + SQ - 1) / SQ) * SQ;
+  if (k <= KCAP) return static_cast<size_t>(device_sm_count() + 8) * KCAP * qpad * 8 + 256;
+  const size_t nseg = static_cast<size_t>((N + SEG - 1) / SEG);
+  size_t need = ((nseg * k * qpad * 8 + 255) & ~size_t(255)) + 256;
+  if (!caller_has_full) need += static_cast<size_t>(Q) * N * 4 + 256;
+  return need;
+}
+
+int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t row_offset, int k,
+             float* out_score, int32_t* out_idx, float* out_full, void* workspace, size_t workspace_bytes,
+             cudaStream_t st) {
+  SPRC_REQUIRE(Q > 0 && N > 0, "sim_topk: empty problem (Q=%d N=%lld)", Q, (long long)N);
+  SPRC_REQUIRE(N * 32 < (1LL << 31), "sim_topk: gallery shard of %lld images exceeds the 2^31-token TMA coordinate "
+               "range; shard it", (long long)N);
+  const bool want_topk = (out_score || out_idx);
+  SPRC_REQUIRE(!want_topk || (k > 0 && k <= 1024), "sim_topk: k=%d outside [1, 1024]", k);
+  SPRC_REQUIRE(want_topk || out_full, "sim_topk: no output requested");
+  const bool fused = want_topk && k <= KCAP;
+  int qtiles, splits;
+  long long ips;
+  scan_plan(Q, N, fused ? k : 1, qtiles, splits, ips);
+  const size_t qpad = static_cast<size_t>(qtiles) * SQ;
+
+  CUtensorMap tmQ, tmG;
+  SPRC_TRY(make_tmap_bf16(&tmQ, queries, 256, (uint64_t)Q, 1, 256, 0, 64, SQ, 1, 2));
+  SPRC_TRY(make_tmap_bf16(&tmG, gallery, 256, (uint64_t)N * 32, 1, 256, 0, 64, ST, 1, 2));
+
+  ScanParams p;
+  p.Q = Q;
+  p.N = N;
+  p.row_offset = row_offset;
+  p.k = fused ? k : 0;
+  p.qtiles = qtiles;
+  p.splits = splits;
+  p.imgs_per_split = ips;
+  p.out_full = out_full;
+  p.cand = nullptr;
+  u64* cand = static_cast<u64*>(workspace);
+  float* full = out_full;
+  if (fused) {
+    const size_t need = static_cast<size_t>(splits) * k * qpad * 8;
+    SPRC_REQUIRE(workspace && workspace_bytes >= need, "sim_topk: workspace too small (%zu < %zu)", workspace_bytes,
+                 need);
+    p.cand = cand;
+  } else if (want_topk) {
+    // large k: materialise the score matrix (in the caller's buffer if given), then segment top-k + merge
+    const int nseg = static_cast<int>((N + SEG - 1) / SEG);
+    const size_t need_c = static_cast<size_t>(nseg) * k * qpad * 8;
+    size_t need = need_c;
+    if (!full) need += static_cast<size_t>(Q) * N * 4 + 256;
+    SPRC_REQUIRE(workspace && workspace_bytes >= need, "sim_topk: workspace too small (%zu < %zu)", workspace_bytes,
+                 need);
+    if (!full) {
+      full = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((need_c + 255) & ~size_t(255)));
+      p.out_full = full;
+    }
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+    attr_set = true;
+  }
+  scan_topk_kernel<<<qtiles * splits, 192, SCAN_SMEM, st>>>(tmQ, tmG, p);
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  if (fused) return launch_merge(cand, qpad, nullptr, nullptr, splits, Q, k, out_score, out_idx, st);
+  if (want_topk) {
+    const int nseg = static_cast<int>((N + SEG - 1) / SEG);
+    SPRC_REQUIRE(static_cast<long long>(nseg) * k <= 16384 * 1, "sim_topk: N=%lld with k=%d exceeds the merge capacity",
+                 (long long)N, k);
+    dim3 grid(nseg, Q);
+    row_topk_kernel<<<grid, 1024, 0, st>>>(full, N, row_offset, k, qpad, cand);
+    count_launch();
+    SPRC_CUDA(cudaGetLastError());
+    return launch_merge(cand, qpad, nullptr, nullptr, nseg, Q, k, out_score, out_idx, st);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather_scores: sim of explicit (query, row) pairs, one warp per pair (lane = gallery token)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_scores_kernel(const bf16* __restrict__ queries, int Q, const bf16* __restrict__ gallery, long long N,
+                     const int32_t* __restrict__ rows, int m, float* __restrict__ out) {
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pair >= Q * m) return;
+  const int lane = threadIdx.x & 31;
+  const int q = pair / m;
+  const int32_t n = rows[pair];
+  if (n < 0 || n >= N) {
+    if (lane == 0) out[pair] = -INFINITY;
+    return;
+  }
+  const uint4* g = reinterpret_cast<const uint4*>(gallery + (static_cast<size_t>(n) * 32 + lane) * 256);
+  const uint4* qv = reinterpret_cast<const uint4*>(queries + static_cast<size_t>(q) * 256);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const uint4 a = g[i], b = __ldg(qv + i);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(b2[j]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = fmaxf(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if (lane == 0) out[pair] = acc;
+}
+
+int gather_scores(const bf16* queries, int Q, const bf16* gallery, int64_t N, const int32_t* rows, int m,
+                  float* out, cudaStream_t st) {
+  if (Q <= 0 || m <= 0) return 0;
+  const int pairs = Q * m;
+  gather_scores_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(queries, Q, gallery, N, rows, m, out);
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sprc
