@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Headline benchmark: composed queries/sec at gallery = 50k (BASELINE.json `metric`).
+
+One "step" = one batch of Bq composed queries (reference image row + 32-token caption) through the
+hot path: Q-Former fusion (two passes) -> similarity scan over the whole gallery -> top-50.
+Workload at N=1: BASELINE.json configs[1] model (ViT-L BLIP-2, full depth, synthetic weights) with the
+gallery enlarged to the 50k rows the metric is quoted on; the gallery index (bf16 features + bf16 raw
+embeds) is built by our own ViT/Q-Former from synthetic images before the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  (N > 1: launched by torch.distributed.run, one rank per GPU; gallery rows sharded, per-shard top-k
+   all-gathered over NCCL and merged; per-GPU query work is fixed => weak scaling)
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on
+both sides, max over ranks; inputs of consecutive steps differ and the gallery (819 MB) + weights exceed
+the 126 MB L2, so no explicit L2 flush is needed ("l2": "inputs_exceed_l2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "composed_queries_per_sec_gallery50k"
+UNIT = "queries/s"
+FLOP_PER_QUERY = {"clip_L": 27.50e9, "eva_clip_g": 29.32e9}   # SURVEY.md §8d (resident reference)
+FLOP_PER_IMAGE = {"clip_L": 166.2e9, "eva_clip_g": 533.5e9}   # SURVEY.md §8d (ViT + Q-Former gallery pass)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vit", default="clip_L", choices=["clip_L", "eva_clip_g"])
+    ap.add_argument("--gallery", type=int, default=50000)
+    ap.add_argument("--batch", type=int, default=256, help="composed queries per step per GPU")
+    ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--index-batch", type=int, default=128)
+    ap.add_argument("--index-images", type=int, default=0,
+                    help="encode only this many gallery rows per GPU with the ViT (0 = all); the remaining rows get "
+                         "synthetic unit-norm features (profiling runs; query-step kernels are unchanged)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="queries in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained",
+                                                                               d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.proc = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            sel = "GPU-" + uuid if not uuid.startswith("GPU-") else uuid
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", sel], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (torch fp32 restatement of the reference) on host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_query_sample(vit, n_queries, gallery_cpu_f32, sd, steps=1, warmup=0):
+    """Times fusion (two Q-Former passes) + similarity + full argsort ranking for `n_queries` composed
+    queries against the whole gallery, as blip2_qformer_cir_align_prompt.py:312-361 and
+    validate_blip.py:253-254 do; reference raw embeds are resident (synthetic LayerNorm-like rows)."""
+    from oracle import restatement as R
+    from oracle import synth
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    Dv = synth.VIT_DIMS[vit][0]
+    g = torch.Generator().manual_seed(77)
+    times = []
+    for it in range(warmup + steps):
+        ref = torch.randn(n_queries, 257, Dv, generator=g)
+        ids, mask = synth.make_token_ids(n_queries, seed=1000 + it)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            sim = R.inference(sd, ref, gallery_cpu_f32, ids, mask)
+            order = torch.argsort(1 - sim, dim=-1)  # noqa: F841  (validate_blip.py:253-254)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return n_queries * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+
+    cores = os.cpu_count() or 1
+    sd = synth.make_state_dict(args.vit, None, 12, seed=0)
+    gal = synth.make_gallery_features(args.gallery, seed=99)
+    nq = args.cpu_sample
+    qps, sec = cpu_query_sample(args.vit, nq, gal, sd, steps=args.steps, warmup=args.warmup)
+    sample = (f"{nq} composed queries/step (reference FashionIQ batch size), resident reference embeds, fp32 torch "
+              f"restatement of the reference (oracle port; the Python reference cannot travel to this box), "
+              f"gallery {args.gallery} unit-norm synthetic features, similarity as ONE matmul (the reference's "
+              f"broadcast matmul is slower), full argsort ranking, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.vit}_blip2_cirr_shape_gallery{args.gallery}", "gallery": args.gallery,
+                       "queries_per_step": nq, "k": args.k},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from oracle import synth
+    from sprc_b200 import _lib as L
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    pk = peaks()
+
+    Bq, k, N = args.batch, args.k, args.gallery
+    model = Blip2QformerCirAlignPrompt(vit_model=args.vit, device=dev, max_images=args.index_batch,
+                                       max_queries=Bq)
+    sd = synth.make_state_dict(args.vit, None, 12, seed=0)
+    assert model.load_state_dict(sd, strict=False).missing_keys == []
+    Dv = model.vit_width
+
+    # ---- gallery index shard: rows [lo, hi) of the N-row gallery, encoded by our ViT + Q-Former ----
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    n_local = hi - lo
+    feats = torch.empty(n_local, 32, 256, device=dev, dtype=torch.bfloat16)
+    raws = torch.empty(n_local, 257, Dv, device=dev, dtype=torch.bfloat16)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    h = model._h
+    st = lambda: L.c_void_p(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    IB = args.index_batch
+    img = torch.empty(IB, 3, 224, 224, device=dev)
+    # warm one batch, then time the whole index build
+    img.normal_(generator=gen).clamp_(-2.2, 2.2)
+    L.check(lib.sprc_encode_gallery(h, L.ptr(img), min(IB, n_local), None, L.ptr(feats), None, L.ptr(raws), st()))
+    torch.cuda.synchronize()
+    launches_index0 = lib.sprc_launch_count()
+    n_index = n_local if args.index_images <= 0 else min(n_local, args.index_images)
+    if n_index < n_local:
+        feats[n_index:] = synth.make_gallery_features(n_local - n_index, seed=99 + rank, device=dev,
+                                                      dtype=torch.bfloat16)
+        raws[n_index:].zero_()
+    e0.record()
+    for s in range(0, n_index, IB):
+        b = min(IB, n_index - s)
+        img.normal_(generator=gen).clamp_(-2.2, 2.2)
+        L.check(lib.sprc_encode_gallery(h, L.ptr(img), b, None, L.ptr(feats[s:]), None, L.ptr(raws[s:]), st()))
+    e1.record()
+    torch.cuda.synchronize()
+    index_s = e0.elapsed_time(e1) / 1e3
+    index_ips = n_index / index_s
+    launches_index = int(lib.sprc_launch_count() - launches_index0)
+
+    # ---- query pool (host pinned + device copies); reference rows come from the local shard ----
+    pool = max(4, min(16, args.steps + args.warmup))
+    ids_h = torch.empty(pool, Bq, 32, dtype=torch.int64).pin_memory()
+    mask_h = torch.empty(pool, Bq, 32, dtype=torch.int64).pin_memory()
+    rows_h = torch.empty(pool, Bq, dtype=torch.int32).pin_memory()
+    for p_ in range(pool):
+        i, m = synth.make_token_ids(Bq, seed=4321 + 100 * rank + p_)
+        ids_h[p_], mask_h[p_] = i, m
+        rows_h[p_] = torch.randint(0, n_index, (Bq,), generator=torch.Generator().manual_seed(7 + 100 * rank + p_))
+    ids_d, mask_d, rows_d = ids_h.to(dev), mask_h.to(dev), rows_h.to(dev)
+    out_sc_h = torch.empty(Bq, k, dtype=torch.float32).pin_memory()
+    out_ix_h = torch.empty(Bq, k, dtype=torch.int32).pin_memory()
+
+    fusion = torch.empty(Bq, 256, device=dev, dtype=torch.bfloat16)
+    fusion_all = torch.empty(world * Bq, 256, device=dev, dtype=torch.bfloat16)
+    sc = torch.empty(world * Bq, k, device=dev)
+    ix = torch.empty(world * Bq, k, device=dev, dtype=torch.int32)
+    cand_sc = torch.empty(world, world * Bq, k, device=dev)
+    cand_ix = torch.empty(world, world * Bq, k, device=dev, dtype=torch.int32)
+    msc = torch.empty(world * Bq, k, device=dev)
+    mix = torch.empty(world * Bq, k, device=dev, dtype=torch.int32)
+
+    def step_device(i):
+        p_ = i % pool
+        L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]), L.ptr(mask_d[p_]),
+                                      Bq, None, L.ptr(fusion), st()))
+        if world == 1:
+            L.check(lib.sprc_sim_topk(h, L.ptr(fusion), Bq, L.ptr(feats), n_local, 0, k, L.ptr(sc), L.ptr(ix), None,
+                                      st()))
+        else:
+            dist.all_gather_into_tensor(fusion_all, fusion)
+            L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all), world * Bq, L.ptr(feats), n_local, lo, k, L.ptr(sc),
+                                      L.ptr(ix), None, st()))
+            dist.all_gather_into_tensor(cand_sc, sc)
+            dist.all_gather_into_tensor(cand_ix, ix)
+            L.check(lib.sprc_topk_merge(h, L.ptr(cand_sc), L.ptr(cand_ix), world, world * Bq, k, L.ptr(msc),
+                                        L.ptr(mix), st()))
+
+    def step_host(i):
+        p_ = i % pool
+        if world == 1:
+            L.check(lib.sprc_query_topk_host(h, L.ptr(raws), L.ptr(feats), n_local, L.ptr(rows_h[p_]),
+                                             L.ptr(ids_h[p_]), L.ptr(mask_h[p_]), Bq, k, L.ptr(out_sc_h),
+                                             L.ptr(out_ix_h), st()))
+        else:
+            ids_d[p_].copy_(ids_h[p_], non_blocking=True)
+            mask_d[p_].copy_(mask_h[p_], non_blocking=True)
+            rows_d[p_].copy_(rows_h[p_], non_blocking=True)
+            step_device(i)
+            out_sc_h.copy_(msc[rank * Bq:(rank + 1) * Bq], non_blocking=True)
+            out_ix_h.copy_(mix[rank * Bq:(rank + 1) * Bq], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        t_wall0 = time.time()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(warmup + i)
+        b.record()
+        barrier()
+        t_wall1 = time.time()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, t_wall0, t_wall1
+
+    K, W = args.steps, max(args.warmup, 3)
+    clocks = ClockSampler(local)
+    time.sleep(0.25)
+    l0 = lib.sprc_launch_count()
+    ms, tw0, tw1 = timed(step_device, K, W)
+    launches = (lib.sprc_launch_count() - l0) * K // (K + W)
+    clk = clocks.window(tw0, tw1)
+    value = world * Bq * K / (ms / 1e3)
+
+    ms_e2e, _, _ = timed(step_host, K, W)
+    e2e_value = world * Bq * K / (ms_e2e / 1e3)
+    clocks.stop()
+
+    # ---- roofline: a second pass of the same K steps with per-launch CUDA events (library profiler) ----
+    import ctypes
+
+    prof = (ctypes.c_double * 20)()
+    barrier()
+    lib.sprc_profile(1)
+    for i in range(K):
+        step_device(W + i)
+    torch.cuda.synchronize()
+    L.check(lib.sprc_profile_read(prof, 5))
+    lib.sprc_profile(0)
+    cat = lambda c: dict(ms=prof[c * 4], flops=prof[c * 4 + 1], bytes=prof[c * 4 + 2], n=prof[c * 4 + 3])  # noqa: E731
+    gemm, attn, lnorm, scan, merge = (cat(c) for c in range(5))
+    prof_total = sum(x["ms"] for x in (gemm, attn, lnorm, scan, merge))
+    gemm_tf = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
+    scan_gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9 if scan["ms"] > 0 else 0.0
+    scan_tf = scan["flops"] / (scan["ms"] / 1e3) / 1e12 if scan["ms"] > 0 else 0.0
+    roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tf,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"], "traffic": None,
+                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": gemm["n"] / K, "avg_launch_us": gemm["ms"] * 1e3 / max(gemm["n"], 1),
+                "share_of_step": gemm["ms"] / prof_total if prof_total else None,
+                "how": "algorithmic 2*M*N*K per launch / CUDA-event time per launch, second pass of the same steps"}
+    roofline_scan = {"kernel": "scan_topk_kernel", "bound": "hbm" if world * Bq <= 128 else "tensor",
+                     "achieved_gbs": scan_gbs, "peak_gbs": pk["hbm"], "frac_hbm": scan_gbs / pk["hbm"],
+                     "achieved_tflops": scan_tf, "frac_tensor": scan_tf / pk["tf_burst"],
+                     "avg_launch_us": scan["ms"] * 1e3 / max(scan["n"], 1),
+                     "share_of_step": scan["ms"] / prof_total if prof_total else None,
+                     "note": "gallery bytes N*32*256*2 per launch; queries/launch = %d" % (world * Bq)}
+    breakdown = {"gemm_ms": gemm["ms"] / K, "attention_ms": attn["ms"] / K, "layernorm_ms": lnorm["ms"] / K,
+                 "scan_ms": scan["ms"] / K, "merge_ms": merge["ms"] / K}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        gal_cpu = feats.float().cpu()
+        qps, sec = cpu_query_sample(args.vit, args.cpu_sample, gal_cpu, sd, steps=1, warmup=0)
+        cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} composed queries (one reference-sized batch) vs the same {N}-row gallery, "
+                         f"fp32 torch restatement of the reference on {cores} host threads, {sec:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.vit}_blip2_cirr_shape_gallery{N}", "gallery": N,
+                       "queries_per_step_per_gpu": Bq, "k": k, "gallery_rows_per_gpu": n_local,
+                       "l2": "inputs_exceed_l2 (gallery %.0f MB + weights; query batches rotate)" % (
+                           n_local * 32 * 256 * 2 / 1e6),
+                       "parallelism": "gallery rows sharded x%d, queries data-parallel" % world,
+                       "weights": "synthetic seed 0, full depth (oracle/synth.py)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * Bq * (32 * 8 * 2 + 4),
+                    "d2h_bytes_per_step": world * Bq * k * 8, "ms_per_step": ms_e2e / K,
+                    "api": "sprc_query_topk_host (pinned host ids/mask/ref rows -> top-k on host)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_scan": roofline_scan, "step_breakdown_ms": breakdown,
+            "frac_of_qformer_gemm_roofline": value / world * FLOP_PER_QUERY[args.vit] / (pk["tf_sust"] * 1e12),
+            "index_build": {"images_per_s_per_gpu": index_ips, "seconds": index_s,
+                            "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (pk["tf_sust"] * 1e12),
+                            "images_encoded_per_gpu": n_index, "launches": launches_index},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,13 @@ int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gall
 /* Number of kernels this library has launched on behalf of the calling process (bench `gpu_launches`). */
 int64_t sprc_launch_count(void);
 
+/* Optional per-launch timing with CUDA events on the launching stream, by kernel category
+ * (0 gemm, 1 attention, 2 layernorm, 3 scan, 4 merge).  sprc_profile(1) clears and enables,
+ * sprc_profile_read fills out[cat*4 + {0,1,2,3}] = {ms, algorithmic flops, algorithmic bytes, launches}. */
+#define SPRC_PROF_NCAT 5
+int sprc_profile(int enable);
+int sprc_profile_read(double* out, int ncat);
+
 /* ---- single-op entry points (tests and micro-benchmarks) ------------------------------------- */
 /* C = act(A[M,K] W[N,K]^T + bias) (+ residual); impl 0 = tcgen05 product kernel, 1 = CUDA-core checker. */
 int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,

@@ -11,6 +11,14 @@ extern "C" {
 int sprc_abi_version(void) { return SPRC_ABI_VERSION; }
 const char* sprc_last_error(void) { return last_error(); }
 int64_t sprc_launch_count(void) { return launch_count(); }
+int sprc_profile(int enable) {
+  prof_set(enable != 0);
+  return 0;
+}
+int sprc_profile_read(double* out, int ncat) {
+  if (!out || ncat <= 0) return set_error(-22, "sprc_profile_read: bad arguments");
+  return prof_read(out, ncat);
+}
 
 int sprc_op_gemm(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int grp_rows, int grp_stride,
                  const float* bias, const float* residual, float* out_f32, void* out_bf16, int ldc, int act,

@@ -210,7 +210,10 @@ static int launch_attention(const AttnDesc& a, cudaStream_t st) {
     configured = smem;
   }
   dim3 grid(a.H, a.B);
+  prof_begin(st);
   attention_kernel<DHP><<<grid, ATT_WARPS * 32, smem, st>>>(a);
+  prof_end(PROF_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * a.dh,
+           2.0 * a.B * a.H * a.dh * (2.0 * a.Lq + 2.0 * a.Lk), st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

@@ -82,12 +82,14 @@ int layernorm(const float* x, int rows, int width, const float* gamma, const flo
   if (rows <= 0) return 0;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
+  prof_begin(st);
   if (width <= 32 * 4 * 6)
     layernorm_kernel<6><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32,
                                                    out_bf16);
   else
     layernorm_kernel<12><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride,
                                                     out_f32, out_bf16);
+  prof_end(PROF_ELEMWISE, 0.0, (double)rows * width * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)), st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

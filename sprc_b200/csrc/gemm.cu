@@ -302,7 +302,11 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  prof_begin(st);
   gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, p);
+  prof_end(PROF_GEMM, 2.0 * d.M * (double)d.N * d.K,
+           2.0 * ((double)d.M * d.K + (double)d.N * d.K) + (double)d.M * d.N * (d.out_f32 ? 4.0 : 2.0), st);
+  count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,6 +7,14 @@ namespace sprc {
 int64_t launch_count();
 void count_launch(int n = 1);
 
+// per-launch CUDA-event timing by category (bench.py roofline; off by default)
+enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ELEMWISE = 2, PROF_SCAN = 3, PROF_MERGE = 4, PROF_NCAT = 5 };
+bool prof_enabled();
+void prof_begin(cudaStream_t st);
+void prof_end(int cat, double flops, double bytes, cudaStream_t st);
+void prof_set(bool on);
+int prof_read(double* out, int ncat);
+
 // ---- elementwise.cu --------------------------------------------------------------------------
 // Row-wise LayerNorm over `width` (fp32 statistics, two-pass like ATen): eva_vit.py:175-176
 // (eps 1e-6), clip_vit.py:100-107 (eps 1e-5), blip2.py:193-199 ln_vision (eps 1e-5),

@@ -3,6 +3,9 @@
 #include <stdio.h>
 
 #include "common.h"
+#include "ops.h"
+
+#include <vector>
 
 namespace sprc {
 
@@ -28,6 +31,74 @@ int device_sm_count() {
     sms[dev] = n;
   }
   return sms[dev];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// optional per-launch timing (CUDA events on the launching stream), by kernel category
+// ------------------------------------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cat;
+  double flops, bytes;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_free_events;
+static cudaEvent_t g_pending = nullptr;
+
+static cudaEvent_t get_event() {
+  if (!g_free_events.empty()) {
+    cudaEvent_t e = g_free_events.back();
+    g_free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_pending = get_event();
+  cudaEventRecord(g_pending, st);
+}
+void prof_end(int cat, double flops, double bytes, cudaStream_t st) {
+  if (!g_prof_on || !g_pending) return;
+  ProfRec r;
+  r.a = g_pending;
+  r.b = get_event();
+  r.cat = cat;
+  r.flops = flops;
+  r.bytes = bytes;
+  cudaEventRecord(r.b, st);
+  g_recs.push_back(r);
+  g_pending = nullptr;
+}
+void prof_set(bool on) {
+  g_prof_on = on;
+  for (auto& r : g_recs) {
+    g_free_events.push_back(r.a);
+    g_free_events.push_back(r.b);
+  }
+  g_recs.clear();
+}
+// out[cat*4 + {0,1,2,3}] = {total ms, flops, bytes, launches}
+int prof_read(double* out, int ncat) {
+  for (int i = 0; i < ncat * 4; ++i) out[i] = 0.0;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return set_error(-5, "profile: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.cat >= 0 && r.cat < ncat) {
+      out[r.cat * 4 + 0] += ms;
+      out[r.cat * 4 + 1] += r.flops;
+      out[r.cat * 4 + 2] += r.bytes;
+      out[r.cat * 4 + 3] += 1.0;
+    }
+  }
+  return 0;
 }
 
 }  // namespace sprc

@@ -323,7 +323,9 @@ static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int
     SPRC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
   }
+  prof_begin(st);
   topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, P, Q, k, np2, out_score, out_idx);
+  prof_end(PROF_MERGE, 0.0, (double)P * k * Q * 8, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;
@@ -416,7 +418,9 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
     SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     attr_set = true;
   }
+  prof_begin(st);
   scan_topk_kernel<<<qtiles * splits, 192, SCAN_SMEM, st>>>(tmQ, tmG, p);
+  prof_end(PROF_SCAN, 2.0 * Q * (double)N * 32 * 256, (double)N * 32 * 256 * 2 + (double)Q * 512, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   if (fused) return launch_merge(cand, qpad, nullptr, nullptr, splits, Q, k, out_score, out_idx, st);
