@@ -214,10 +214,7 @@ def load_caption_processor():
     """The reference's BlipCaptionProcessor (processors/blip_processors.py:28-68)."""
     _install_shims()
     _mod("lavis.processors.randaugment", RandomAugment=object)
-    try:
-        bp = importlib.import_module("lavis.processors.blip_processors")
-    except Exception:
-        # torchvision-dependent image processors live in the same file; fall back to exec'ing only
-        # the caption class if the module cannot be imported as a whole
-        raise
+    base = importlib.import_module("lavis.processors.base_processor")
+    sys.modules["lavis.processors"].BaseProcessor = base.BaseProcessor  # registry.py:124 imports it from here
+    bp = importlib.import_module("lavis.processors.blip_processors")
     return bp.BlipCaptionProcessor

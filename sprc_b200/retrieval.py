@@ -1,0 +1,301 @@
+"""Host-side retrieval drivers: the reference's eval loops (src/utils.py:46-77, src/validate_blip.py:24-57,
+149-207,232-285,359-410, src/cirr_test_submission.py:61-132) re-expressed over integer gallery rows and the
+fused CUDA scan/top-k, with optional row-sharding of the gallery over ranks.
+
+What changes relative to the reference (results are identical; see tests/test_dropin_gpu.py):
+  * the gallery index keeps bf16 features [N,32,256] and bf16 raw embeds [N,257,Dv] (half of the
+    reference's fp32 residency);
+  * queries are ranked with top-(k+1) + the 6 subset scores instead of a full argsort of N scores and
+    O(Q*N) string comparisons (validate_blip.py:253-271); labels are integer row ids;
+  * with world_size > 1 each rank indexes and scans rows [lo, hi); per-shard top-k candidates are
+    exchanged with ONE all-gather (scores+ids) and merged; query vectors are combined with one all-reduce.
+
+`backend` is the CUDA model (sprc_b200.model.Blip2QformerCirAlignPrompt).  Tests may inject a CPU
+checker with the same five methods; the product never does.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row shard of rank `rank`: [rank*n//world, (rank+1)*n//world)."""
+    return rank * n // world, (rank + 1) * n // world
+
+
+def owner_of(row: torch.Tensor, n: int, world: int) -> torch.Tensor:
+    """Rank that owns global gallery row(s) `row` under `shard_range`."""
+    # smallest r with (r+1)*n//world > row
+    his = torch.tensor([(r + 1) * n // world for r in range(world)], dtype=torch.int64)
+    return torch.bucketize(row.to(torch.int64), his, right=True).clamp_(0, world - 1)
+
+
+@dataclass
+class GalleryIndex:
+    """Row shard [lo, hi) of an N-row gallery.  `names` always lists ALL N rows (names are tiny)."""
+    feats: torch.Tensor               # bf16 [hi-lo, 32, 256]
+    raws: Optional[torch.Tensor]      # bf16 [hi-lo, 257, Dv] (None if raw embeds were not kept)
+    names: List[str]
+    lo: int = 0
+    hi: int = 0
+    n_total: int = 0
+    name_to_row: Dict[str, int] = field(default_factory=dict)
+
+    def __post_init__(self):
+        if not self.n_total:
+            self.n_total = len(self.names)
+        if not self.hi:
+            self.hi = self.lo + self.feats.shape[0]
+        if not self.name_to_row:
+            self.name_to_row = {n: i for i, n in enumerate(self.names)}
+
+    def rows_of(self, names: Sequence[str]) -> torch.Tensor:
+        return torch.tensor([self.name_to_row[n] for n in names], dtype=torch.int64)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# indexing  (utils.py:46-77)
+# ---------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, collate_fn=None,
+                keep_raws: bool = True, progress: bool = False) -> GalleryIndex:
+    """Encode this rank's row shard of `dataset` ('classic' mode: items are (name, image))."""
+    from torch.utils.data import DataLoader, Subset
+
+    dist, rank, world = _dist()
+    n = len(dataset)
+    lo, hi = shard_range(n, rank, world)
+    sub = Subset(dataset, range(lo, hi)) if world > 1 else dataset
+    loader = DataLoader(dataset=sub, batch_size=batch_size, num_workers=num_workers, pin_memory=True,
+                        collate_fn=collate_fn)
+    feats, raws, names = [], [], []
+    it = loader
+    if progress:
+        from tqdm import tqdm
+
+        it = tqdm(loader)
+    for batch_names, images in it:
+        o = backend.encode_gallery(images.to(backend.device, non_blocking=True), want_f32=False, want_bf16=True,
+                                   want_raws_f32=False, want_raws_bf16=keep_raws)
+        feats.append(o["feats_bf16"])
+        if keep_raws:
+            raws.append(o["raws_bf16"])
+        names.extend(batch_names)
+    f = torch.cat(feats) if feats else torch.empty(0, 32, 256, dtype=torch.bfloat16, device=backend.device)
+    r = (torch.cat(raws) if raws else None) if keep_raws else None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, names)
+        all_names = [x for part in gathered for x in part]
+    else:
+        all_names = names
+    # the reference drops unreadable images silently (data_utils.py:191-192 + collate_fn); keep that:
+    # rows are numbered by position among the images that were actually encoded
+    if world > 1:
+        counts = [len(p) for p in gathered]
+        lo = sum(counts[:rank])
+    return GalleryIndex(feats=f.contiguous(), raws=None if r is None else r.contiguous(), names=all_names, lo=lo,
+                        hi=lo + f.shape[0], n_total=len(all_names))
+
+
+# ---------------------------------------------------------------------------------------------------
+# query -> top-k (+ subset scores)
+# ---------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: torch.Tensor,
+               attention_mask: torch.Tensor, k: int, subset_rows: Optional[torch.Tensor] = None):
+    """ref_rows: global gallery rows of the reference images [Q]; ids/mask [Q,32];
+    subset_rows (optional) global rows [Q,m] (-1 = skip).
+    Returns (scores [Q,k] fp32, rows [Q,k] int32 global, subset_scores [Q,m] or None), identical on all ranks."""
+    dist, rank, world = _dist()
+    dev = backend.device
+    Q = ref_rows.shape[0]
+    ref_rows = ref_rows.to(torch.int64)
+    if world == 1:
+        fusion = backend.encode_query(index.raws, input_ids, attention_mask, ref_rows=(ref_rows - index.lo))
+    else:
+        # owner-computes: the rank holding the reference row's raw embeds runs the Q-Former fusion
+        mine = (ref_rows >= index.lo) & (ref_rows < index.hi)
+        fusion32 = torch.zeros(Q, 256, dtype=torch.float32, device=dev)
+        if bool(mine.any()):
+            sel = mine.nonzero().flatten()
+            f = backend.encode_query(index.raws, input_ids[sel], attention_mask[sel],
+                                     ref_rows=(ref_rows[sel] - index.lo))
+            fusion32[sel.to(dev)] = f.float()
+        dist.all_reduce(fusion32)  # exactly one rank contributes each row: x + 0 + ... is exact
+        fusion = fusion32.to(torch.bfloat16)
+    sc, ix, _ = backend.sim_topk(fusion, index.feats, k=k, row_offset=index.lo)
+    sub = None
+    if subset_rows is not None:
+        local = subset_rows.to(torch.int64) - index.lo
+        local = torch.where((subset_rows >= index.lo) & (subset_rows < index.hi), local, torch.full_like(local, -1))
+        sub = backend.gather_scores(fusion, index.feats, local.to(torch.int32))
+    if world > 1:
+        cs = torch.empty(world, Q, k, dtype=torch.float32, device=dev)
+        ci = torch.empty(world, Q, k, dtype=torch.int32, device=dev)
+        # ONE exchange of candidates: scores and ids travel in one buffer (int32 ids bit-cast to fp32 lanes)
+        packed = torch.cat([sc.contiguous().view(torch.int32), ix.contiguous()], dim=1)
+        allp = torch.empty(world * Q, 2 * k, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, packed)  # rank-major concatenation along dim 0
+        allp = allp.view(world, Q, 2 * k)
+        cs.copy_(allp[:, :, :k].contiguous().view(torch.float32))
+        ci.copy_(allp[:, :, k:])
+        sc, ix = backend.topk_merge(cs, ci)
+        if sub is not None:
+            dist.all_reduce(sub, op=dist.ReduceOp.MAX)  # non-owners hold -inf
+    return sc, ix, sub
+
+
+def _tokenize(backend, captions):
+    tok = backend.tokenizer(list(captions), padding="max_length", truncation=True, max_length=32, return_tensors="pt")
+    return tok.input_ids, tok.attention_mask
+
+
+# ---------------------------------------------------------------------------------------------------
+# metrics on integer rows  (validate_blip.py:44-55, 253-285)
+# ---------------------------------------------------------------------------------------------------
+def cirr_recalls_from_topk(top_rows: torch.Tensor, ref_rows: torch.Tensor, tgt_rows: torch.Tensor,
+                           group_rows: torch.Tensor, group_scores: torch.Tensor):
+    """top_rows [Q,51] ranking; group_rows/scores [Q,6].  Returns the 7 recalls in percent, as
+    compute_cirr_val_metrics does: the reference row is deleted from the ranking first (:258-261)."""
+    top_rows = top_rows.cpu().to(torch.int64)
+    ref_rows, tgt_rows = ref_rows.cpu().to(torch.int64), tgt_rows.cpu().to(torch.int64)
+    Q, K1 = top_rows.shape
+    if bool((ref_rows == tgt_rows).any()):
+        raise AssertionError("a query's target equals its reference: no positive left after reference removal")
+    keep = top_rows != ref_rows[:, None]
+    # stable compaction of each row to its first K1-1 kept entries
+    pos = torch.cumsum(keep.to(torch.int64), dim=1) - 1
+    ranked = torch.full((Q, K1), -1, dtype=torch.int64)
+    qi = torch.arange(Q)[:, None].expand(Q, K1)
+    ranked[qi[keep], pos[keep]] = top_rows[keep]
+    ranked = ranked[:, : K1 - 1]
+    labels = ranked == tgt_rows[:, None]
+    rec = lambda kk: (labels[:, :kk].any(dim=1).sum().item() / Q) * 100.0  # noqa: E731
+    # subset ranking: group members without the reference, by (score desc, row asc) like the global order
+    g_rows = group_rows.cpu().to(torch.int64)
+    g_sc = group_scores.cpu().float().clone()
+    g_sc[g_rows == ref_rows[:, None]] = float("-inf")
+    g_sc[g_rows < 0] = float("-inf")
+    order = torch.argsort(g_rows, dim=1, stable=True)
+    g_rows_s, g_sc_s = torch.gather(g_rows, 1, order), torch.gather(g_sc, 1, order)
+    order2 = torch.argsort(-g_sc_s, dim=1, stable=True)
+    g_ranked = torch.gather(g_rows_s, 1, order2)
+    g_valid = torch.gather(g_sc_s, 1, order2) > float("-inf")
+    g_labels = (g_ranked == tgt_rows[:, None]) & g_valid
+    if not bool((g_labels.sum(dim=1) == 1).all()):
+        raise AssertionError("each query needs exactly one positive among its group members "
+                             "(validate_blip.py:274)")
+    grec = lambda kk: (g_labels[:, :kk].any(dim=1).sum().item() / Q) * 100.0  # noqa: E731
+    return grec(1), grec(2), grec(3), rec(1), rec(5), rec(10), rec(50)
+
+
+def fiq_recalls_from_topk(top_rows: torch.Tensor, tgt_rows: torch.Tensor):
+    top_rows = top_rows.cpu().to(torch.int64)
+    labels = top_rows == tgt_rows.cpu().to(torch.int64)[:, None]
+    Q = top_rows.shape[0]
+    return (labels[:, :10].any(dim=1).sum().item() / Q) * 100.0, (labels[:, :50].any(dim=1).sum().item() / Q) * 100.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# drop-in entry points (same signatures as the reference's)
+# ---------------------------------------------------------------------------------------------------
+def as_index(index_features, index_names) -> GalleryIndex:
+    """Accept what `extract_index_blip_features` returns: a GalleryIndex, or the reference's
+    (features, raw_features) tuple of tensors."""
+    if isinstance(index_features, GalleryIndex):
+        return index_features
+    feats, raws = index_features[0], index_features[-1]
+    return GalleryIndex(feats=feats.to(torch.bfloat16).contiguous(), raws=raws.to(torch.bfloat16).contiguous(),
+                        names=list(index_names))
+
+
+class IndexFeatures(tuple):
+    """What the fast `extract_index_blip_features` returns as `index_features`: behaves like the reference's
+    (features, raw_features) tuple (validate_blip.py:169,377 index it with [0], [1], [-1]) and carries the
+    sharded GalleryIndex for the fast compute_* functions."""
+
+    def __new__(cls, index: GalleryIndex):
+        obj = super().__new__(cls, (index.feats, index.raws))
+        obj.index = index
+        return obj
+
+
+def extract_index_blip_features(dataset, blip_model, save_memory=False):
+    """utils.py:46-77 -> ((index_features, index_features_raw), index_names)."""
+    from torch.utils.data.dataloader import default_collate
+
+    def collate_fn(batch):  # utils.py:141-148
+        return default_collate([b for b in batch if b is not None])
+
+    index = build_index(dataset, blip_model, batch_size=64, num_workers=2, collate_fn=collate_fn)
+    return IndexFeatures(index), index.names
+
+
+@torch.no_grad()
+def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, index_names, txt_processors):
+    """validate_blip.py:232-285 -> (gR@1, gR@2, gR@3, R@1, R@5, R@10, R@50) in percent."""
+    index = index_features.index if isinstance(index_features, IndexFeatures) else as_index(index_features,
+                                                                                            index_names)
+    ref_names, tgt_names, caps, groups = [], [], [], []
+    for i in range(len(relative_val_dataset)):
+        item = relative_val_dataset[i]
+        if item is None:
+            continue
+        r, t, c, g = item
+        ref_names.append(r)
+        tgt_names.append(t)
+        caps.append(txt_processors["eval"](c))
+        groups.append(list(g))
+    ref_rows, tgt_rows = index.rows_of(ref_names), index.rows_of(tgt_names)
+    group_rows = torch.tensor([[index.name_to_row.get(n, -1) for n in g] for g in groups], dtype=torch.int64)
+    ids, mask = _tokenize(blip_model, caps)
+    tops, subs = [], []
+    B = max(1, blip_model.max_queries)
+    for s in range(0, len(caps), B):
+        sl = slice(s, s + B)
+        _, ix, sub = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=51, subset_rows=group_rows[sl])
+        tops.append(ix.cpu())
+        subs.append(sub.cpu())
+    return cirr_recalls_from_topk(torch.cat(tops), ref_rows, tgt_rows, group_rows, torch.cat(subs))
+
+
+@torch.no_grad()
+def compute_fiq_val_metrics(relative_val_dataset, blip_model, index_features, index_names, txt_processors,
+                            save_memory=False):
+    """validate_blip.py:24-57 -> (R@10, R@50) in percent; captions joined as :180-183."""
+    index = index_features.index if isinstance(index_features, IndexFeatures) else as_index(index_features,
+                                                                                            index_names)
+    ref_names, tgt_names, caps = [], [], []
+    for i in range(len(relative_val_dataset)):
+        item = relative_val_dataset[i]
+        if item is None:
+            continue
+        r, t, c = item
+        ref_names.append(r)
+        tgt_names.append(t)
+        c0, c1 = c[0], c[1]
+        caps.append(txt_processors["eval"](f"{c0.strip('.?, ').capitalize()} and {c1.strip('.?, ')}"))
+    ref_rows, tgt_rows = index.rows_of(ref_names), index.rows_of(tgt_names)
+    ids, mask = _tokenize(blip_model, caps)
+    tops = []
+    B = max(1, blip_model.max_queries)
+    for s in range(0, len(caps), B):
+        sl = slice(s, s + B)
+        _, ix, _ = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=50)
+        tops.append(ix.cpu())
+    top = torch.cat(tops)
+    if not bool((top >= 0).all()) and index.n_total >= 50:
+        raise AssertionError("top-k returned unfilled slots")
+    return fiq_recalls_from_topk(top, tgt_rows)

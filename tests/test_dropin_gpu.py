@@ -1,0 +1,210 @@
+"""Drop-in proof on the GPU: the reference's UNCHANGED scripts (byte-identical copies staged by
+tools/stage_reference_scripts.py into baseline/_ref/src) run against our `lavis.models` replacement on a
+generated CIRR / FashionIQ tree.
+
+Mode A: reference's own utils.py / validate_blip.py loops call our model's `extract_target_features` /
+        `inference` (full [Bq,N] similarity returned, their argsort + string matching computes recalls).
+Mode B: sprc_b200/dropin_fast shadows utils / validate_blip with the fused scan + top-k drivers.
+Targets are planted from our own ranking at known ranks, so the recalls the REFERENCE code prints are
+known in advance (and keep every recall > 0); Mode A and Mode B must print the same JSON.
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(ROOT, "baseline", "_ref", "src")
+DROPIN = os.path.join(ROOT, "sprc_b200", "dropin")
+DROPIN_FAST = os.path.join(ROOT, "sprc_b200", "dropin_fast")
+DEPTH_ENV = {"SPRC_VIT_DEPTH": "2", "SPRC_QF_LAYERS": "2", "SPRC_MAX_IMAGES": "64", "SPRC_MAX_QUERIES": "32"}
+
+N_GALLERY, N_QUERIES = 56, 16
+PLANT_RANKS = [1, 1, 1, 1, 3, 3, 4, 5, 7, 8, 9, 10, 20, 30, 40, 52]  # rank of the target AFTER reference removal
+
+
+def _write_png(path, rng, w=240, h=200):
+    from PIL import Image
+
+    Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(path)
+
+
+def _words(rng, n):
+    vocab = ["red", "blue", "longer", "sleeves", "dog", "two", "remove", "add", "darker", "stripes", "instead",
+             "of", "the", "is", "more", "and", "with", "a", "shorter", "bright"]
+    return " ".join(rng.choice(vocab, size=n).tolist())
+
+
+@pytest.fixture(scope="module")
+def staged_tree(tmp_path_factory):
+    if not os.path.exists(os.path.join(STAGED, "blip_validate.py")):
+        pytest.skip("reference driver scripts are not staged (baseline/_ref/src; build() stages them when "
+                    "/root/reference exists)")
+    from oracle import synth
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+
+    root = str(tmp_path_factory.mktemp("sprc_dropin"))
+    shutil.copytree(STAGED, os.path.join(root, "src"))
+    rng = np.random.default_rng(0)
+    names = [f"dev-{i:03d}-img{i % 3}" for i in range(N_GALLERY)]
+    # ---- images: CIRR dev split + FashionIQ images (same pixels, two directory layouts) ----
+    os.makedirs(os.path.join(root, "cirr_dataset", "dev"))
+    os.makedirs(os.path.join(root, "cirr_dataset", "cirr", "captions"))
+    os.makedirs(os.path.join(root, "cirr_dataset", "cirr", "image_splits"))
+    os.makedirs(os.path.join(root, "fashionIQ_dataset", "images"))
+    os.makedirs(os.path.join(root, "fashionIQ_dataset", "captions"))
+    os.makedirs(os.path.join(root, "fashionIQ_dataset", "image_splits"))
+    for n in names:
+        p = os.path.join(root, "cirr_dataset", "dev", n + ".png")
+        _write_png(p, rng)
+        shutil.copyfile(p, os.path.join(root, "fashionIQ_dataset", "images", n + ".png"))
+    split = {n: f"./dev/{n}.png" for n in names}
+    for sp in ("val", "test1"):
+        with open(os.path.join(root, "cirr_dataset", "cirr", "image_splits", f"split.rc2.{sp}.json"), "w") as f:
+            json.dump(split, f)
+    # ---- checkpoint (truncated ViT-L, synthetic weights) ----
+    sd = synth.make_state_dict("clip_L", 2, 2, seed=0)
+    ckpt = os.path.join(root, "ckpt.pt")
+    torch.save({"epoch": 0, "Blip2QformerCirAlignPrompt": sd}, ckpt)
+    # ---- plant targets from OUR ranking over the images as the reference's data pipeline decodes them ----
+    sys.path.insert(0, os.path.join(root, "src"))
+    try:
+        import importlib
+
+        du = importlib.import_module("data_utils")
+        importlib.reload(du)
+        pre = du.targetpad_transform(1.25, 224)
+        ds = du.CIRRDataset("val", "classic", pre)
+        imgs = torch.stack([ds[i][1] for i in range(len(ds))])
+        assert [ds[i][0] for i in range(len(ds))] == names
+    finally:
+        sys.path.remove(os.path.join(root, "src"))
+        sys.modules.pop("data_utils", None)
+    model = Blip2QformerCirAlignPrompt(vit_model="clip_L", device="cuda:0", max_images=64, max_queries=32,
+                                       vit_depth=2, qf_layers=2)
+    model.load_state_dict(sd)
+    feats, raws = model.extract_target_features(imgs.cuda())
+    from sprc_b200.tokenizer import BlipCaptionProcessor
+
+    proc = BlipCaptionProcessor()
+    ref_idx = rng.choice(N_GALLERY, size=N_QUERIES, replace=False)
+    captions = [_words(rng, int(rng.integers(3, 9))).capitalize() + "." for _ in range(N_QUERIES)]
+    sim = model.inference(raws[torch.as_tensor(ref_idx).cuda()], feats, [proc(c) for c in captions]).cpu()
+    order = torch.argsort(1 - sim, dim=-1)
+    cirr, expected = [], {"ranks": [], "granks": []}
+    for j in range(N_QUERIES):
+        ranked = [int(x) for x in order[j] if int(x) != int(ref_idx[j])]
+        tgt = ranked[PLANT_RANKS[j] - 1]
+        # 6 group members: reference + target + 4 others; the target's subset rank is known from `ranked`
+        others = [x for x in ranked if x != tgt][j % 5:: 9][:4]
+        members = [int(ref_idx[j]), tgt] + others
+        sub = [x for x in ranked if x in members]
+        expected["ranks"].append(PLANT_RANKS[j])
+        expected["granks"].append(sub.index(tgt) + 1)
+        rng.shuffle(members)
+        cirr.append({"pairid": j, "reference": names[ref_idx[j]], "target_hard": names[tgt], "caption": captions[j],
+                     "img_set": {"members": [names[m] for m in members]}})
+    for sp in ("val", "test1"):
+        with open(os.path.join(root, "cirr_dataset", "cirr", "captions", f"cap.rc2.{sp}.json"), "w") as f:
+            json.dump(cirr, f)
+    # FashionIQ: three categories share the gallery split; captions are pairs
+    fiq_expected = {}
+    for ci, cat in enumerate(("dress", "toptee", "shirt")):
+        trip = []
+        ranks = []
+        caps2 = [(_words(rng, 3), _words(rng, 4)) for _ in range(N_QUERIES)]
+        joined = [proc(f"{a.strip('.?, ').capitalize()} and {b.strip('.?, ')}") for a, b in caps2]
+        s2 = model.inference(raws[torch.as_tensor(ref_idx).cuda()], feats, joined).cpu()
+        o2 = torch.argsort(1 - s2, dim=-1)
+        for j in range(N_QUERIES):
+            r = [1, 5, 10, 11, 30, 50, 51, 56][(j + ci) % 8]
+            tgt = int(o2[j][r - 1])
+            ranks.append(r)
+            trip.append({"candidate": names[ref_idx[j]], "target": names[tgt], "captions": list(caps2[j])})
+        fiq_expected[cat] = ranks
+        with open(os.path.join(root, "fashionIQ_dataset", "captions", f"cap.{cat}.val.json"), "w") as f:
+            json.dump(trip, f)
+        with open(os.path.join(root, "fashionIQ_dataset", "image_splits", f"split.{cat}.val.json"), "w") as f:
+            json.dump(names, f)
+    del model
+    torch.cuda.empty_cache()
+    return dict(root=root, ckpt=ckpt, expected=expected, fiq_expected=fiq_expected, names=names)
+
+
+def _run(tree, script, args, fast):
+    env = dict(os.environ)
+    env.update(DEPTH_ENV)
+    paths = ([DROPIN_FAST] if fast else []) + [DROPIN, ROOT]
+    env["PYTHONPATH"] = os.pathsep.join(paths)
+    cmd = [sys.executable, os.path.join(tree["root"], "src", script)] + args
+    if fast:
+        # python puts the script's own directory first on sys.path, which would pick the staged utils.py /
+        # validate_blip.py; run the unchanged file through runpy with the fast modules ahead of it
+        code = ("import sys, runpy; sys.path.insert(0, %r); sys.path.insert(1, %r); sys.argv = %r; "
+                "runpy.run_path(%r, run_name='__main__')") % (
+                    DROPIN_FAST, os.path.join(tree["root"], "src"), [script] + args,
+                    os.path.join(tree["root"], "src", script))
+        cmd = [sys.executable, "-c", code]
+    p = subprocess.run(cmd, env=env, cwd=tree["root"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
+    return p.stdout
+
+
+def _last_json(stdout):
+    end = stdout.rfind("}")
+    start = stdout.rfind("{", 0, end)
+    return json.loads(stdout[start:end + 1])
+
+
+def _pct(ranks, k):
+    return 100.0 * sum(r <= k for r in ranks) / len(ranks)
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["modeA_reference_loops", "modeB_fused_scan"])
+def test_blip_validate_cirr_unchanged_script(staged_tree, fast):
+    out = _run(staged_tree, "blip_validate.py", ["--dataset", "CIRR", "--blip-model-name", "blip2_cir_align_prompt",
+                                                 "--backbone", "pretrain_vitL", "--model-path", staged_tree["ckpt"]],
+               fast)
+    assert "Missing keys []" in out
+    res = _last_json(out)
+    e = staged_tree["expected"]
+    for k in (1, 5, 10, 50):
+        assert res[f"recall_at{k}"] == pytest.approx(_pct(e["ranks"], k), abs=0.05), (k, res)
+    for k in (1, 2, 3):
+        assert res[f"group_recall_at{k}"] == pytest.approx(_pct(e["granks"], k), abs=0.05), (k, res)
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["modeA_reference_loops", "modeB_fused_scan"])
+def test_blip_validate_fashioniq_unchanged_script(staged_tree, fast):
+    out = _run(staged_tree, "blip_validate.py", ["--dataset", "fashionIQ", "--blip-model-name",
+                                                 "blip2_cir_align_prompt", "--backbone", "pretrain_vitL",
+                                                 "--model-path", staged_tree["ckpt"]], fast)
+    res = _last_json(out)
+    fe = staged_tree["fiq_expected"]
+    for cat in ("dress", "toptee", "shirt"):
+        assert res[f"{cat}_recall_at10"] == pytest.approx(_pct(fe[cat], 10), abs=0.05), res
+        assert res[f"{cat}_recall_at50"] == pytest.approx(_pct(fe[cat], 50), abs=0.05), res
+
+
+def test_cirr_test_submission_unchanged_script(staged_tree):
+    _run(staged_tree, "cirr_test_submission.py",
+         ["--blip-model-name", "blip2_cir_align_prompt", "--backbone", "pretrain_vitL", "--model-path",
+          staged_tree["ckpt"]], False)
+    sub_dir = os.path.join(staged_tree["root"], "submission", "CIRR")
+    files = sorted(os.listdir(sub_dir))
+    assert len(files) == 2, files
+    for f in files:
+        with open(os.path.join(sub_dir, f)) as fh:
+            d = json.load(fh)
+        assert d["version"] == "rc2"
+        rows = {k: v for k, v in d.items() if k not in ("version", "metric")}
+        assert len(rows) == N_QUERIES
+        want = 3 if d["metric"] == "recall_subset" else 50
+        for v in rows.values():
+            assert set(v) <= set(staged_tree["names"]) and len(set(v)) == len(v) == want

@@ -1,0 +1,129 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import restatement as R
+from sprc_b200 import _lib as L
+from sprc_b200 import retrieval as RT
+from sprc_b200.tokenizer import BlipCaptionProcessor, OfflineBertTokenizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """Every function include/sprc_b200.h declares is exported by the .so and bound by the ctypes layer."""
+    header = open(os.path.join(ROOT, "include", "sprc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sprc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert L.load().sprc_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly without a CUDA device / handle instead of computing elsewhere."""
+    from sprc_b200.model import Blip2QformerCirAlignPrompt, load_model_and_preprocess
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.SprcError):
+        Blip2QformerCirAlignPrompt(vit_model="clip_L")
+    with pytest.raises(L.SprcError):
+        load_model_and_preprocess("blip2_cir_align_prompt", "pretrain_vitL", device="cpu")
+    with pytest.raises(KeyError):
+        load_model_and_preprocess("blip2_opt", "pretrain", device="cpu")
+    # error reporting through the ABI (argument validation happens before any CUDA call)
+    lib = L.load()
+    rc = lib.sprc_create(None, None)
+    assert rc < 0 and b"null" in lib.sprc_last_error()
+
+
+def test_product_package_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sprc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+CAPTIONS = ["Is  darker; and (has) a \"Longer\" sleeve.", "  Two dogs: REMOVE one!  ", "a" + " word" * 60,
+            "no-punct here~", "tabs\tand\nnewlines\n"]
+
+
+def test_caption_processor_known_answers():
+    p = BlipCaptionProcessor()
+    assert p(CAPTIONS[0]) == "is darker and has a longer sleeve"
+    assert p(CAPTIONS[1]) == "two dogs remove one"
+    assert len(p(CAPTIONS[2]).split(" ")) == 50
+    assert p("") == ""
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_caption_processor_matches_reference():
+    ref = ref_loader.load_caption_processor()()
+    ours = BlipCaptionProcessor()
+    for c in CAPTIONS:
+        assert ours(c) == ref(c)
+
+
+def test_tokenizer_layout_and_determinism():
+    t = OfflineBertTokenizer()
+    assert len(t) == 30523 and t.bos_token_id == 30522
+    b = t(["Hello, World!", "x " * 80], padding="max_length", truncation=True, max_length=32, return_tensors="pt")
+    assert b.input_ids.shape == (2, 32) and b.input_ids.dtype == torch.int64
+    assert b.input_ids[0, 0] == 101 and b.input_ids[0, 5] == 102 and (b.input_ids[0, 6:] == 0).all()
+    assert b.attention_mask[0].sum() == 6
+    assert b.input_ids[1, 0] == 101 and b.input_ids[1, 31] == 102 and b.attention_mask[1].all()  # truncation
+    assert torch.equal(t(["hello , world !"]).input_ids, t(["Hello, World!"]).input_ids)  # lower-case + punct split
+    assert ((b.input_ids[0, 1:5] >= 1000) & (b.input_ids[0, 1:5] < 30000)).all()
+
+
+def test_tokenizer_wordpiece_with_vocab_file(tmp_path):
+    """Greedy longest-match-first WordPiece (transformers 4.36 BertTokenizer semantics) on a toy vocab."""
+    toks = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    toks += ["sleeve", "##s", "long", "##er", "un", "##aff", "##able", ",", "caf", "##e"]
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(toks) + "\n")
+    t = OfflineBertTokenizer(str(vf))
+    ids = t.encode("Longer sleeves, unaffable café zzz")
+    v = {tok: i for i, tok in enumerate(toks)}
+    assert ids == [101, v["long"], v["##er"], v["sleeve"], v["##s"], v[","], v["un"], v["##aff"], v["##able"],
+                   v["caf"], v["##e"], 100, 102]
+
+
+def test_shard_ranges_and_owner():
+    for n, w in ((50000, 8), (7, 3), (5, 8), (200000, 8)):
+        spans = [RT.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        rows = torch.arange(n)
+        own = RT.owner_of(rows, n, w)
+        for r, (lo, hi) in enumerate(spans):
+            assert bool((own[lo:hi] == r).all())
+
+
+def test_recalls_from_topk_match_oracle_full_sort():
+    """The top-(k+1) + subset-score formulation == the oracle's full-sort formulation (same as the reference's)."""
+    g = torch.Generator().manual_seed(1)
+    Q, N = 40, 300
+    sim = torch.rand(Q, N, generator=g)
+    order = R.ranking(sim)
+    ref = torch.randint(0, N, (Q,), generator=g)
+    pick = [0, 0, 1, 4, 5, 9, 10, 49, 50, 120]
+    tgt = torch.stack([order[q][order[q] != ref[q]][pick[q % len(pick)]] for q in range(Q)])
+    members = torch.stack([torch.cat([ref[q:q + 1], tgt[q:q + 1],
+                                      order[q][(order[q] != ref[q]) & (order[q] != tgt[q])][3:7]]) for q in range(Q)])
+    want = R.cirr_recalls(order, ref, tgt, members)
+    got = RT.cirr_recalls_from_topk(order[:, :51], ref, tgt, members, torch.gather(sim, 1, members))
+    assert got == pytest.approx(want, abs=1e-9)
+    assert RT.fiq_recalls_from_topk(order[:, :50], tgt) == pytest.approx(R.fiq_recalls(order, tgt), abs=1e-9)
+    with pytest.raises(AssertionError):
+        RT.cirr_recalls_from_topk(order[:, :51], ref, ref, members, torch.gather(sim, 1, members))
