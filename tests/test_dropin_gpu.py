@@ -68,6 +68,8 @@ def staged_tree(tmp_path_factory):
     for sp in ("val", "test1"):
         with open(os.path.join(root, "cirr_dataset", "cirr", "image_splits", f"split.rc2.{sp}.json"), "w") as f:
             json.dump(split, f)
+        with open(os.path.join(root, "cirr_dataset", "cirr", "captions", f"cap.rc2.{sp}.json"), "w") as f:
+            json.dump([], f)  # placeholder: CIRRDataset opens it even in 'classic' mode (data_utils.py:235)
     # ---- checkpoint (truncated ViT-L, synthetic weights) ----
     sd = synth.make_state_dict("clip_L", 2, 2, seed=0)
     ckpt = os.path.join(root, "ckpt.pt")
