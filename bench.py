@@ -53,6 +53,7 @@ def parse():
                          "synthetic unit-norm features (profiling runs; query-step kernels are unchanged)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-dump", default="", help="write per-shape kernel timings (CSV) of the profiling pass")
     return ap.parse_args()
 
 
@@ -333,6 +334,12 @@ def main():
         step_device(W + i)
     torch.cuda.synchronize()
     L.check(lib.sprc_profile_read(prof, 5))
+    if args.profile_dump and rank == 0:
+        L.check(lib.sprc_profile_dump((args.profile_dump + ".query.csv").encode()))
+        lib.sprc_profile(1)
+        L.check(lib.sprc_encode_gallery(h, L.ptr(img), min(IB, n_local), None, L.ptr(feats), None, L.ptr(raws), st()))
+        torch.cuda.synchronize()
+        L.check(lib.sprc_profile_dump((args.profile_dump + ".index.csv").encode()))
     lib.sprc_profile(0)
     cat = lambda c: dict(ms=prof[c * 4], flops=prof[c * 4 + 1], bytes=prof[c * 4 + 2], n=prof[c * 4 + 3])  # noqa: E731
     gemm, attn, lnorm, scan, merge = (cat(c) for c in range(5))

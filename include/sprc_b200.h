@@ -126,6 +126,8 @@ int64_t sprc_launch_count(void);
 #define SPRC_PROF_NCAT 5
 int sprc_profile(int enable);
 int sprc_profile_read(double* out, int ncat);
+/* CSV of per-(category, shape tag) aggregates of the recorded launches: cat,tag,launches,total_ms,flops,bytes */
+int sprc_profile_dump(const char* path);
 
 /* ---- single-op entry points (tests and micro-benchmarks) ------------------------------------- */
 /* C = act(A[M,K] W[N,K]^T + bias) (+ residual); impl 0 = tcgen05 product kernel, 1 = CUDA-core checker. */

@@ -78,6 +78,7 @@ SIGNATURES = {
     "sprc_launch_count": (c_int64, []),
     "sprc_profile": (c_int, [c_int]),
     "sprc_profile_read": (c_int, [POINTER(ctypes.c_double), c_int]),
+    "sprc_profile_dump": (c_int, [c_char_p]),
     "sprc_op_gemm": (
         c_int,
         [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

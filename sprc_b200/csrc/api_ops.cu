@@ -15,6 +15,10 @@ int sprc_profile(int enable) {
   prof_set(enable != 0);
   return 0;
 }
+int sprc_profile_dump(const char* path) {
+  if (!path) return set_error(-22, "sprc_profile_dump: null path");
+  return prof_dump(path);
+}
 int sprc_profile_read(double* out, int ncat) {
   if (!out || ncat <= 0) return set_error(-22, "sprc_profile_read: bad arguments");
   return prof_read(out, ncat);

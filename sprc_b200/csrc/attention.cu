@@ -8,6 +8,7 @@
 // the score matrix never touches HBM (the reference materialises [B,H,257,257] in HBM).
 // The attention core is 2.8 % of the ViT FLOPs; the GEMMs around it are tcgen05.
 #include <math.h>
+#include <stdio.h>
 
 #include "ops.h"
 #include "ptx.cuh"
@@ -212,8 +213,12 @@ static int launch_attention(const AttnDesc& a, cudaStream_t st) {
   dim3 grid(a.H, a.B);
   prof_begin(st);
   attention_kernel<DHP><<<grid, ATT_WARPS * 32, smem, st>>>(a);
-  prof_end(PROF_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * a.dh,
-           2.0 * a.B * a.H * a.dh * (2.0 * a.Lq + 2.0 * a.Lk), st);
+  if (prof_enabled()) {
+    char tag[56];
+    snprintf(tag, sizeof(tag), "B%d H%d dh%d Lq%d Lk%d", a.B, a.H, a.dh, a.Lq, a.Lk);
+    prof_end(PROF_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * a.dh,
+             2.0 * a.B * a.H * a.dh * (2.0 * a.Lq + 2.0 * a.Lk), st, tag);
+  }
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

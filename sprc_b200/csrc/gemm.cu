@@ -9,8 +9,10 @@
 //   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) into a STAGES-deep ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators
 //               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, each draining half of the columns): tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
 //               128-bit global stores (fp32 residual stream or bf16 activations)
+#include <stdio.h>
+
 #include "common.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -19,12 +21,15 @@ namespace sprc {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter (column halves)
+static constexpr int EPI_STAGE_BYTES = 32 * 128;         // per-warp transpose tile: 32 rows x 128 B, XOR-swizzled
+static constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct GemmKernelParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
   int a_grp_rows;  // 0: dense (coords k, m0, 0); else (k, 0, m0 / a_grp_rows)
-  int grp_rows, grp_stride;
+  int grp_rows, grp_stride, grp_shift;
   const float* bias;
   const float* residual;
   float* out_f32;
@@ -39,11 +44,12 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int RING_BYTES = STAGES * (A_BYTES + B_BYTES);
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int TOTAL = RING_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
@@ -51,7 +57,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * L::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
+  uint8_t* sEpi = smem + L::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -70,7 +77,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -141,72 +148,85 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two phases per 32-column chunk.  Phase 1: tcgen05.ld gives each thread ONE ROW x 32 columns; it is
+    // written to this warp's swizzled smem tile.  Phase 2: the warp re-reads the tile so that 8 consecutive
+    // lanes hold one row's 128 contiguous bytes (4 rows per instruction) and applies bias / activation /
+    // residual there - every global load and store is then a run of full 128-byte lines.  (The first
+    // version stored row-per-thread: 32 different lines per instruction, and was epilogue-bound at K=768.)
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int cpart = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    uint8_t* stile = sEpi + (warp - 2) * EPI_STAGE_BYTES;
+    const int prow = lane >> 3;          // phase 2: row within a 4-row group
+    const int ppiece = lane & 7;         // phase 2: 16-byte piece (4 fp32 columns) of the 128-byte row
+    constexpr int CPW = BN / 64;         // 32-column chunks per warp
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_blocks) * BM;
       const int n0 = (tile % p.num_n_blocks) * BN;
+      // physical output rows of the 8 rows this lane serves in phase 2 (-1: out of range)
+      long long orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + q * 32 + i * 4 + prow;
+        long long r = m;
+        if (p.grp_rows > 0) r = static_cast<long long>(m >> p.grp_shift) * p.grp_stride + (m & (p.grp_rows - 1));
+        orow[i] = m < p.M ? r : -1;
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      long long orow = m;
-      if (p.grp_rows > 0) orow = static_cast<long long>(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = cpart * CPW + cc;
+        const int n = n0 + c * 32;                 // first column of the chunk (warp-uniform)
+        const bool col_ok = n < p.N;
+        const int ncol = n + ppiece * 4;           // this lane's 4 columns in phase 2
+        // residual and bias do not depend on the accumulator: issue their loads first
+        float4 res[8];
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (orow[i] >= 0)
+                res[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(orow[i]) * p.ldc + ncol);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (row_ok && n < p.N) {
-          float v[32];
+        // phase 1: row `lane`, piece j -> byte offset lane*128 + ((j ^ (lane & 7)) * 16)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        if (col_ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + prow;
+            const uint4 raw = *reinterpret_cast<const uint4*>(stile + row * 128 + ((ppiece ^ (row & 7)) << 4));
+            float v0 = __uint_as_float(raw.x) + bia.x, v1 = __uint_as_float(raw.y) + bia.y;
+            float v2 = __uint_as_float(raw.z) + bia.z, v3 = __uint_as_float(raw.w) + bia.w;
+            if (p.act == ACT_GELU) {
+              v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
+            } else if (p.act == ACT_QUICKGELU) {
+              v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
             }
-          }
-          if (p.act == ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == ACT_QUICKGELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-          }
-          const size_t off = static_cast<size_t>(orow) * p.ldc + n;
-          if (p.residual) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = r4[j];
-              v[4 * j + 0] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
+            if (orow[i] >= 0) {
+              const size_t off = static_cast<size_t>(orow[i]) * p.ldc + ncol;
+              if (p.residual) v0 += res[i].x, v1 += res[i].y, v2 += res[i].z, v3 += res[i].w;
+              if (p.out_f32)
+                *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v0, v1, v2, v3);
+              else
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
             }
-          }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
           }
         }
+        __syncwarp();  // the tile is rewritten by the next chunk's phase 1
       }
       tc_fence_before();
       __syncwarp();
@@ -287,6 +307,8 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   p.a_grp_rows = d.grp_rows;
   p.grp_rows = d.grp_rows;
   p.grp_stride = d.grp_stride;
+  p.grp_shift = 0;
+  while (d.grp_rows > 0 && (1 << p.grp_shift) < d.grp_rows) ++p.grp_shift;
   p.bias = d.bias;
   p.residual = d.residual;
   p.out_f32 = d.out_f32;
@@ -303,9 +325,14 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   prof_begin(st);
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, p);
-  prof_end(PROF_GEMM, 2.0 * d.M * (double)d.N * d.K,
-           2.0 * ((double)d.M * d.K + (double)d.N * d.K) + (double)d.M * d.N * (d.out_f32 ? 4.0 : 2.0), st);
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, p);
+  if (prof_enabled()) {
+    char tag[56];
+    snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d bn%d", d.M, d.N, d.K, d.grp_rows, d.act,
+             d.residual ? 1 : 0, d.out_f32 ? 1 : 0, BN);
+    prof_end(PROF_GEMM, 2.0 * d.M * (double)d.N * d.K,
+             2.0 * ((double)d.M * d.K + (double)d.N * d.K) + (double)d.M * d.N * (d.out_f32 ? 4.0 : 2.0), st, tag);
+  }
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

@@ -11,7 +11,8 @@ void count_launch(int n = 1);
 enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ELEMWISE = 2, PROF_SCAN = 3, PROF_MERGE = 4, PROF_NCAT = 5 };
 bool prof_enabled();
 void prof_begin(cudaStream_t st);
-void prof_end(int cat, double flops, double bytes, cudaStream_t st);
+void prof_end(int cat, double flops, double bytes, cudaStream_t st, const char* tag = nullptr);
+int prof_dump(const char* path);
 void prof_set(bool on);
 int prof_read(double* out, int ncat);
 

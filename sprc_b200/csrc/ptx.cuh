@@ -173,7 +173,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+// erf-GELU (nn.GELU default, eva_vit.py:55-56 / Qformer.py:360): 0.5 x (1 + erf(x / sqrt 2)) with the
+// Abramowitz-Stegun 7.1.26 rational erf (|abs err| <= 1.5e-7, far below the bf16 rounding of the output);
+// one MUFU.RCP + one MUFU.EX2 + 8 FMAs instead of libdevice erff's two-branch polynomial.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * ex2_approx(z * z * -1.4426950408889634f);  // 1 - erf(z), z >= 0
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(1.0f - e, x), hx);
+}
+__device__ __forceinline__ float quick_gelu(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
+}
 
 }  // namespace sprc

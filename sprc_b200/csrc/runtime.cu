@@ -5,6 +5,7 @@
 #include "common.h"
 #include "ops.h"
 
+#include <string>
 #include <vector>
 
 namespace sprc {
@@ -41,6 +42,7 @@ struct ProfRec {
   cudaEvent_t a, b;
   int cat;
   double flops, bytes;
+  char tag[56];
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_recs;
@@ -64,7 +66,7 @@ void prof_begin(cudaStream_t st) {
   g_pending = get_event();
   cudaEventRecord(g_pending, st);
 }
-void prof_end(int cat, double flops, double bytes, cudaStream_t st) {
+void prof_end(int cat, double flops, double bytes, cudaStream_t st, const char* tag) {
   if (!g_prof_on || !g_pending) return;
   ProfRec r;
   r.a = g_pending;
@@ -72,6 +74,7 @@ void prof_end(int cat, double flops, double bytes, cudaStream_t st) {
   r.cat = cat;
   r.flops = flops;
   r.bytes = bytes;
+  snprintf(r.tag, sizeof(r.tag), "%s", tag ? tag : "");
   cudaEventRecord(r.b, st);
   g_recs.push_back(r);
   g_pending = nullptr;
@@ -98,6 +101,39 @@ int prof_read(double* out, int ncat) {
       out[r.cat * 4 + 3] += 1.0;
     }
   }
+  return 0;
+}
+
+
+// CSV of per-(category, tag) aggregates: cat,tag,launches,total_ms,flops,bytes
+int prof_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) return set_error(-2, "profile: cannot open %s", path);
+  struct Agg {
+    int cat;
+    std::string tag;
+    double n, ms, flops, bytes;
+  };
+  std::vector<Agg> aggs;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg* a = nullptr;
+    for (auto& x : aggs)
+      if (x.cat == r.cat && x.tag == r.tag) a = &x;
+    if (!a) {
+      aggs.push_back({r.cat, r.tag, 0, 0, 0, 0});
+      a = &aggs.back();
+    }
+    a->n += 1;
+    a->ms += ms;
+    a->flops += r.flops;
+    a->bytes += r.bytes;
+  }
+  fprintf(f, "cat,tag,launches,total_ms,flops,bytes\n");
+  for (auto& a : aggs) fprintf(f, "%d,%s,%.0f,%.6f,%.6e,%.6e\n", a.cat, a.tag.c_str(), a.n, a.ms, a.flops, a.bytes);
+  fclose(f);
   return 0;
 }
 
