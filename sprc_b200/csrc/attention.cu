@@ -10,29 +10,13 @@
 #include <math.h>
 #include <stdio.h>
 
+#include "mma_sync.cuh"
 #include "ops.h"
 #include "ptx.cuh"
 
 namespace sprc {
 
 static constexpr int ATT_WARPS = 6;
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 template <int DHP>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDesc a) {
@@ -200,6 +184,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
   }
 }
 
+int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
+
 template <int DHP>
 static int launch_attention(const AttnDesc& a, cudaStream_t st) {
   const int Lkp = (a.Lk + 63) & ~63;
@@ -230,6 +216,7 @@ int attention(const AttnDesc& a, cudaStream_t st) {
   SPRC_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 2 == 0,
                "attention: row pitches must keep 16-byte alignment");
   SPRC_REQUIRE(a.B <= 65535, "attention: B=%d exceeds grid limit", a.B);
+  if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // Q-Former shapes
   if (a.dh <= 64) return launch_attention<64>(a, st);
   return launch_attention<96>(a, st);
 }
