@@ -9,7 +9,7 @@
 //   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) into a STAGES-deep ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators
 //               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, each draining half of the columns): tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
+//   warps 2..17 epilogue (four warps per TMEM lane quarter, each draining a quarter of the columns): tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
 //               128-bit global stores (fp32 residual stream or bf16 activations)
 #include <stdio.h>
 
@@ -21,8 +21,8 @@ namespace sprc {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter (column halves)
-static constexpr int EPI_STAGE_BYTES = 32 * 128;         // per-warp transpose tile: 32 rows x 128 B, XOR-swizzled
+static constexpr int EPI_WARPS = 16;                     // four warps per TMEM lane quarter (column quarters)
+static constexpr int EPI_STAGE_BYTES = 32 * 64;          // per-warp transpose tile: 32 rows x 64 B, XOR-swizzled
 static constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct GemmKernelParams {
@@ -148,28 +148,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // Two phases per 32-column chunk.  Phase 1: tcgen05.ld gives each thread ONE ROW x 32 columns; it is
-    // written to this warp's swizzled smem tile.  Phase 2: the warp re-reads the tile so that 8 consecutive
-    // lanes hold one row's 128 contiguous bytes (4 rows per instruction) and applies bias / activation /
-    // residual there - every global load and store is then a run of full 128-byte lines.  (The first
-    // version stored row-per-thread: 32 different lines per instruction, and was epilogue-bound at K=768.)
+    // ===================== epilogue (warps 2..17) =====================
+    // Two phases per 16-column chunk.  Phase 1: tcgen05.ld gives each thread ONE ROW x 16 columns; it is
+    // written to this warp's swizzled smem tile.  Phase 2: the warp re-reads the tile so that 4 consecutive
+    // lanes hold one row's 64 contiguous bytes (8 rows per instruction) and applies bias / activation /
+    // residual there - every global load and store then covers whole 32-byte sectors of consecutive
+    // addresses.  (The first version stored row-per-thread, 32 different lines per instruction, and was
+    // epilogue-bound at K = 768.)  Four warps per SMSP keep the GELU math off the critical path.
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int cpart = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    const int cpart = (warp - 2) >> 2;   // which quarter of the tile's columns this warp drains
     uint8_t* stile = sEpi + (warp - 2) * EPI_STAGE_BYTES;
-    const int prow = lane >> 3;          // phase 2: row within a 4-row group
-    const int ppiece = lane & 7;         // phase 2: 16-byte piece (4 fp32 columns) of the 128-byte row
-    constexpr int CPW = BN / 64;         // 32-column chunks per warp
+    const int prow = lane >> 2;          // phase 2: row within an 8-row group
+    const int ppiece = lane & 3;         // phase 2: 16-byte piece (4 fp32 columns) of the 64-byte row
+    constexpr int CPW = BN / 64;         // 16-column chunks per warp
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_blocks) * BM;
       const int n0 = (tile % p.num_n_blocks) * BN;
-      // physical output rows of the 8 rows this lane serves in phase 2 (-1: out of range)
-      long long orow[8];
+      // physical output rows of the 4 rows this lane serves in phase 2 (-1: out of range)
+      long long orow[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + q * 32 + i * 4 + prow;
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + q * 32 + i * 8 + prow;
         long long r = m;
         if (p.grp_rows > 0) r = static_cast<long long>(m >> p.grp_shift) * p.grp_stride + (m & (p.grp_rows - 1));
         orow[i] = m < p.M ? r : -1;
@@ -180,35 +181,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll 1
       for (int cc = 0; cc < CPW; ++cc) {
         const int c = cpart * CPW + cc;
-        const int n = n0 + c * 32;                 // first column of the chunk (warp-uniform)
+        const int n = n0 + c * 16;                 // first column of the chunk (warp-uniform)
         const bool col_ok = n < p.N;
         const int ncol = n + ppiece * 4;           // this lane's 4 columns in phase 2
         // residual and bias do not depend on the accumulator: issue their loads first
-        float4 res[8];
+        float4 res[4];
         float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok) {
           if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
           if (p.residual) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
               if (orow[i] >= 0)
                 res[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(orow[i]) * p.ldc + ncol);
           }
         }
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
+        uint32_t r[16];
+        tmem_ld16(t_row + c * 16, r);
         tmem_ld_wait();
-        // phase 1: row `lane`, piece j -> byte offset lane*128 + ((j ^ (lane & 7)) * 16)
+        // phase 1: row `lane`, piece j -> byte offset lane*64 + ((j ^ ((lane >> 1) & 3)) * 16)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(stile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
               make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         if (col_ok) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + prow;
-            const uint4 raw = *reinterpret_cast<const uint4*>(stile + row * 128 + ((ppiece ^ (row & 7)) << 4));
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + prow;
+            const uint4 raw = *reinterpret_cast<const uint4*>(stile + row * 64 + ((ppiece ^ ((row >> 1) & 3)) << 4));
             float v0 = __uint_as_float(raw.x) + bia.x, v1 = __uint_as_float(raw.y) + bia.y;
             float v2 = __uint_as_float(raw.z) + bia.z, v3 = __uint_as_float(raw.w) + bia.w;
             if (p.act == ACT_GELU) {
