@@ -9,6 +9,7 @@
 // The attention core is 2.8 % of the ViT FLOPs; the GEMMs around it are tcgen05.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "mma_sync.cuh"
 #include "ops.h"
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
 }
 
 int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
+bool attention_tc_eligible(const AttnDesc& a);               // attention_tc.cu
+int attention_tc(const AttnDesc& a, cudaStream_t st);
 
 template <int DHP>
 static int launch_attention(const AttnDesc& a, cudaStream_t st) {
@@ -217,6 +220,8 @@ int attention(const AttnDesc& a, cudaStream_t st) {
                "attention: row pitches must keep 16-byte alignment");
   SPRC_REQUIRE(a.B <= 65535, "attention: B=%d exceeds grid limit", a.B);
   if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // Q-Former shapes
+  static const bool legacy = getenv("SPRC_ATTN_MMA_SYNC") != nullptr;  // A/B switch for tests
+  if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT: tcgen05
   if (a.dh <= 64) return launch_attention<64>(a, st);
   return launch_attention<96>(a, st);
 }
