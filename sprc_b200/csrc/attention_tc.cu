@@ -127,7 +127,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* o_full = bars + 6;
   uint64_t* o_empty = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* xch = reinterpret_cast<float*>(bars + 10);  // [4 segments][128 rows] row max, then [4][128] row sum
+  const uint32_t xch = smem_u32(bars + 10);  // [4 segments][128 rows] row max, then [4][128] row sum (byte address)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.B * p.H;
@@ -268,10 +268,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             for (int j = 0; j < 64; ++j)
               if (key0 + j < p.L) mx = fmaxf(mx, __uint_as_float(sr[j]));
           }
-          xch[seg * 128 + row_in_tile] = mx;
+          sts32f(xch + (seg * 128 + row_in_tile) * 4, mx);
           asm volatile("bar.sync 1, 512;" ::: "memory");
-          mx = fmaxf(fmaxf(xch[row_in_tile], xch[128 + row_in_tile]),
-                     fmaxf(xch[256 + row_in_tile], xch[384 + row_in_tile]));
+          mx = fmaxf(fmaxf(lds32f(xch + row_in_tile * 4), lds32f(xch + (128 + row_in_tile) * 4)),
+                     fmaxf(lds32f(xch + (256 + row_in_tile) * 4), lds32f(xch + (384 + row_in_tile) * 4)));
           const float moff = mx * p.scale_log2;
           // ---- p = 2^(s*scale - max*scale), packed bf16 -> TMEM, 32 keys (16 columns) at a time ----
           const int nblk = nkeys / 32;  // 2 (+ a 16-key tail for segment 0)
@@ -307,7 +307,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           // rows beyond L: P content is irrelevant (rows are never stored) - only keep the barriers in step
           asm volatile("bar.sync 1, 512;" ::: "memory");
         }
-        xch[512 + seg * 128 + row_in_tile] = sum;
+        sts32f(xch + (512 + seg * 128 + row_in_tile) * 4, sum);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
@@ -319,8 +319,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int qrow = mt * 128 + row_in_tile;
         constexpr int OC = DHP / 4;  // output columns per warp (16 or 24)
         if (warp_has_rows) {
-          const float inv = 1.0f / ((xch[512 + row_in_tile] + xch[640 + row_in_tile]) +
-                                    (xch[768 + row_in_tile] + xch[896 + row_in_tile]));
+          const float inv = 1.0f / ((lds32f(xch + (512 + row_in_tile) * 4) + lds32f(xch + (640 + row_in_tile) * 4)) +
+                                    (lds32f(xch + (768 + row_in_tile) * 4) + lds32f(xch + (896 + row_in_tile) * 4)));
           const uint32_t o_addr = tmem_base + lane_addr + TA_COL_O + seg * OC;
           bf16* orow = p.O + (static_cast<size_t>(b) * p.L + qrow) * p.ldo + h * DH + seg * OC;
           uint32_t r[16];

@@ -157,7 +157,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // epilogue-bound at K = 768.)  Four warps per SMSP keep the GELU math off the critical path.
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int cpart = (warp - 2) >> 2;   // which quarter of the tile's columns this warp drains
-    uint8_t* stile = sEpi + (warp - 2) * EPI_STAGE_BYTES;
+    const uint32_t stile = smem_u32(sEpi) + (warp - 2) * EPI_STAGE_BYTES;
     const int prow = lane >> 2;          // phase 2: row within an 8-row group
     const int ppiece = lane & 3;         // phase 2: 16-byte piece (4 fp32 columns) of the 64-byte row
     constexpr int CPW = BN / 64;         // 16-column chunks per warp
@@ -202,14 +202,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // phase 1: row `lane`, piece j -> byte offset lane*64 + ((j ^ ((lane >> 1) & 3)) * 16)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(stile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          sts128(stile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         if (col_ok) {
+          uint4 raws[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row = i * 8 + prow;
-            const uint4 raw = *reinterpret_cast<const uint4*>(stile + row * 64 + ((ppiece ^ ((row >> 1) & 3)) << 4));
+            raws[i] = lds128(stile + row * 64 + ((ppiece ^ ((row >> 1) & 3)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 raw = raws[i];
             float v0 = __uint_as_float(raw.x) + bia.x, v1 = __uint_as_float(raw.y) + bia.y;
             float v2 = __uint_as_float(raw.z) + bia.z, v3 = __uint_as_float(raw.w) + bia.w;
             if (p.act == ACT_GELU) {

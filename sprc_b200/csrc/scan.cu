@@ -166,8 +166,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q = qt * SQ + ql;
     const bool q_ok = q < p.Q;
     const int k = p.k;
-    u64* myheap = heap + ql;               // slot j at myheap[j * SQ]
-    for (int j = 0; j < k; ++j) myheap[j * SQ] = static_cast<u64>(j);  // distinct sub-minimal keys, valid min-heap
+    const uint32_t myheap = smem_u32(heap + ql);   // slot j at byte offset j * SQ * 8 (explicit shared-space accesses)
+    constexpr uint32_t HS = SQ * 8;
+    for (int j = 0; j < k; ++j) sts64(myheap + j * HS, static_cast<u64>(j));  // distinct sub-minimal keys, valid min-heap
     u64 root = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -203,16 +204,16 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               while (true) {
                 const int l = 2 * i + 1;
                 if (l >= k) break;
-                const u64 kl = myheap[l * SQ];
-                const u64 kr = (l + 1 < k) ? myheap[(l + 1) * SQ] : ~0ull;
+                const u64 kl = lds64(myheap + l * HS);
+                const u64 kr = (l + 1 < k) ? lds64(myheap + (l + 1) * HS) : ~0ull;
                 const int c = kr < kl ? l + 1 : l;
                 const u64 kc = kr < kl ? kr : kl;
                 if (kc >= key) break;
-                myheap[i * SQ] = kc;
+                sts64(myheap + i * HS, kc);
                 i = c;
               }
-              myheap[i * SQ] = key;
-              root = myheap[0];
+              sts64(myheap + i * HS, key);
+              root = lds64(myheap);
             }
           }
         }
@@ -224,7 +225,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     if (p.cand && q_ok) {
       const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
-      for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = myheap[j * SQ];
+      for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = lds64(myheap + j * HS);
     }
   }
 
