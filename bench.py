@@ -53,6 +53,8 @@ def parse():
                          "synthetic unit-norm features (profiling runs; query-step kernels are unchanged)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--act-dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit tensor-core operand format (bf16 = BASELINE dtype; fp16 = the reference's autocast)")
     ap.add_argument("--profile-dump", default="", help="write per-shape kernel timings (CSV) of the profiling pass")
     return ap.parse_args()
 
@@ -196,7 +198,8 @@ def main():
 
     Bq, k, N = args.batch, args.k, args.gallery
     model = Blip2QformerCirAlignPrompt(vit_model=args.vit, device=dev, max_images=args.index_batch,
-                                       max_queries=Bq)
+                                       max_queries=Bq, act_dtype=args.act_dtype)
+    adt = model.act_torch_dtype
     sd = synth.make_state_dict(args.vit, None, 12, seed=0)
     assert model.load_state_dict(sd, strict=False).missing_keys == []
     Dv = model.vit_width
@@ -204,8 +207,8 @@ def main():
     # ---- gallery index shard: rows [lo, hi) of the N-row gallery, encoded by our ViT + Q-Former ----
     lo, hi = rank * N // world, (rank + 1) * N // world
     n_local = hi - lo
-    feats = torch.empty(n_local, 32, 256, device=dev, dtype=torch.bfloat16)
-    raws = torch.empty(n_local, 257, Dv, device=dev, dtype=torch.bfloat16)
+    feats = torch.empty(n_local, 32, 256, device=dev, dtype=adt)
+    raws = torch.empty(n_local, 257, Dv, device=dev, dtype=adt)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     h = model._h
     st = lambda: L.c_void_p(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
@@ -221,7 +224,7 @@ def main():
     n_index = n_local if args.index_images <= 0 else min(n_local, args.index_images)
     if n_index < n_local:
         feats[n_index:] = synth.make_gallery_features(n_local - n_index, seed=99 + rank, device=dev,
-                                                      dtype=torch.bfloat16)
+                                                      dtype=adt)
         raws[n_index:].zero_()
     e0.record()
     for s in range(0, n_index, IB):
@@ -247,8 +250,8 @@ def main():
     out_sc_h = torch.empty(Bq, k, dtype=torch.float32).pin_memory()
     out_ix_h = torch.empty(Bq, k, dtype=torch.int32).pin_memory()
 
-    fusion = torch.empty(Bq, 256, device=dev, dtype=torch.bfloat16)
-    fusion_all = torch.empty(world * Bq, 256, device=dev, dtype=torch.bfloat16)
+    fusion = torch.empty(Bq, 256, device=dev, dtype=adt)
+    fusion_all = torch.empty(world * Bq, 256, device=dev, dtype=adt)
     sc = torch.empty(world * Bq, k, device=dev)
     ix = torch.empty(world * Bq, k, device=dev, dtype=torch.int32)
     cand_sc = torch.empty(world, world * Bq, k, device=dev)
@@ -376,7 +379,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": args.act_dtype, "data": "synthetic",
             "config": {"workload": f"{args.vit}_blip2_cirr_shape_gallery{N}", "gallery": N,
                        "queries_per_step_per_gpu": Bq, "k": k, "gallery_rows_per_gpu": n_local,
                        "l2": "inputs_exceed_l2 (gallery %.0f MB + weights; query batches rotate)" % (

@@ -49,6 +49,9 @@ typedef struct sprc_config {
   int max_queries; /* largest Bq accepted by sprc_encode_query */
   int max_pairs;   /* largest R*T accepted by sprc_rerank (0 = rerank workspace not allocated) */
   int device;      /* CUDA device ordinal */
+  int act_dtype;   /* 16-bit operand/activation format of every kernel: 0 = bf16 (default), 1 = fp16 (the
+                      reference's own autocast precision, blip2.py:36-44).  Process-wide; tensors named
+                      *_bf16 in this header hold whichever format is active. */
 } sprc_config;
 
 /* One tensor of the reference checkpoint (`ckpt["Blip2QformerCirAlignPrompt"]`, utils.py:208-222),
@@ -119,6 +122,9 @@ int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gall
 
 /* Number of kernels this library has launched on behalf of the calling process (bench `gpu_launches`). */
 int64_t sprc_launch_count(void);
+
+/* Sets the process-wide 16-bit format for the single-op entry points (sprc_create sets it from the config). */
+int sprc_set_act_dtype(int fp16);
 
 /* Optional per-launch timing with CUDA events on the launching stream, by kernel category
  * (0 gemm, 1 attention, 2 layernorm, 3 scan, 4 merge).  sprc_profile(1) clears and enables,

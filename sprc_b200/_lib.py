@@ -27,6 +27,7 @@ class SprcConfig(ctypes.Structure):
         ("max_queries", c_int),
         ("max_pairs", c_int),
         ("device", c_int),
+        ("act_dtype", c_int),
     ]
 
 
@@ -76,6 +77,7 @@ SIGNATURES = {
          c_void_p],
     ),
     "sprc_launch_count": (c_int64, []),
+    "sprc_set_act_dtype": (c_int, [c_int]),
     "sprc_profile": (c_int, [c_int]),
     "sprc_profile_read": (c_int, [POINTER(ctypes.c_double), c_int]),
     "sprc_profile_dump": (c_int, [c_char_p]),

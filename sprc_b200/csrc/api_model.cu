@@ -36,6 +36,11 @@ int sprc_create(const sprc_config* cfg, sprc_handle** out) {
   *out = nullptr;
   sprc_handle* h = new (std::nothrow) sprc_handle();
   if (!h) return set_error(-12, "sprc_create: out of host memory");
+  if (cfg->act_dtype != 0 && cfg->act_dtype != 1) {
+    delete h;
+    return set_error(-22, "sprc_create: act_dtype must be 0 (bf16) or 1 (fp16)");
+  }
+  set_act_fp16(cfg->act_dtype);  // process-wide mode: one handle per process (include/sprc_b200.h)
   int rc = h->m.init(cfg->vit_kind, cfg->vit_depth, cfg->qf_layers, cfg->max_images, cfg->max_queries,
                      cfg->max_pairs, cfg->device);
   if (rc != 0) {

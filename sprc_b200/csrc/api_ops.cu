@@ -11,6 +11,11 @@ extern "C" {
 int sprc_abi_version(void) { return SPRC_ABI_VERSION; }
 const char* sprc_last_error(void) { return last_error(); }
 int64_t sprc_launch_count(void) { return launch_count(); }
+int sprc_set_act_dtype(int fp16) {
+  if (fp16 != 0 && fp16 != 1) return set_error(-22, "sprc_set_act_dtype: 0 (bf16) or 1 (fp16)");
+  set_act_fp16(fp16);
+  return 0;
+}
 int sprc_profile(int enable) {
   prof_set(enable != 0);
   return 0;

@@ -19,7 +19,7 @@ namespace sprc {
 
 static constexpr int ATT_WARPS = 6;
 
-template <int DHP>
+template <int DHP, bool FP16>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDesc a) {
   constexpr int LDS = DHP + 8;    // padded smem row (elements): conflict-free ldmatrix
   constexpr int KS = DHP / 16;    // k-steps of Q K^T
@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
           const int col = ks * 16 + ((lane >> 3) & 1) * 8;
           uint32_t r0, r1, r2, r3;
           ldsm_x4(smem_u32(sK + (size_t)key * LDS + col), r0, r1, r2, r3);
-          mma_bf16_16816(s[np * 2], aq[ks], r0, r1);
-          mma_bf16_16816(s[np * 2 + 1], aq[ks], r2, r3);
+          mma_16816<FP16>(s[np * 2], aq[ks], r0, r1);
+          mma_16816<FP16>(s[np * 2 + 1], aq[ks], r2, r3);
         }
       }
       // ---- scale + mask, chunk row max ----
@@ -148,18 +148,18 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        pa[0] = pack_act(s[2 * kk][0], s[2 * kk][1], FP16);
+        pa[1] = pack_act(s[2 * kk][2], s[2 * kk][3], FP16);
+        pa[2] = pack_act(s[2 * kk + 1][0], s[2 * kk + 1][1], FP16);
+        pa[3] = pack_act(s[2 * kk + 1][2], s[2 * kk + 1][3], FP16);
 #pragma unroll
         for (int dp = 0; dp < DT / 2; ++dp) {
           const int key = c0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
           const int col = (dp * 2 + (lane >> 4)) * 8;
           uint32_t r0, r1, r2, r3;
           ldsm_x4_t(smem_u32(sV + (size_t)key * LDS + col), r0, r1, r2, r3);
-          mma_bf16_16816(o[dp * 2], pa, r0, r1);
-          mma_bf16_16816(o[dp * 2 + 1], pa, r2, r3);
+          mma_16816<FP16>(o[dp * 2], pa, r0, r1);
+          mma_16816<FP16>(o[dp * 2 + 1], pa, r2, r3);
         }
       }
     }
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
       if (col < a.dh) {
         if (r_lo < a.Lq)
           *reinterpret_cast<uint32_t*>(a.O + ((long long)b * a.q_batch_rows + r_lo) * a.ldo + h * a.dh + col) =
-              pack_bf16(o[dt][0] * inv_lo, o[dt][1] * inv_lo);
+              pack_act(o[dt][0] * inv_lo, o[dt][1] * inv_lo, FP16);
         if (r_hi < a.Lq)
           *reinterpret_cast<uint32_t*>(a.O + ((long long)b * a.q_batch_rows + r_hi) * a.ldo + h * a.dh + col) =
-              pack_bf16(o[dt][2] * inv_hi, o[dt][3] * inv_hi);
+              pack_act(o[dt][2] * inv_hi, o[dt][3] * inv_hi, FP16);
       }
     }
   }
@@ -189,19 +189,19 @@ int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
 bool attention_tc_eligible(const AttnDesc& a);               // attention_tc.cu
 int attention_tc(const AttnDesc& a, cudaStream_t st);
 
-template <int DHP>
+template <int DHP, bool FP16>
 static int launch_attention(const AttnDesc& a, cudaStream_t st) {
   const int Lkp = (a.Lk + 63) & ~63;
   const size_t smem = ((size_t)2 * Lkp + ATT_WARPS * 16) * (DHP + 8) * sizeof(bf16) + (size_t)Lkp * sizeof(float);
   SPRC_REQUIRE(smem <= 227 * 1024, "attention: Lk=%d needs %zu B of shared memory", a.Lk, smem);
   static size_t configured = 0;
   if (smem > configured) {
-    SPRC_CUDA(cudaFuncSetAttribute(attention_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPRC_CUDA(cudaFuncSetAttribute(attention_kernel<DHP, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid(a.H, a.B);
   prof_begin(st);
-  attention_kernel<DHP><<<grid, ATT_WARPS * 32, smem, st>>>(a);
+  attention_kernel<DHP, FP16><<<grid, ATT_WARPS * 32, smem, st>>>(a);
   if (prof_enabled()) {
     char tag[56];
     snprintf(tag, sizeof(tag), "B%d H%d dh%d Lq%d Lk%d", a.B, a.H, a.dh, a.Lq, a.Lk);
@@ -222,8 +222,9 @@ int attention(const AttnDesc& a, cudaStream_t st) {
   if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // Q-Former shapes
   static const bool legacy = getenv("SPRC_ATTN_MMA_SYNC") != nullptr;  // A/B switch for tests
   if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT: tcgen05
-  if (a.dh <= 64) return launch_attention<64>(a, st);
-  return launch_attention<96>(a, st);
+  if (act_fp16()) return a.dh <= 64 ? launch_attention<64, true>(a, st) : launch_attention<96, true>(a, st);
+  if (a.dh <= 64) return launch_attention<64, false>(a, st);
+  return launch_attention<96, false>(a, st);
 }
 
 }  // namespace sprc

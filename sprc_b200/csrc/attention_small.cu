@@ -35,7 +35,7 @@ struct SmallAttnLayout {
   int stage_bytes;  // ITEMS items
 };
 
-template <int NQT, int KSPLIT>
+template <int NQT, int KSPLIT, bool FP16>
 __global__ void __launch_bounds__(SA_WARPS * 32)
 attention_small_kernel(const AttnDesc a, const SmallAttnLayout lay, const int nstages) {
   constexpr int ITEMS = SA_WARPS / (NQT * KSPLIT);
@@ -158,8 +158,8 @@ attention_small_kernel(const AttnDesc a, const SmallAttnLayout lay, const int ns
             const int col = kq * 16 + ((lane >> 3) & 1) * 8;
             uint32_t r0, r1, r2, r3;
             ldsm_x4(smem_u32(sK + (size_t)key * SA_LDS + col), r0, r1, r2, r3);
-            mma_bf16_16816(s[np * 2], aq[kq], r0, r1);
-            mma_bf16_16816(s[np * 2 + 1], aq[kq], r2, r3);
+            mma_16816<FP16>(s[np * 2], aq[kq], r0, r1);
+            mma_16816<FP16>(s[np * 2 + 1], aq[kq], r2, r3);
           }
         }
         float mx_lo = -INFINITY, mx_hi = -INFINITY;
@@ -205,18 +205,18 @@ attention_small_kernel(const AttnDesc a, const SmallAttnLayout lay, const int ns
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t pa[4];
-          pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-          pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-          pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-          pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+          pa[0] = pack_act(s[2 * kk][0], s[2 * kk][1], FP16);
+          pa[1] = pack_act(s[2 * kk][2], s[2 * kk][3], FP16);
+          pa[2] = pack_act(s[2 * kk + 1][0], s[2 * kk + 1][1], FP16);
+          pa[3] = pack_act(s[2 * kk + 1][2], s[2 * kk + 1][3], FP16);
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {
             const int key = c0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
             const int col = (dp * 2 + (lane >> 4)) * 8;
             uint32_t r0, r1, r2, r3;
             ldsm_x4_t(smem_u32(sV + (size_t)key * SA_LDS + col), r0, r1, r2, r3);
-            mma_bf16_16816(o[dp * 2], pa, r0, r1);
-            mma_bf16_16816(o[dp * 2 + 1], pa, r2, r3);
+            mma_16816<FP16>(o[dp * 2], pa, r0, r1);
+            mma_16816<FP16>(o[dp * 2 + 1], pa, r2, r3);
           }
         }
       }
@@ -278,17 +278,17 @@ attention_small_kernel(const AttnDesc a, const SmallAttnLayout lay, const int ns
         const int col = dt * 8 + (lane & 3) * 2;
         if (r_lo < a.Lq)
           *reinterpret_cast<uint32_t*>(a.O + ((long long)b * a.q_batch_rows + r_lo) * a.ldo + h * 64 + col) =
-              pack_bf16(o[dt][0] * inv_lo, o[dt][1] * inv_lo);
+              pack_act(o[dt][0] * inv_lo, o[dt][1] * inv_lo, FP16);
         if (r_hi < a.Lq)
           *reinterpret_cast<uint32_t*>(a.O + ((long long)b * a.q_batch_rows + r_hi) * a.ldo + h * 64 + col) =
-              pack_bf16(o[dt][2] * inv_hi, o[dt][3] * inv_hi);
+              pack_act(o[dt][2] * inv_hi, o[dt][3] * inv_hi, FP16);
       }
     }
     __syncthreads();  // every warp is done with this stage (and with sPart) before it is refilled
   }
 }
 
-template <int NQT, int KSPLIT>
+template <int NQT, int KSPLIT, bool FP16>
 static int launch_small(const AttnDesc& a, cudaStream_t st) {
   constexpr int ITEMS = SA_WARPS / (NQT * KSPLIT);
   SmallAttnLayout lay;
@@ -304,7 +304,7 @@ static int launch_small(const AttnDesc& a, cudaStream_t st) {
   SPRC_REQUIRE(smem <= 227 * 1024, "attention_small: Lk=%d needs %zu B of shared memory", a.Lk, smem);
   static size_t configured = 0;
   if (smem > configured) {
-    SPRC_CUDA(cudaFuncSetAttribute(attention_small_kernel<NQT, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPRC_CUDA(cudaFuncSetAttribute(attention_small_kernel<NQT, KSPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     configured = smem;
   }
@@ -313,7 +313,7 @@ static int launch_small(const AttnDesc& a, cudaStream_t st) {
   int grid = device_sm_count() * ctas_per_sm;
   if (grid > n_iters) grid = n_iters;
   prof_begin(st);
-  attention_small_kernel<NQT, KSPLIT><<<grid, SA_WARPS * 32, smem, st>>>(a, lay, nstages);
+  attention_small_kernel<NQT, KSPLIT, FP16><<<grid, SA_WARPS * 32, smem, st>>>(a, lay, nstages);
   if (prof_enabled()) {
     char tag[56];
     snprintf(tag, sizeof(tag), "B%d H%d dh%d Lq%d Lk%d", a.B, a.H, a.dh, a.Lq, a.Lk);
@@ -326,10 +326,16 @@ static int launch_small(const AttnDesc& a, cudaStream_t st) {
 }
 
 int attention_small(const AttnDesc& a, cudaStream_t st) {
-  if (a.Lk > 64 && a.Lq > 32) return launch_small<4, 2>(a, st);  // (not on the reference path)
-  if (a.Lk > 64) return launch_small<2, 4>(a, st);            // cross-attention, Lq <= 32
-  if (a.Lq > 32) return launch_small<4, 1>(a, st);            // self-attention S = 64
-  return launch_small<2, 1>(a, st);                           // self-attention S = 32
+  if (act_fp16()) {
+    if (a.Lk > 64 && a.Lq > 32) return launch_small<4, 2, true>(a, st);
+    if (a.Lk > 64) return launch_small<2, 4, true>(a, st);
+    if (a.Lq > 32) return launch_small<4, 1, true>(a, st);
+    return launch_small<2, 1, true>(a, st);
+  }
+  if (a.Lk > 64 && a.Lq > 32) return launch_small<4, 2, false>(a, st);  // (not on the reference path)
+  if (a.Lk > 64) return launch_small<2, 4, false>(a, st);            // cross-attention, Lq <= 32
+  if (a.Lq > 32) return launch_small<4, 1, false>(a, st);            // self-attention S = 64
+  return launch_small<2, 1, false>(a, st);                           // self-attention S = 32
 }
 
 }  // namespace sprc

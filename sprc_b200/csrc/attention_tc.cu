@@ -39,6 +39,7 @@ struct TcAttnParams {
   int B, H, L;        // images, heads, tokens (257)
   int ldo;            // output row pitch (elements)
   float scale_log2;   // scale * log2(e)
+  int fp16;           // operand format
   bf16* O;
 };
 
@@ -182,9 +183,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
-    constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DHP) | (1u << 16);  // B operand MN-major
+    const uint32_t idesc_s256 = umma_idesc_16(128, 256, p.fp16);
+    const uint32_t idesc_s16 = umma_idesc_16(128, 16, p.fp16);
+    const uint32_t idesc_pv = umma_idesc_16(128, DHP, p.fp16) | (1u << 16);  // B operand MN-major
     uint32_t kv_ph = 0, q_ph = 0, p_ph = 0, oe_ph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       mbar_wait(kv_full, kv_ph);
@@ -286,7 +287,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               if (key >= p.L) e0 = 0.f;
               if (key + 1 >= p.L) e1 = 0.f;
               sum += e0 + e1;
-              pk[j / 2] = pack_bf16(e0, e1);
+              pk[j / 2] = pack_act(e0, e1, p.fp16);
             }
             tmem_st16(p_addr + blk * 16, pk);
           }
@@ -298,7 +299,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               const float e0 = ex2_approx(fmaf(__uint_as_float(sr[64 + j]), p.scale_log2, -moff));
               const float e1 = ex2_approx(fmaf(__uint_as_float(sr[64 + j + 1]), p.scale_log2, -moff));
               sum += e0 + e1;
-              pk[j / 2] = pack_bf16(e0, e1);
+              pk[j / 2] = pack_act(e0, e1, p.fp16);
             }
             tmem_st8(p_addr + 32, pk);
           }
@@ -332,17 +333,17 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int j = 0; j < 16; j += 8)
               *reinterpret_cast<uint4*>(orow + j) = make_uint4(
-                  pack_bf16(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv),
-                  pack_bf16(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv),
-                  pack_bf16(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv),
-                  pack_bf16(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv));
+                  pack_act(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv, p.fp16),
+                  pack_act(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv, p.fp16),
+                  pack_act(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv, p.fp16),
+                  pack_act(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv, p.fp16));
             if constexpr (OC == 24) {
               if (seg * OC + 16 < DH)
                 *reinterpret_cast<uint4*>(orow + 16) = make_uint4(
-                    pack_bf16(__uint_as_float(r2[0]) * inv, __uint_as_float(r2[1]) * inv),
-                    pack_bf16(__uint_as_float(r2[2]) * inv, __uint_as_float(r2[3]) * inv),
-                    pack_bf16(__uint_as_float(r2[4]) * inv, __uint_as_float(r2[5]) * inv),
-                    pack_bf16(__uint_as_float(r2[6]) * inv, __uint_as_float(r2[7]) * inv));
+                    pack_act(__uint_as_float(r2[0]) * inv, __uint_as_float(r2[1]) * inv, p.fp16),
+                    pack_act(__uint_as_float(r2[2]) * inv, __uint_as_float(r2[3]) * inv, p.fp16),
+                    pack_act(__uint_as_float(r2[4]) * inv, __uint_as_float(r2[5]) * inv, p.fp16),
+                    pack_act(__uint_as_float(r2[6]) * inv, __uint_as_float(r2[7]) * inv, p.fp16));
             }
           }
         }
@@ -376,6 +377,7 @@ static int launch_tc(const AttnDesc& a, cudaStream_t st) {
   p.L = a.Lq;
   p.ldo = a.ldo;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.fp16 = act_fp16();
   p.O = a.O;
   static bool attr_set = false;
   if (!attr_set) {

@@ -36,6 +36,9 @@ const char* last_error();
   } while (0)
 
 int device_sm_count();
+// 16-bit activation / operand format of the whole library: 0 = bf16 (default), 1 = fp16
+int act_fp16();
+void set_act_fp16(int on);
 
 // ------------------------------------------------------------------------------------------------
 // GEMM:  C[M,N] = epilogue( A[M,K] (bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw) )

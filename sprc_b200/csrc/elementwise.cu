@@ -25,7 +25,7 @@ template <int MAXV>  // float4 vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, int grp_rows, int grp_stride, float* out_f32,
-                 bf16* out_bf16) {
+                 bf16* out_bf16, int fp16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -71,7 +71,7 @@ layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* 
       if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)prow * width)[c] = o;
       if (out_bf16)
         reinterpret_cast<uint2*>(out_bf16 + (size_t)prow * width)[c] =
-            make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            make_uint2(pack_act(o.x, o.y, fp16), pack_act(o.z, o.w, fp16));
     }
   }
 }
@@ -85,10 +85,10 @@ int layernorm(const float* x, int rows, int width, const float* gamma, const flo
   prof_begin(st);
   if (width <= 32 * 4 * 6)
     layernorm_kernel<6><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32,
-                                                   out_bf16);
+                                                   out_bf16, act_fp16());
   else
     layernorm_kernel<12><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride,
-                                                    out_f32, out_bf16);
+                                                    out_f32, out_bf16, act_fp16());
   prof_end(PROF_ELEMWISE, 0.0, (double)rows * width * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)), st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
@@ -99,7 +99,8 @@ int layernorm(const float* x, int rows, int width, const float* gamma, const flo
 // patch extraction: one CTA per (image, patch-row of 16 patches); coalesced reads of 14 image rows
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int ldp) {
+im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches_, int ldp, int fp16) {
+  unsigned short* patches = reinterpret_cast<unsigned short*>(patches_);
   const int b = blockIdx.x >> 4;
   const int py = blockIdx.x & 15;
   // element (c, ky, x) with x in [0,224): source img[b][c][py*14+ky][x]; dest patch (py*16 + x/14),
@@ -110,20 +111,20 @@ im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int ldp
     const int c = i / (224 * 14);
     const float v = img[(((size_t)b * 3 + c) * 224 + (py * 14 + ky)) * 224 + x];
     const int px = x / 14, kx = x % 14;
-    patches[((size_t)b * 256 + py * 16 + px) * ldp + c * 196 + ky * 14 + kx] = __float2bfloat16(v);
+    patches[((size_t)b * 256 + py * 16 + px) * ldp + c * 196 + ky * 14 + kx] = to_act(v, fp16);
   }
   // zero the K padding columns [588, ldp)
   const int pad = ldp - 588;
   for (int i = threadIdx.x; i < 16 * pad; i += blockDim.x) {
     const int px = i / pad, j = i % pad;
-    patches[((size_t)b * 256 + py * 16 + px) * ldp + 588 + j] = __float2bfloat16(0.f);
+    patches[((size_t)b * 256 + py * 16 + px) * ldp + 588 + j] = 0;
   }
 }
 
 int im2col_patches(const float* images, int B, bf16* patches, int ldp, cudaStream_t st) {
   SPRC_REQUIRE(ldp >= 588, "im2col: ldp %d < 588", ldp);
   if (B <= 0) return 0;
-  im2col_kernel<<<B * 16, 256, 0, st>>>(images, patches, ldp);
+  im2col_kernel<<<B * 16, 256, 0, st>>>(images, patches, ldp, act_fp16());
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;
@@ -237,9 +238,11 @@ static int launch_convert(const TIn* in, TOut* out, size_t n, cudaStream_t st) {
 }
 
 int convert_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st) {
+  if (act_fp16()) return launch_convert<float, __half>(in, reinterpret_cast<__half*>(out), n, st);
   return launch_convert<float, bf16>(in, out, n, st);
 }
 int convert_f16_to_bf16(const void* in, bf16* out, size_t n, cudaStream_t st) {
+  if (act_fp16()) return launch_convert<__half, __half>(static_cast<const __half*>(in), reinterpret_cast<__half*>(out), n, st);
   return launch_convert<__half, bf16>(static_cast<const __half*>(in), out, n, st);
 }
 int convert_f16_to_f32(const void* in, float* out, size_t n, cudaStream_t st) {
@@ -249,7 +252,7 @@ int convert_f16_to_f32(const void* in, float* out, size_t n, cudaStream_t st) {
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const TIn* __restrict__ table, const int32_t* __restrict__ rows, size_t row_elems,
-                   bf16* __restrict__ out) {
+                   bf16* __restrict__ out, int fp16) {
   const size_t r = blockIdx.x;
   const TIn* src = table + (size_t)rows[r] * row_elems;
   bf16* dst = out + r * row_elems;
@@ -262,7 +265,7 @@ gather_rows_kernel(const TIn* __restrict__ table, const int32_t* __restrict__ ro
     uint2* d2 = reinterpret_cast<uint2*>(dst);
     for (size_t i = threadIdx.x; i < row_elems / 4; i += blockDim.x) {
       const float4 v = s4[i];
-      d2[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      d2[i] = make_uint2(pack_act(v.x, v.y, fp16), pack_act(v.z, v.w, fp16));
     }
   }
 }
@@ -272,9 +275,9 @@ int gather_rows_bf16(const void* table, int table_dtype, const int32_t* rows, in
   SPRC_REQUIRE(row_elems % 8 == 0, "gather_rows: row_elems %zu not a multiple of 8", row_elems);
   if (n_rows <= 0) return 0;
   if (table_dtype == 2)
-    gather_rows_kernel<bf16><<<n_rows, 256, 0, st>>>(static_cast<const bf16*>(table), rows, row_elems, out);
+    gather_rows_kernel<bf16><<<n_rows, 256, 0, st>>>(static_cast<const bf16*>(table), rows, row_elems, out, act_fp16());
   else if (table_dtype == 0)
-    gather_rows_kernel<float><<<n_rows, 256, 0, st>>>(static_cast<const float*>(table), rows, row_elems, out);
+    gather_rows_kernel<float><<<n_rows, 256, 0, st>>>(static_cast<const float*>(table), rows, row_elems, out, act_fp16());
   else
     return set_error(-22, "gather_rows: unsupported table dtype %d", table_dtype);
   count_launch();
@@ -286,7 +289,8 @@ int gather_rows_bf16(const void* table, int table_dtype, const int32_t* rows, in
 // L2 normalisation of 256-wide rows: one warp per row, 8 floats per lane
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-l2norm256_kernel(const float* __restrict__ in, size_t in_row_stride, int rows, float* out_f32, bf16* out_bf16) {
+l2norm256_kernel(const float* __restrict__ in, size_t in_row_stride, int rows, float* out_f32, bf16* out_bf16,
+                 int fp16) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -303,14 +307,15 @@ l2norm256_kernel(const float* __restrict__ in, size_t in_row_stride, int rows, f
   }
   if (out_bf16) {
     uint4* d = reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 256) + lane;
-    *d = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    *d = make_uint4(pack_act(o[0], o[1], fp16), pack_act(o[2], o[3], fp16), pack_act(o[4], o[5], fp16),
+                    pack_act(o[6], o[7], fp16));
   }
 }
 
 int l2norm_rows256(const float* in, size_t in_row_stride, int rows, float* out_f32, bf16* out_bf16,
                    cudaStream_t st) {
   if (rows <= 0) return 0;
-  l2norm256_kernel<<<(rows + 7) / 8, 256, 0, st>>>(in, in_row_stride, rows, out_f32, out_bf16);
+  l2norm256_kernel<<<(rows + 7) / 8, 256, 0, st>>>(in, in_row_stride, rows, out_f32, out_bf16, act_fp16());
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

@@ -36,6 +36,7 @@ struct GemmKernelParams {
   bf16* out_bf16;
   int ldc;
   int act;
+  int fp16;  // operand / bf16-output format: 0 bf16, 1 fp16
 };
 
 template <int BN, int STAGES>
@@ -113,7 +114,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    const uint32_t idesc = umma_idesc_16(BM, BN, p.fp16);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -227,7 +228,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (p.out_f32)
                 *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v0, v1, v2, v3);
               else
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) =
+                    make_uint2(pack_act(v0, v1, p.fp16), pack_act(v2, v3, p.fp16));
             }
           }
         }
@@ -320,6 +322,7 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   p.out_bf16 = d.out_bf16;
   p.ldc = d.ldc;
   p.act = d.act;
+  p.fp16 = act_fp16();
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -369,7 +372,9 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
   const bf16* a = A + prow * lda;
   const bf16* w = W + (size_t)n * ldw;
   float acc = 0.f;
-  for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+  const unsigned short* au = reinterpret_cast<const unsigned short*>(a);
+  const unsigned short* wu = reinterpret_cast<const unsigned short*>(w);
+  for (int k = 0; k < p.K; ++k) acc += from_act(au[k], p.fp16) * from_act(wu[k], p.fp16);
   if (p.bias) acc += p.bias[n];
   if (p.act == ACT_GELU) acc = gelu_erf(acc);
   if (p.act == ACT_QUICKGELU) acc = quick_gelu(acc);
@@ -378,7 +383,7 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
   if (p.out_f32)
     p.out_f32[off] = acc;
   else
-    p.out_bf16[off] = __float2bfloat16(acc);
+    reinterpret_cast<unsigned short*>(p.out_bf16)[off] = to_act(acc, p.fp16);
 }
 
 int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st) {
@@ -394,6 +399,7 @@ int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st) {
   p.out_bf16 = d.out_bf16;
   p.ldc = d.ldc;
   p.act = d.act;
+  p.fp16 = act_fp16();
   dim3 grid((d.N + 127) / 128, d.M);
   gemm_simt_kernel<<<grid, 128, 0, st>>>(d.A, d.W, p, d.lda, d.ldw);
   SPRC_CUDA(cudaGetLastError());

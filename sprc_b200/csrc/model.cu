@@ -61,6 +61,7 @@ int Model::init(int kind, int vit_depth, int qf_layers_, int max_images_, int ma
                 int device_) {
   SPRC_REQUIRE(kind == SPRC_VIT_EVA_G || kind == SPRC_VIT_CLIP_L, "unknown vit_kind %d", kind);
   device = device_;
+  act_dtype_fp16 = act_fp16();
   SPRC_CUDA(cudaSetDevice(device));
   {
     cudaDeviceProp prop;
@@ -347,7 +348,15 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
     else
       launch_pack<bf16, float>(staging, rows, s.cols, dst, s.ld);
   } else {
-    if (dtype == SPRC_F32)
+    // 16-bit GEMM operands are stored in the library's active format (bf16, or fp16 in fp16 mode)
+    if (act_fp16()) {
+      if (dtype == SPRC_F32)
+        launch_pack<float, __half>(staging, rows, s.cols, dst, s.ld);
+      else if (dtype == SPRC_F16)
+        launch_pack<__half, __half>(staging, rows, s.cols, dst, s.ld);
+      else
+        launch_pack<bf16, __half>(staging, rows, s.cols, dst, s.ld);
+    } else if (dtype == SPRC_F32)
       launch_pack<float, bf16>(staging, rows, s.cols, dst, s.ld);
     else if (dtype == SPRC_F16)
       launch_pack<__half, bf16>(staging, rows, s.cols, dst, s.ld);

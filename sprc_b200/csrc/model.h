@@ -50,6 +50,7 @@ struct Model {
   int qf_layers = 12, n_cross = 6;
   int max_images = 0, max_queries = 0, max_pairs = 0;
   int device = 0;
+  int act_dtype_fp16 = 0;  // format the weights were packed in (library mode at creation)
   int vocab = 30523;
   static constexpr int KP = 592;  // patch K (588) padded to a 16-byte pitch
 

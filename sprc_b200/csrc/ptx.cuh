@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -123,11 +124,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16, A/B = bf16 K-major, D = fp32.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4)                               // D format: f32
-         | (1u << 7)                             // A format: bf16
-         | (1u << 10)                            // B format: bf16
+// Instruction descriptor, kind::f16, A/B = bf16 (format 1) or fp16 (format 0) K-major, D = fp32.
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fp16) {
+  return (1u << 4)                                // D format: f32
+         | ((fp16 ? 0u : 1u) << 7)                // A format
+         | ((fp16 ? 0u : 1u) << 10)               // B format
          | (static_cast<uint32_t>(N >> 3) << 17)  // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24); // M / 16
 }
@@ -208,6 +209,23 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit activation type is a run-time mode of the library: bf16 (default) or fp16 (the reference's own
+// autocast precision, blip2.py:36-44).  Buffers are typed `bf16*` but hold whichever format is active.
+__device__ __forceinline__ uint32_t pack_act(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ unsigned short to_act(float a, int fp16) {
+  if (fp16) return __half_as_ushort(__float2half_rn(a));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
+__device__ __forceinline__ float from_act(unsigned short u, int fp16) {
+  if (fp16) return __half2float(__ushort_as_half(u));
+  return __bfloat162float(__ushort_as_bfloat16(u));
 }
 // erf-GELU (nn.GELU default, eva_vit.py:55-56 / Qformer.py:360): 0.5 x (1 + erf(x / sqrt 2)) with the
 // Abramowitz-Stegun 7.1.26 rational erf (|abs err| <= 1.5e-7, far below the bf16 rounding of the output);

@@ -22,6 +22,10 @@ int set_error(int code, const char* fmt, ...) {
 
 const char* last_error() { return g_err; }
 
+static int g_act_fp16 = 0;
+int act_fp16() { return g_act_fp16; }
+void set_act_fp16(int on) { g_act_fp16 = on ? 1 : 0; }
+
 int device_sm_count() {
   static int sms[64] = {0};
   int dev = 0;

@@ -59,6 +59,7 @@ struct ScanParams {
   int k;
   int qtiles, splits;
   long long imgs_per_split;  // even
+  int fp16;                  // operand format of queries / gallery
   float* out_full;           // [Q, N] or null
   u64* cand;                 // [splits][k][qtiles*128] or null
 };
@@ -128,7 +129,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_bf16(SQ, ST);
+    const uint32_t idesc = umma_idesc_16(SQ, ST, p.fp16);
     mbar_wait(q_bar, 0);
     tc_fence_after();
     int stage = 0, as = 0;
@@ -391,6 +392,7 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
   p.qtiles = qtiles;
   p.splits = splits;
   p.imgs_per_split = ips;
+  p.fp16 = act_fp16();
   p.out_full = out_full;
   p.cand = nullptr;
   u64* cand = static_cast<u64*>(workspace);
@@ -443,7 +445,7 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gather_scores_kernel(const bf16* __restrict__ queries, int Q, const bf16* __restrict__ gallery, long long N,
-                     const int32_t* __restrict__ rows, int m, float* __restrict__ out) {
+                     const int32_t* __restrict__ rows, int m, float* __restrict__ out, int fp16) {
   const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pair >= Q * m) return;
   const int lane = threadIdx.x & 31;
@@ -459,14 +461,10 @@ gather_scores_kernel(const bf16* __restrict__ queries, int Q, const bf16* __rest
 #pragma unroll 4
   for (int i = 0; i < 32; ++i) {
     const uint4 a = g[i], b = __ldg(qv + i);
-    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+    const unsigned short* a2 = reinterpret_cast<const unsigned short*>(&a);
+    const unsigned short* b2 = reinterpret_cast<const unsigned short*>(&b);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(b2[j]);
-      acc = fmaf(x.x, y.x, acc);
-      acc = fmaf(x.y, y.y, acc);
-    }
+    for (int j = 0; j < 8; ++j) acc = fmaf(from_act(a2[j], fp16), from_act(b2[j], fp16), acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc = fmaxf(acc, __shfl_xor_sync(0xffffffffu, acc, o));
@@ -477,7 +475,7 @@ int gather_scores(const bf16* queries, int Q, const bf16* gallery, int64_t N, co
                   float* out, cudaStream_t st) {
   if (Q <= 0 || m <= 0) return 0;
   const int pairs = Q * m;
-  gather_scores_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(queries, Q, gallery, N, rows, m, out);
+  gather_scores_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(queries, Q, gallery, N, rows, m, out, act_fp16());
   count_launch();
   SPRC_CUDA(cudaGetLastError());
   return 0;

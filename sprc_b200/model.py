@@ -40,7 +40,7 @@ class Blip2QformerCirAlignPrompt:
     def __init__(self, vit_model="eva_clip_g", img_size=224, drop_path_rate=0, use_grad_checkpoint=False,
                  vit_precision="fp16", freeze_vit=True, num_query_token=32, cross_attention_freq=2, embed_dim=256,
                  max_txt_len=32, *, device=None, max_images=64, max_queries=64, max_pairs=0, vit_depth=0,
-                 qf_layers=0, tokenizer=None):
+                 qf_layers=0, tokenizer=None, act_dtype=None):
         if vit_model not in _VIT:
             raise ValueError("vit model must be eva_clip_g or clip_L")
         if img_size != 224 or num_query_token != 32 or cross_attention_freq != 2 or embed_dim != 256 \
@@ -62,8 +62,17 @@ class Blip2QformerCirAlignPrompt:
         self.max_images, self.max_queries, self.max_pairs = int(max_images), int(max_queries), int(max_pairs)
         self.tokenizer = tokenizer if tokenizer is not None else OfflineBertTokenizer()
         self.training = False
+        # 16-bit operand format of every kernel: bf16 (default) or fp16 (the reference's autocast precision);
+        # SPRC_ACT_DTYPE overrides the default for unchanged reference scripts
+        import os
+
+        act_dtype = act_dtype or os.environ.get("SPRC_ACT_DTYPE", "bf16")
+        if act_dtype not in ("bf16", "fp16"):
+            raise ValueError("act_dtype must be 'bf16' or 'fp16'")
+        self.act_dtype = act_dtype
+        self.act_torch_dtype = torch.float16 if act_dtype == "fp16" else torch.bfloat16
         cfg = L.SprcConfig(_VIT[vit_model][0], int(vit_depth), int(qf_layers), self.max_images, self.max_queries,
-                           self.max_pairs, dev.index)
+                           self.max_pairs, dev.index, 1 if act_dtype == "fp16" else 0)
         h = L.c_void_p()
         with torch.cuda.device(dev):
             L.check(self._lib.sprc_create(L.ctypes.byref(cfg), L.ctypes.byref(h)))
@@ -179,11 +188,11 @@ class Blip2QformerCirAlignPrompt:
             if want_f32:
                 out["feats"] = torch.empty(B, 32, 256, device=self._device)
             if want_bf16:
-                out["feats_bf16"] = torch.empty(B, 32, 256, device=self._device, dtype=torch.bfloat16)
+                out["feats_bf16"] = torch.empty(B, 32, 256, device=self._device, dtype=self.act_torch_dtype)
             if want_raws_f32:
                 out["raws"] = torch.empty(B, 257, Dv, device=self._device)
             if want_raws_bf16:
-                out["raws_bf16"] = torch.empty(B, 257, Dv, device=self._device, dtype=torch.bfloat16)
+                out["raws_bf16"] = torch.empty(B, 257, Dv, device=self._device, dtype=self.act_torch_dtype)
             for s in range(0, B, self.max_images):
                 e = min(B, s + self.max_images)
                 sl = lambda t: L.ptr(t[s:e]) if t is not None else L.c_void_p(0)  # noqa: E731
@@ -193,11 +202,12 @@ class Blip2QformerCirAlignPrompt:
         return out
 
     def encode_query(self, reference_embeds: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
-                     ref_rows: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+                     ref_rows: Optional[torch.Tensor] = None, out_dtype=None) -> torch.Tensor:
         """fusion_feats [Bq,256].  `reference_embeds` is [Bq,257,Dv] (fp32/bf16) or, with `ref_rows`
         (int32 [Bq]), a resident table [*,257,Dv] whose rows are gathered on the device."""
+        out_dtype = out_dtype or self.act_torch_dtype
         ref = reference_embeds
-        if ref.dtype not in (torch.float32, torch.bfloat16):
+        if ref.dtype not in (torch.float32, self.act_torch_dtype):
             ref = ref.float()
         ref = ref.to(self._device).contiguous()
         ids = input_ids.to(self._device, torch.int64).contiguous()
@@ -209,9 +219,9 @@ class Blip2QformerCirAlignPrompt:
             for s in range(0, Bq, self.max_queries):
                 e = min(Bq, s + self.max_queries)
                 of = L.ptr(out[s:e]) if out_dtype == torch.float32 else L.c_void_p(0)
-                ob = L.ptr(out[s:e]) if out_dtype == torch.bfloat16 else L.c_void_p(0)
+                ob = L.ptr(out[s:e]) if out_dtype != torch.float32 else L.c_void_p(0)
                 rp = L.ptr(ref) if rows is not None else L.ptr(ref[s:e])
-                L.check(self._lib.sprc_encode_query(self._h, rp, _DTYPES[ref.dtype],
+                L.check(self._lib.sprc_encode_query(self._h, rp, L.F32 if ref.dtype == torch.float32 else L.BF16,
                                                     L.ptr(rows[s:e]) if rows is not None else L.c_void_p(0),
                                                     L.ptr(ids[s:e]), L.ptr(am[s:e]), e - s, of, ob, self._stream()))
         return out
@@ -219,9 +229,9 @@ class Blip2QformerCirAlignPrompt:
     def sim_topk(self, queries_bf16: torch.Tensor, gallery_bf16: torch.Tensor, k: int = 0, row_offset: int = 0,
                  want_full: bool = False):
         """-> (scores [Q,k] fp32, idx [Q,k] int32, full [Q,N] fp32 or None)."""
-        q = queries_bf16.to(self._device, torch.bfloat16).contiguous()
+        q = queries_bf16.to(self._device, self.act_torch_dtype).contiguous()
         g = gallery_bf16
-        assert g.dtype == torch.bfloat16 and g.is_contiguous() and g.device == self._device
+        assert g.dtype == self.act_torch_dtype and g.is_contiguous() and g.device == self._device
         Q, N = q.shape[0], g.shape[0]
         sc = ix = full = None
         with torch.cuda.device(self._device):
@@ -235,7 +245,7 @@ class Blip2QformerCirAlignPrompt:
         return sc, ix, full
 
     def gather_scores(self, queries_bf16, gallery_bf16, rows: torch.Tensor) -> torch.Tensor:
-        q = queries_bf16.to(self._device, torch.bfloat16).contiguous()
+        q = queries_bf16.to(self._device, self.act_torch_dtype).contiguous()
         rows = rows.to(self._device, torch.int32).contiguous()
         out = torch.empty(rows.shape, device=self._device)
         with torch.cuda.device(self._device):
@@ -282,11 +292,11 @@ class Blip2QformerCirAlignPrompt:
         return o["feats"], o["raws"]
 
     def _gallery_bf16(self, target_feats: torch.Tensor) -> torch.Tensor:
-        if target_feats.dtype == torch.bfloat16 and target_feats.device == self._device:
+        if target_feats.dtype == self.act_torch_dtype and target_feats.device == self._device:
             return target_feats.contiguous()
         key = (target_feats.data_ptr(), tuple(target_feats.shape), target_feats._version, target_feats.device)
         if self._gallery_cache is None or self._gallery_cache[0] != key:
-            self._gallery_cache = (key, target_feats.to(self._device, torch.bfloat16).contiguous())
+            self._gallery_cache = (key, target_feats.to(self._device, self.act_torch_dtype).contiguous())
         return self._gallery_cache[1]
 
     @torch.no_grad()
@@ -305,7 +315,7 @@ class Blip2QformerCirAlignPrompt:
         tgt = target_embeds.to(self._device)
         R, n = ref.shape[0], tgt.shape[0]
         T = n // R if R > 1 else n
-        table = torch.cat([ref, tgt], dim=0).to(torch.bfloat16).contiguous()
+        table = torch.cat([ref, tgt], dim=0).to(self.act_torch_dtype).contiguous()
         ref_rows = torch.arange(R, device=self._device, dtype=torch.int32)
         cand_rows = torch.arange(R, R + R * T, device=self._device, dtype=torch.int32)
         return self.rerank_rows(table, ref_rows, cand_rows, tok.input_ids, tok.attention_mask, T)

@@ -92,7 +92,7 @@ def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, co
         if keep_raws:
             raws.append(o["raws_bf16"])
         names.extend(batch_names)
-    f = torch.cat(feats) if feats else torch.empty(0, 32, 256, dtype=torch.bfloat16, device=backend.device)
+    f = torch.cat(feats) if feats else torch.empty(0, 32, 256, dtype=getattr(backend, 'act_torch_dtype', torch.bfloat16), device=backend.device)
     r = (torch.cat(raws) if raws else None) if keep_raws else None
     if world > 1:
         gathered = [None] * world
@@ -134,7 +134,7 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
                                      ref_rows=(ref_rows[sel] - index.lo))
             fusion32[sel.to(dev)] = f.float()
         dist.all_reduce(fusion32)  # exactly one rank contributes each row: x + 0 + ... is exact
-        fusion = fusion32.to(torch.bfloat16)
+        fusion = fusion32.to(index.feats.dtype)
     sc, ix, _ = backend.sim_topk(fusion, index.feats, k=k, row_offset=index.lo)
     sub = None
     if subset_rows is not None:
@@ -217,8 +217,7 @@ def as_index(index_features, index_names) -> GalleryIndex:
     if isinstance(index_features, GalleryIndex):
         return index_features
     feats, raws = index_features[0], index_features[-1]
-    return GalleryIndex(feats=feats.to(torch.bfloat16).contiguous(), raws=raws.to(torch.bfloat16).contiguous(),
-                        names=list(index_names))
+    return GalleryIndex(feats=feats.contiguous(), raws=raws.contiguous(), names=list(index_names))
 
 
 class IndexFeatures(tuple):

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 def sim_topk(q, g, k, row_offset=0, want_full=False):
     lib = L.load()
+    L.check(lib.sprc_set_act_dtype(1 if q.dtype == torch.float16 else 0))  # process-wide 16-bit operand format
     Q, N = q.shape[0], g.shape[0]
     sc = torch.empty(Q, k, device="cuda") if k > 0 else None
     ix = torch.empty(Q, k, device="cuda", dtype=torch.int32) if k > 0 else None
@@ -46,6 +47,16 @@ def test_topk_bit_exact_dyadic(Q, N, k):
     assert torch.equal(sc.cpu()[:, :kk], osc[:, :kk])
     if k > N:  # fewer than k gallery rows: the tail is (-inf, -1)
         assert (ix.cpu()[:, N:] == -1).all() and torch.isinf(sc.cpu()[:, N:]).all()
+
+
+def test_topk_bit_exact_dyadic_fp16_mode():
+    """fp16 operand mode (sprc_config.act_dtype = 1): same kernel, fp16 instruction descriptor."""
+    Q, N, k = 70, 1500, 50
+    q = synth.make_dyadic((Q, 256), seed=31).cuda().half()
+    g = synth.make_dyadic((N, 32, 256), seed=32).cuda().half()
+    sc, ix, full = sim_topk(q, g, k, want_full=True)
+    sim, order, osc = oracle_topk(q, g, k)
+    assert torch.equal(full.cpu(), sim) and torch.equal(ix.cpu().long(), order) and torch.equal(sc.cpu(), osc)
 
 
 @pytest.mark.parametrize("k", [100, 200])
@@ -92,6 +103,7 @@ def test_row_offset_and_sharded_merge_equals_single_scan():
         ci.append(i)
     cs, ci = torch.stack(cs), torch.stack(ci)
     lib = L.load()
+    L.check(lib.sprc_set_act_dtype(0))
     ms = torch.empty(Q, k, device="cuda")
     mi = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     L.check(lib.sprc_topk_merge(None, L.ptr(cs), L.ptr(ci), P, Q, k, L.ptr(ms), L.ptr(mi), L.cur_stream()))
