@@ -9,8 +9,10 @@
 //   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) into a STAGES-deep ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators
 //               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2..17 epilogue (four warps per TMEM lane quarter, each draining a quarter of the columns): tcgen05.ld 32 lanes x 32 columns -> bias / GELU / QuickGELU / residual ->
-//               128-bit global stores (fp32 residual stream or bf16 activations)
+//   warps 2..17 epilogue (four warps per TMEM lane quarter, each draining a quarter of the columns): tcgen05.ld
+//               (thread = row) -> bias / GELU / QuickGELU -> 64-byte row pieces into a swizzled 2 KB staging tile ->
+//               one TMA store per 32-row x 64-byte chunk (bf16 activations / fp32), or a TMA reduce-add into the
+//               fp32 residual stream (the residual is never loaded by the SM)
 #include <stdio.h>
 
 #include "common.h"
@@ -37,6 +39,8 @@ struct GemmKernelParams {
   int ldc;
   int act;
   int fp16;  // operand / bf16-output format: 0 bf16, 1 fp16
+  int out_is_f32;  // output element type of tmC
+  int accumulate;  // 1: out_f32 += result (TMA reduce-add; the residual already lives in the output buffer)
 };
 
 template <int BN, int STAGES>
@@ -52,7 +56,7 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmKernelParams p) {
+                         const __grid_constant__ CUtensorMap tmC, const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,6 +76,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -150,99 +155,110 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // Two phases per 16-column chunk.  Phase 1: tcgen05.ld gives each thread ONE ROW x 16 columns; it is
-    // written to this warp's swizzled smem tile.  Phase 2: the warp re-reads the tile so that 4 consecutive
-    // lanes hold one row's 64 contiguous bytes (8 rows per instruction) and applies bias / activation /
-    // residual there - every global load and store then covers whole 32-byte sectors of consecutive
-    // addresses.  (The first version stored row-per-thread, 32 different lines per instruction, and was
-    // epilogue-bound at K = 768.)  Four warps per SMSP keep the GELU math off the critical path.
+    // tcgen05.ld (32x32b) gives each thread ONE ROW x CH consecutive columns.  Bias and activation are applied
+    // there, the row's 64 output bytes (16 fp32 / 32 bf16 columns) go to this warp's staging tile with the
+    // SWIZZLE_64B pattern (16-byte piece j of row r at r*64 + ((j ^ (r >> 1 & 3)) << 4): conflict-free STS.128)
+    // and lane 0 hands the 32-row x 64-byte tile to the TMA: a plain store, or a reduce-add into the fp32
+    // residual stream.  Shared-memory traffic per output byte is one write + one TMA read; the earlier
+    // STS/LDS/STG transpose cost more of the shared-memory pipe than the UMMA operand reads at K = 768 and
+    // paced those GEMMs (profiles/r01_*: 7-8 us per 128x256 tile against 5.8 us of MMA).
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int cpart = (warp - 2) >> 2;   // which quarter of the tile's columns this warp drains
     const uint32_t stile = smem_u32(sEpi) + (warp - 2) * EPI_STAGE_BYTES;
-    const int prow = lane >> 2;          // phase 2: row within an 8-row group
-    const int ppiece = lane & 3;         // phase 2: 16-byte piece (4 fp32 columns) of the 64-byte row
-    constexpr int CPW = BN / 64;         // 16-column chunks per warp
+    const uint32_t srow = stile + lane * 64;
+    const uint32_t sw = (lane >> 1) & 3;
+    const bool out32 = p.out_is_f32 != 0;
+    const int CH = out32 ? 16 : 32;                  // columns per chunk (64 bytes of output per row)
+    const int nchunks = (BN / 4) / CH;               // chunks per warp per tile
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_blocks) * BM;
-      const int n0 = (tile % p.num_n_blocks) * BN;
-      // physical output rows of the 4 rows this lane serves in phase 2 (-1: out of range)
-      long long orow[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = m0 + q * 32 + i * 8 + prow;
-        long long r = m;
-        if (p.grp_rows > 0) r = static_cast<long long>(m >> p.grp_shift) * p.grp_stride + (m & (p.grp_rows - 1));
-        orow[i] = m < p.M ? r : -1;
+      const int m0 = (tile / p.num_n_blocks) * BM + q * 32;   // first row of this warp's 32 rows
+      const int n0 = (tile % p.num_n_blocks) * BN + cpart * (BN / 4);
+      // TMA coordinates of the warp's rows (dense: row m0; grouped: see GemmDesc)
+      int c1 = m0, c2 = 0;
+      if (p.grp_rows > 0) {
+        c2 = m0 >> p.grp_shift;
+        c1 = p.grp_rows >= 32 ? (m0 & (p.grp_rows - 1)) : 0;
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + cpart * (BN / 4));
 #pragma unroll 1
-      for (int cc = 0; cc < CPW; ++cc) {
-        const int c = cpart * CPW + cc;
-        const int n = n0 + c * 16;                 // first column of the chunk (warp-uniform)
-        const bool col_ok = n < p.N;
-        const int ncol = n + ppiece * 4;           // this lane's 4 columns in phase 2
-        // residual and bias do not depend on the accumulator: issue their loads first
-        float4 res[4];
-        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok) {
-          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
-          if (p.residual) {
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int n = n0 + cc * CH;                  // first column of the chunk (warp-uniform)
+        const bool live = n < p.N && m0 < p.M;
+        uint32_t o[16];                              // the row's 64 output bytes
+        if (out32) {
+          tmem_ld16(t_row + cc * 16, o);
+          tmem_ld_wait();
+          if (live) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (orow[i] >= 0)
-                res[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(orow[i]) * p.ldc + ncol);
-          }
-        }
-        uint32_t r[16];
-        tmem_ld16(t_row + c * 16, r);
-        tmem_ld_wait();
-        // phase 1: row `lane`, piece j -> byte offset lane*64 + ((j ^ ((lane >> 1) & 3)) * 16)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(stile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        if (col_ok) {
-          uint4 raws[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + prow;
-            raws[i] = lds128(stile + row * 64 + ((ppiece ^ ((row >> 1) & 3)) << 4));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 raw = raws[i];
-            float v0 = __uint_as_float(raw.x) + bia.x, v1 = __uint_as_float(raw.y) + bia.y;
-            float v2 = __uint_as_float(raw.z) + bia.z, v3 = __uint_as_float(raw.w) + bia.w;
-            if (p.act == ACT_GELU) {
-              v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
-            } else if (p.act == ACT_QUICKGELU) {
-              v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
+            for (int j = 0; j < 4; ++j) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+              float v0 = __uint_as_float(o[4 * j]) + b.x, v1 = __uint_as_float(o[4 * j + 1]) + b.y;
+              float v2 = __uint_as_float(o[4 * j + 2]) + b.z, v3 = __uint_as_float(o[4 * j + 3]) + b.w;
+              if (p.act == ACT_GELU) {
+                v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
+              } else if (p.act == ACT_QUICKGELU) {
+                v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
+              }
+              o[4 * j] = __float_as_uint(v0), o[4 * j + 1] = __float_as_uint(v1);
+              o[4 * j + 2] = __float_as_uint(v2), o[4 * j + 3] = __float_as_uint(v3);
             }
-            if (orow[i] >= 0) {
-              const size_t off = static_cast<size_t>(orow[i]) * p.ldc + ncol;
-              if (p.residual) v0 += res[i].x, v1 += res[i].y, v2 += res[i].z, v3 += res[i].w;
-              if (p.out_f32)
-                *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v0, v1, v2, v3);
-              else
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) =
-                    make_uint2(pack_act(v0, v1, p.fp16), pack_act(v2, v3, p.fp16));
+          }
+        } else {
+          uint32_t r[32];
+          tmem_ld32(t_row + cc * 32, r);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+              float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
+              float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
+              if (p.act == ACT_GELU) {
+                v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
+              } else if (p.act == ACT_QUICKGELU) {
+                v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
+              }
+              o[2 * j] = pack_act(v0, v1, p.fp16);
+              o[2 * j + 1] = pack_act(v2, v3, p.fp16);
             }
           }
         }
-        __syncwarp();  // the tile is rewritten by the next chunk's phase 1
+        if (cc == nchunks - 1) {
+          // the accumulator stage is in registers: hand it back to the MMA warp before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (live) {
+          if (lane == 0) bulk_wait_read0();  // the previous chunk's TMA store has read the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(srow + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accumulate)
+              tma_reduce_add_3d(&tmC, stile, n, c1, c2);
+            else
+              tma_store_3d(&tmC, stile, n, c1, c2);
+            bulk_commit();
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (lane == 0) bulk_wait0();  // stores performed before the CTA (and its shared memory) retires
   }
 
   tc_fence_before();
@@ -272,29 +288,66 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor [d2][d1][d0] with d0 contiguous; strides in elements; box {b0,b1,b2}; 128B swizzle.
-int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
-                   uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank) {
+// Tensor [d2][d1][d0] with d0 contiguous, element size esz (2: bf16/fp16, 4: fp32); strides in elements;
+// box {b0,b1,b2}; swizzle_bytes 128 (operand tiles) or 64 (epilogue staging tiles).
+static int make_tmap(CUtensorMap* tm, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank,
+                     int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(-38, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint64_t strides[2] = {stride1 * esz, stride2 * esz};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (rank == 3 && (strides[1] & 15)))
     return set_error(-22, "TMA operand must be 16-byte aligned (ptr %p, pitches %llu/%llu B)", ptr,
                      (unsigned long long)strides[0], (unsigned long long)strides[1]);
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(-22, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                   uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank) {
+  return make_tmap(tm, ptr, 2, d0, d1, d2, stride1, stride2, b0, b1, b2, rank, 128);
+}
+
+// out[row, 0:N] = src[row, 0:N] over the (possibly grouped) rows of a GemmDesc: used only when the residual
+// does not already live in the output buffer (the model always accumulates in place).
+__global__ void __launch_bounds__(256)
+copy_rows_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int n4, int ld, int grp_rows,
+                     int grp_stride) {
+  const long long total = static_cast<long long>(M) * n4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / n4), c = static_cast<int>(i % n4);
+    long long r = m;
+    if (grp_rows > 0) r = static_cast<long long>(m / grp_rows) * grp_stride + (m % grp_rows);
+    reinterpret_cast<float4*>(dst + r * ld)[c] = reinterpret_cast<const float4*>(src + r * ld)[c];
+  }
 }
 
 template <int BN, int STAGES>
 static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
+  {
+    // output map: 64-byte row pieces (16 fp32 / 32 bf16 columns) x the 32 rows one epilogue warp owns
+    const bool f32 = d.out_f32 != nullptr;
+    const void* out = f32 ? static_cast<const void*>(d.out_f32) : static_cast<const void*>(d.out_bf16);
+    const int esz = f32 ? 4 : 2;
+    const uint32_t ch = f32 ? 16 : 32;
+    if (d.grp_rows > 0) {
+      const uint32_t br = d.grp_rows < 32 ? d.grp_rows : 32;
+      SPRC_TRY(make_tmap(&tmC, out, esz, d.N, d.grp_rows, d.M / d.grp_rows, d.ldc, (uint64_t)d.grp_stride * d.ldc,
+                         ch, br, 32 / br, 3, 64));
+    } else {
+      SPRC_TRY(make_tmap(&tmC, out, esz, d.N, d.M, 1, d.ldc, (uint64_t)d.M * d.ldc, ch, 32, 1, 3, 64));
+    }
+  }
   if (d.grp_rows > 0) {
     const int groups = d.M / d.grp_rows;
     SPRC_TRY(make_tmap_bf16(&tmA, d.A, d.K, d.grp_rows, groups, d.lda, (uint64_t)d.grp_stride * d.lda, BK,
@@ -323,6 +376,16 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   p.ldc = d.ldc;
   p.act = d.act;
   p.fp16 = act_fp16();
+  p.out_is_f32 = d.out_f32 ? 1 : 0;
+  p.accumulate = d.residual ? 1 : 0;
+  if (d.residual && d.residual != d.out_f32) {
+    const long long total = (long long)d.M * (d.N / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    copy_rows_f32_kernel<<<(int)blocks, 256, 0, st>>>(d.residual, d.out_f32, d.M, d.N / 4, d.ldc, d.grp_rows,
+                                                      d.grp_stride);
+    count_launch();
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -333,7 +396,7 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   prof_begin(st);
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, p);
   if (prof_enabled()) {
     char tag[56];
     snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d bn%d", d.M, d.N, d.K, d.grp_rows, d.act,
@@ -352,6 +415,8 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   SPRC_REQUIRE(d.K % 8 == 0 && d.lda % 8 == 0 && d.ldw % 8 == 0 && d.ldc % 8 == 0,
                "gemm: K/lda/ldw/ldc must be multiples of 8 (K=%d lda=%d ldw=%d ldc=%d)", d.K, d.lda, d.ldw, d.ldc);
   SPRC_REQUIRE((d.out_f32 != nullptr) != (d.out_bf16 != nullptr), "gemm: exactly one output pointer");
+  SPRC_REQUIRE(!d.residual || d.out_f32, "gemm: a residual needs the fp32 output");
+  SPRC_REQUIRE(!d.residual || d.act == ACT_NONE, "gemm: activation with a residual is not supported");
   SPRC_REQUIRE(d.grp_rows == 0 || (BM % d.grp_rows == 0 && d.M % d.grp_rows == 0 && d.grp_stride >= d.grp_rows),
                "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);

@@ -469,8 +469,9 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
     a.key_mask = key_mask;
     a.scale = 0.125f;
     SPRC_TRY(attention(a, st));
-    SPRC_TRY(linear(qctx, rows, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh, qt, nullptr, 768, 0, 0, st));
-    SPRC_TRY(layernorm(qt, rows, 768, L.so_g, L.so_beta, 1e-12f, 0, 0, qh, qhb, st));
+    // post-LN residual sublayers (Qformer.py:291-295): qh += dense(ctx) by TMA reduce-add, then LayerNorm in place
+    SPRC_TRY(linear(qctx, rows, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
+    SPRC_TRY(layernorm(qh, rows, 768, L.so_g, L.so_beta, 1e-12f, 0, 0, qh, qhb, st));
     if (with_enc) {
       if (L.has_cross) {
         const int ci = l / 2;
@@ -496,27 +497,27 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         c.kv_idx1 = kv_idx1;
         c.Lk1 = 257;
         SPRC_TRY(attention(c, st));
-        SPRC_TRY(linear(qctx, B * 32, 768, 768, L.co_w, 768, L.co_b, ACT_NONE, qh, qt, nullptr, 768, g, gs, st));
-        SPRC_TRY(layernorm(qt, B * 32, 768, L.co_g, L.co_beta, 1e-12f, g, gs, qh, qhb, st));
+        SPRC_TRY(linear(qctx, B * 32, 768, 768, L.co_w, 768, L.co_b, ACT_NONE, qh, qh, nullptr, 768, g, gs, st));
+        SPRC_TRY(layernorm(qh, B * 32, 768, L.co_g, L.co_beta, 1e-12f, g, gs, qh, qhb, st));
       }
       // query rows -> *_query FFN; text rows -> text FFN (Qformer.py:455-468)
       SPRC_TRY(linear(qhb, B * 32, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, g, gs, st));
-      SPRC_TRY(linear(qffn, B * 32, 3072, 3072, L.qo_w, 768, L.qo_b, ACT_NONE, qh, qt, nullptr, 768, g, gs, st));
-      SPRC_TRY(layernorm(qt, B * 32, 768, L.qo_g, L.qo_beta, 1e-12f, g, gs, qh, qhb, st));
+      SPRC_TRY(linear(qffn, B * 32, 3072, 3072, L.qo_w, 768, L.qo_b, ACT_NONE, qh, qh, nullptr, 768, g, gs, st));
+      SPRC_TRY(layernorm(qh, B * 32, 768, L.qo_g, L.qo_beta, 1e-12f, g, gs, qh, qhb, st));
       if (S == 64) {
         const size_t o = 32;
         SPRC_TRY(linear(qhb + o * 768, B * 32, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
                         qffn + o * 3072, 3072, g, gs, st));
         SPRC_TRY(linear(qffn + o * 3072, B * 32, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh + o * 768,
-                        qt + o * 768, nullptr, 768, g, gs, st));
-        SPRC_TRY(layernorm(qt + o * 768, B * 32, 768, L.to_g, L.to_beta, 1e-12f, g, gs, qh + o * 768,
+                        qh + o * 768, nullptr, 768, g, gs, st));
+        SPRC_TRY(layernorm(qh + o * 768, B * 32, 768, L.to_g, L.to_beta, 1e-12f, g, gs, qh + o * 768,
                            qhb + o * 768, st));
       }
     } else {
       // no encoder states: every row takes the text FFN (Qformer.py:469-475, the "baiyang change" at :434-435)
       SPRC_TRY(linear(qhb, rows, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
-      SPRC_TRY(linear(qffn, rows, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh, qt, nullptr, 768, 0, 0, st));
-      SPRC_TRY(layernorm(qt, rows, 768, L.to_g, L.to_beta, 1e-12f, 0, 0, qh, qhb, st));
+      SPRC_TRY(linear(qffn, rows, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
+      SPRC_TRY(layernorm(qh, rows, 768, L.to_g, L.to_beta, 1e-12f, 0, 0, qh, qhb, st));
     }
   }
   return 0;

@@ -92,6 +92,29 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar
       : "memory");
 }
 
+// TMA stores (shared -> global through a tensor map; rows outside the tensor are clipped).  The staging tile must
+// be made visible to the async proxy (fence_proxy_async by every writing thread, then a warp sync) before ONE thread
+// issues the store; bulk async-groups are per-thread, so the same thread commits and waits.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// global[box] += smem[box] (element type of the tensor map; one L2 reduction per element, no read in the SM)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (the staging tile may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (writes performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, load
 // ----------------------------------------------------------------------------------------------
