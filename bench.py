@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: composed queries/sec at gallery = 50k (BASELINE.json `metric`).
 
-One "step" = one batch of Bq (default 512) composed queries (reference image row + 32-token caption) through the
+One "step" = one batch of Bq (default 592 = 4 x 148 SMs) composed queries (reference image row + 32-token caption) through the
 hot path: Q-Former fusion (two passes) -> similarity scan over the whole gallery -> top-50.
 Workload at N=1: BASELINE.json configs[1] model (ViT-L BLIP-2, full depth, synthetic weights) with the
 gallery enlarged to the 50k rows the metric is quoted on; the gallery index (bf16 features + bf16 raw
@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vit", default="clip_L", choices=["clip_L", "eva_clip_g"])
     ap.add_argument("--gallery", type=int, default=50000)
-    ap.add_argument("--batch", type=int, default=512, help="composed queries per step per GPU")
+    ap.add_argument("--batch", type=int, default=592,
+                    help="composed queries per step per GPU (592 = 4 x 148 SMs: every Q-Former GEMM is a whole "
+                         "number of 128-row tile waves)")
     ap.add_argument("--k", type=int, default=50)
     ap.add_argument("--index-batch", type=int, default=128)
     ap.add_argument("--index-images", type=int, default=0,

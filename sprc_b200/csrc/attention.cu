@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
 
 int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
 bool attention_tc_eligible(const AttnDesc& a);               // attention_tc.cu
+bool attention_qf_eligible(const AttnDesc& a);               // attention_qf.cu
+int attention_qf(const AttnDesc& a, cudaStream_t st);
 int attention_tc(const AttnDesc& a, cudaStream_t st);
 
 template <int DHP, bool FP16>
@@ -219,8 +221,9 @@ int attention(const AttnDesc& a, cudaStream_t st) {
   SPRC_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 2 == 0,
                "attention: row pitches must keep 16-byte alignment");
   SPRC_REQUIRE(a.B <= 65535, "attention: B=%d exceeds grid limit", a.B);
-  if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // Q-Former shapes
   static const bool legacy = getenv("SPRC_ATTN_MMA_SYNC") != nullptr;  // A/B switch for tests
+  if (!legacy && attention_qf_eligible(a)) return attention_qf(a, st);  // Q-Former self / cross: tcgen05
+  if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // remaining small shapes (rerank two-segment keys)
   if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT: tcgen05
   if (act_fp16()) return a.dh <= 64 ? launch_attention<64, true>(a, st) : launch_attention<96, true>(a, st);
   if (a.dh <= 64) return launch_attention<64, false>(a, st);

@@ -111,6 +111,8 @@ attention_small_kernel(const AttnDesc a, const SmallAttnLayout lay, const int ns
   const float sc = a.scale * 1.4426950408889634f;
   const int nqt_valid = (a.Lq + 15) >> 4;
 
+  griddep_wait();
+  griddep_launch();
   if (blockIdx.x < n_iters) prefetch(blockIdx.x, 0);
   int iter = 0;
   for (int it = blockIdx.x; it < n_iters; it += gridDim.x, ++iter) {
@@ -313,7 +315,8 @@ static int launch_small(const AttnDesc& a, cudaStream_t st) {
   int grid = device_sm_count() * ctas_per_sm;
   if (grid > n_iters) grid = n_iters;
   prof_begin(st);
-  attention_small_kernel<NQT, KSPLIT, FP16><<<grid, SA_WARPS * 32, smem, st>>>(a, lay, nstages);
+  SPRC_CUDA(launch_pdl(attention_small_kernel<NQT, KSPLIT, FP16>, dim3(grid), dim3(SA_WARPS * 32), smem, st, a, lay,
+                       nstages));
   if (prof_enabled()) {
     char tag[56];
     snprintf(tag, sizeof(tag), "B%d H%d dh%d Lq%d Lk%d", a.B, a.H, a.dh, a.Lq, a.Lk);

@@ -36,6 +36,27 @@ const char* last_error();
   } while (0)
 
 int device_sm_count();
+
+// Programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor on the stream is
+// still draining; every kernel launched this way executes griddepcontrol.wait (ptx.cuh: griddep_wait) before
+// it touches global memory, so only its prologue (barrier init, TMEM alloc, descriptor prefetch, index math)
+// overlaps the predecessor's tail.  SPRC_PDL=0 in the environment falls back to plain launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // 16-bit activation / operand format of the whole library: 0 = bf16 (default), 1 = fp16
 int act_fp16();
 void set_act_fp16(int on);

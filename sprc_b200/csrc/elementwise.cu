@@ -27,6 +27,8 @@ layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* 
                  const float* __restrict__ beta, float eps, int grp_rows, int grp_stride, float* out_f32,
                  bf16* out_bf16, int fp16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  griddep_wait();
+  griddep_launch();
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   long long prow = row;
@@ -84,11 +86,11 @@ int layernorm(const float* x, int rows, int width, const float* gamma, const flo
   const int grid = (rows + wpb - 1) / wpb;
   prof_begin(st);
   if (width <= 32 * 4 * 6)
-    layernorm_kernel<6><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32,
-                                                   out_bf16, act_fp16());
+    SPRC_CUDA(launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, width, gamma, beta, eps,
+                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16()));
   else
-    layernorm_kernel<12><<<grid, wpb * 32, 0, st>>>(x, rows, width, gamma, beta, eps, grp_rows, grp_stride,
-                                                    out_f32, out_bf16, act_fp16());
+    SPRC_CUDA(launch_pdl(layernorm_kernel<12>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, width, gamma, beta, eps,
+                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16()));
   prof_end(PROF_ELEMWISE, 0.0, (double)rows * width * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)), st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());

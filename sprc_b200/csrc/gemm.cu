@@ -92,6 +92,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();    // operands / residual are written by the preceding kernels on the stream
+  griddep_launch();  // the next kernel may set itself up on this SM as soon as this CTA retires
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -396,7 +398,8 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   prof_begin(st);
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, p);
+  SPRC_CUDA(launch_pdl(gemm_bf16_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, st, tmA, tmB,
+                       tmC, p));
   if (prof_enabled()) {
     char tag[56];
     snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d bn%d", d.M, d.N, d.K, d.grp_rows, d.act,

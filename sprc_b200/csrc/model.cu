@@ -444,14 +444,19 @@ int Model::cross_kv(const bf16* raws_bf16, int n_img, cudaStream_t st) {
 }
 
 int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
-                          const float* key_mask, cudaStream_t st) {
+                          const float* key_mask, int live_out, cudaStream_t st) {
   const int rows = B * S;
   SPRC_REQUIRE(rows <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows, qf_rows);
+  SPRC_REQUIRE(live_out == QF_OUT_ALL || S == 64, "qformer: row-restricted output needs S = 64");
   const int g = (S == 64) ? 32 : 0;  // row grouping for "first/last 32 rows of each 64-row sample"
   const int gs = (S == 64) ? 64 : 0;
   const int ldkv = n_cross * 1536;
   for (int l = 0; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
+    // Rows whose output nobody reads are not computed in the LAST layer (their keys/values still are): the
+    // fusion pass is consumed through its 32 query rows only (align_prompt.py:343 `fusion_output[:, :32]`,
+    // rerank.py:440 `[:, :query_tokens.size(1)]`), the text pass through row 32 only (align_prompt.py:348).
+    const int live = (l == qf_layers - 1) ? live_out : QF_OUT_ALL;
     // ---- self-attention over all S rows ----
     SPRC_TRY(linear(qhb, rows, 768, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, nullptr, nullptr, qqkv, 2304, 0, 0, st));
     AttnDesc a;
@@ -470,8 +475,18 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
     a.scale = 0.125f;
     SPRC_TRY(attention(a, st));
     // post-LN residual sublayers (Qformer.py:291-295): qh += dense(ctx) by TMA reduce-add, then LayerNorm in place
-    SPRC_TRY(linear(qctx, rows, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
-    SPRC_TRY(layernorm(qh, rows, 768, L.so_g, L.so_beta, 1e-12f, 0, 0, qh, qhb, st));
+    if (live == QF_OUT_ALL) {
+      SPRC_TRY(linear(qctx, rows, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
+      SPRC_TRY(layernorm(qh, rows, 768, L.so_g, L.so_beta, 1e-12f, 0, 0, qh, qhb, st));
+    } else {
+      // QF_OUT_QUERY_ROWS: rows [0,32) of each sample; QF_OUT_TEXT_CLS: row 32 of each sample
+      const int gr = live == QF_OUT_QUERY_ROWS ? 32 : 1;
+      const size_t o = live == QF_OUT_QUERY_ROWS ? 0 : 32;
+      const int m = B * gr;
+      SPRC_TRY(linear(qctx + o * 768, m, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh + o * 768, qh + o * 768, nullptr,
+                      768, gr, 64, st));
+      SPRC_TRY(layernorm(qh + o * 768, m, 768, L.so_g, L.so_beta, 1e-12f, gr, 64, qh + o * 768, qhb + o * 768, st));
+    }
     if (with_enc) {
       if (L.has_cross) {
         const int ci = l / 2;
@@ -504,7 +519,7 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
       SPRC_TRY(linear(qhb, B * 32, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, g, gs, st));
       SPRC_TRY(linear(qffn, B * 32, 3072, 3072, L.qo_w, 768, L.qo_b, ACT_NONE, qh, qh, nullptr, 768, g, gs, st));
       SPRC_TRY(layernorm(qh, B * 32, 768, L.qo_g, L.qo_beta, 1e-12f, g, gs, qh, qhb, st));
-      if (S == 64) {
+      if (S == 64 && live == QF_OUT_ALL) {
         const size_t o = 32;
         SPRC_TRY(linear(qhb + o * 768, B * 32, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
                         qffn + o * 3072, 3072, g, gs, st));
@@ -513,6 +528,13 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         SPRC_TRY(layernorm(qh + o * 768, B * 32, 768, L.to_g, L.to_beta, 1e-12f, g, gs, qh + o * 768,
                            qhb + o * 768, st));
       }
+    } else if (live == QF_OUT_TEXT_CLS) {
+      const size_t o = 32;
+      SPRC_TRY(linear(qhb + o * 768, B, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn + o * 3072,
+                      3072, 1, 64, st));
+      SPRC_TRY(linear(qffn + o * 3072, B, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh + o * 768, qh + o * 768,
+                      nullptr, 768, 1, 64, st));
+      SPRC_TRY(layernorm(qh + o * 768, B, 768, L.to_g, L.to_beta, 1e-12f, 1, 64, qh + o * 768, qhb + o * 768, st));
     } else {
       // no encoder states: every row takes the text FFN (Qformer.py:469-475, the "baiyang change" at :434-435)
       SPRC_TRY(linear(qhb, rows, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
@@ -533,7 +555,7 @@ int Model::encode_gallery(const float* images, int B, float* feats_f32, bf16* fe
   // embeddings = LayerNorm(query_tokens)  (Qformer.py:110-112), broadcast over the batch
   SPRC_TRY(qformer_embed_rows(query_tokens, 0, nullptr, 1, word_emb, pos_emb, vocab, B, qt, st));
   SPRC_TRY(layernorm(qt, B * 32, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(B, 32, true, 257, nullptr, nullptr, nullptr, st));
+  SPRC_TRY(qformer_layers(B, 32, true, 257, nullptr, nullptr, nullptr, QF_OUT_ALL, st));
   SPRC_TRY(linear(qhb, B * 32, 768, 768, vproj_w, 256, vproj_b, ACT_NONE, nullptr, qproj, nullptr, 256, 0, 0, st));
   SPRC_TRY(l2norm_rows256(qproj, 256, B * 32, feats_f32, feats_bf16, st));
   return 0;
@@ -559,11 +581,11 @@ int Model::encode_query(const void* ref_raws, int ref_dtype, const int32_t* ref_
   // pass 1: fusion = Qformer(text, query_tokens, enc = reference embeds)   (align_prompt.py:332-339)
   SPRC_TRY(qformer_embed_rows(query_tokens, 0, ids, 1, word_emb, pos_emb, vocab, Bq, qt, st));
   SPRC_TRY(layernorm(qt, Bq * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(Bq, 64, true, 257, nullptr, nullptr, qmask, st));
+  SPRC_TRY(qformer_layers(Bq, 64, true, 257, nullptr, nullptr, qmask, QF_OUT_QUERY_ROWS, st));
   // pass 2: text = Qformer(text, query_embeds = fusion[:, :32])  with no encoder states (:341-346)
   SPRC_TRY(qformer_embed_rows(qh, 64, ids, 1, word_emb, pos_emb, vocab, Bq, qt, st));
   SPRC_TRY(layernorm(qt, Bq * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(Bq, 64, false, 0, nullptr, nullptr, qmask, st));
+  SPRC_TRY(qformer_layers(Bq, 64, false, 0, nullptr, nullptr, qmask, QF_OUT_TEXT_CLS, st));
   // fusion_feats = normalize(text_proj(h[:, 32]))   (:348-350): row 32 of every 64-row sample
   SPRC_TRY(linear(qhb + (size_t)32 * 768, Bq, 768, 768, tproj_w, 256, tproj_b, ACT_NONE, nullptr, qproj, nullptr, 256,
                   1, 64, st));
@@ -602,7 +624,7 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_TRY(qformer_key_mask(mask + (size_t)r0 * 32, T, pairs, qmask, st));
     SPRC_TRY(qformer_embed_rows(query_tokens, 0, ids + (size_t)r0 * 32, T, word_emb, pos_emb, vocab, pairs, qt, st));
     SPRC_TRY(layernorm(qt, pairs * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-    SPRC_TRY(qformer_layers(pairs, 64, true, 514, d_rows, d_rows2, qmask, st));
+    SPRC_TRY(qformer_layers(pairs, 64, true, 514, d_rows, d_rows2, qmask, QF_OUT_QUERY_ROWS, st));
     SPRC_TRY(itm_head_prob(qh, 64, pairs, itm_w, itm_b, p + (size_t)r0 * T, st));
   }
   return 0;

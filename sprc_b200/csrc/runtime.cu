@@ -1,6 +1,7 @@
 // Error reporting and device queries for libsprc_b200 (see include/sprc_b200.h conventions).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ops.h"
@@ -25,6 +26,15 @@ const char* last_error() { return g_err; }
 static int g_act_fp16 = 0;
 int act_fp16() { return g_act_fp16; }
 void set_act_fp16(int on) { g_act_fp16 = on ? 1 : 0; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SPRC_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 int device_sm_count() {
   static int sms[64] = {0};
