@@ -364,6 +364,30 @@ def main():
                      "avg_launch_us": scan["ms"] * 1e3 / max(scan["n"], 1),
                      "share_of_step": scan["ms"] / prof_total if prof_total else None,
                      "note": "gallery bytes N*32*256*2 per launch; queries/launch = %d" % (world * Bq)}
+    # ---- scan in its HBM-bound regime (one 128-query tile per gallery pass: every gallery byte is read once) ----
+    q128 = torch.nn.functional.normalize(torch.randn(128, 256, device=dev), dim=-1).to(adt)
+    sc128 = torch.empty(128, k, device=dev)
+    ix128 = torch.empty(128, k, device=dev, dtype=torch.int32)
+    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.sprc_profile(1)
+    for i in range(W + K):
+        if i == W:
+            lib.sprc_profile(1)
+        L.check(lib.sprc_sim_topk(h, L.ptr(q128), 128, L.ptr(feats), n_local, lo, k, L.ptr(sc128), L.ptr(ix128), None,
+                                  st()))
+    torch.cuda.synchronize()
+    prof2 = (ctypes.c_double * 20)()
+    L.check(lib.sprc_profile_read(prof2, 5))
+    lib.sprc_profile(0)
+    s_ms, s_bytes, s_n = prof2[3 * 4], prof2[3 * 4 + 2], prof2[3 * 4 + 3]
+    hbm_gbs = s_bytes / (s_ms / 1e3) / 1e9 if s_ms > 0 else 0.0
+    roofline_scan_hbm = {"kernel": "scan_topk_kernel", "bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm"],
+                         "unit": "GB/s", "frac": hbm_gbs / pk["hbm"], "traffic": None,
+                         "avg_launch_us": s_ms * 1e3 / max(s_n, 1),
+                         "note": "128 queries (one UMMA M tile) x the %d-row gallery shard, top-%d; gallery "
+                                 "(%.0f MB) exceeds L2; algorithmic bytes N*32*256*2 + Q*512 per launch" % (
+                                     n_local, k, n_local * 32 * 256 * 2 / 1e6)}
+
     breakdown = {"gemm_ms": gemm["ms"] / K, "attention_ms": attn["ms"] / K, "layernorm_ms": lnorm["ms"] / K,
                  "scan_ms": scan["ms"] / K, "merge_ms": merge["ms"] / K}
 
@@ -393,7 +417,8 @@ def main():
                     "d2h_bytes_per_step": world * Bq * k * 8, "ms_per_step": ms_e2e / K,
                     "api": "sprc_query_topk_host (pinned host ids/mask/ref rows -> top-k on host)"},
             "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_scan": roofline_scan, "step_breakdown_ms": breakdown,
+            "roofline": roofline, "roofline_scan": roofline_scan, "roofline_scan_hbm": roofline_scan_hbm,
+            "step_breakdown_ms": breakdown,
             "frac_of_qformer_gemm_roofline": value / world * FLOP_PER_QUERY[args.vit] / (pk["tf_sust"] * 1e12),
             "index_build": {"images_per_s_per_gpu": index_ips, "seconds": index_s,
                             "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (pk["tf_sust"] * 1e12),

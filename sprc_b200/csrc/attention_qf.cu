@@ -42,6 +42,7 @@ struct QfSelfParams {
   int rows, B, H;
   float scale_log2;
   int fp16;
+  int rev;  // sweep the items from the last one down (next_sweep_reverse)
   const float* key_mask;  // additive [B, S] or null
 };
 
@@ -94,7 +95,8 @@ qf_self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int g = item / p.H, h = item % p.H;
+        const int itm = p.rev ? n_items - 1 - item : item;
+        const int g = itm / p.H, h = itm % p.H;
         uint8_t* st = smem + s * QS_STAGE;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], QS_STAGE);
@@ -154,7 +156,8 @@ qf_self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1;
-      const int g = item / p.H, h = item % p.H;
+      const int itm = p.rev ? n_items - 1 - item : item;
+        const int g = itm / p.H, h = itm % p.H;
       const int sample = (g * 128 + row) / S;
       mbar_wait(s_full, it & 1);
       tc_fence_after();
@@ -265,6 +268,7 @@ static int launch_qf_self(const AttnDesc& a, cudaStream_t st) {
   p.H = a.H;
   p.scale_log2 = a.scale * kLog2e;
   p.fp16 = act_fp16();
+  p.rev = next_sweep_reverse();
   p.key_mask = a.key_mask;
   static bool attr_set = false;
   if (!attr_set) {
@@ -306,6 +310,7 @@ struct QfCrossParams {
   int q_batch_rows, kv_batch_rows;
   float scale_log2;
   int fp16;
+  int rev;  // sweep the items from the last one down (next_sweep_reverse)
 };
 
 __global__ void __launch_bounds__(QF_THREADS, 1)
@@ -359,7 +364,8 @@ qf_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int s = it & 1;
-        const int b = item / p.H, h = item % p.H;
+        const int itm = p.rev ? n_items - 1 - item : item;
+        const int b = itm / p.H, h = itm % p.H;
         uint8_t* st = stages + s * QC_STAGE;
         mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&full[s], QC_STAGE);
@@ -418,7 +424,8 @@ qf_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     const uint32_t prow = smem_u32(sP) + lane * 128;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int b = item / p.H, h = item % p.H;
+      const int itm = p.rev ? n_items - 1 - item : item;
+        const int b = itm / p.H, h = itm % p.H;
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       uint32_t sr[80];
@@ -537,6 +544,7 @@ static int launch_qf_cross(const AttnDesc& a, cudaStream_t st) {
   p.kv_batch_rows = a.kv_batch_rows;
   p.scale_log2 = a.scale * kLog2e;
   p.fp16 = act_fp16();
+  p.rev = next_sweep_reverse();
   static bool attr_set = false;
   if (!attr_set) {
     SPRC_CUDA(cudaFuncSetAttribute(qf_cross_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

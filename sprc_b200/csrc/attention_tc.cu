@@ -40,6 +40,7 @@ struct TcAttnParams {
   int ldo;            // output row pitch (elements)
   float scale_log2;   // scale * log2(e)
   int fp16;           // operand format
+  int rev;            // sweep the items from the last one down (next_sweep_reverse)
   bf16* O;
 };
 
@@ -99,7 +100,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (elect_one()) {
       uint32_t kv_ph = 0, q_ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = item / p.H, h = item % p.H;
+        const int itm = p.rev ? n_items - 1 - item : item;
+        const int b = itm / p.H, h = itm % p.H;
         const int row0 = b * p.L;
         mbar_wait(kv_empty, kv_ph ^ 1);
         mbar_expect_tx(kv_full, 2 * DHB * TA_KBYTES);
@@ -175,7 +177,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int nkeys = seg == 0 ? 80 : 64;
     uint32_t s_ph = 0, o_ph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = item / p.H, h = item % p.H;
+      const int itm = p.rev ? n_items - 1 - item : item;
+        const int b = itm / p.H, h = itm % p.H;
       for (int mt = 0; mt < n_mt; ++mt) {
         const bool warp_has_rows = mt * 128 + q * 32 < p.L;  // warp-uniform
         mbar_wait(s_full, s_ph);
@@ -318,6 +321,7 @@ static int launch_tc(const AttnDesc& a, cudaStream_t st) {
   p.ldo = a.ldo;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.fp16 = act_fp16();
+  p.rev = next_sweep_reverse();
   p.O = a.O;
   static bool attr_set = false;
   if (!attr_set) {

@@ -25,11 +25,12 @@ template <int MAXV>  // float4 vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, int grp_rows, int grp_stride, float* out_f32,
-                 bf16* out_bf16, int fp16) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                 bf16* out_bf16, int fp16, int rev) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   griddep_wait();
   griddep_launch();
   if (row >= rows) return;
+  if (rev) row = rows - 1 - row;  // low block indices (scheduled first) take the last rows
   const int lane = threadIdx.x & 31;
   long long prow = row;
   if (grp_rows > 0) prow = (long long)(row / grp_rows) * grp_stride + (row % grp_rows);
@@ -84,13 +85,14 @@ int layernorm(const float* x, int rows, int width, const float* gamma, const flo
   if (rows <= 0) return 0;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
+  const int rev = next_sweep_reverse();
   prof_begin(st);
   if (width <= 32 * 4 * 6)
     SPRC_CUDA(launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, width, gamma, beta, eps,
-                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16()));
+                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16(), rev));
   else
     SPRC_CUDA(launch_pdl(layernorm_kernel<12>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, width, gamma, beta, eps,
-                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16()));
+                         grp_rows, grp_stride, out_f32, out_bf16, act_fp16(), rev));
   prof_end(PROF_ELEMWISE, 0.0, (double)rows * width * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)), st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());

@@ -41,6 +41,7 @@ struct GemmKernelParams {
   int fp16;  // operand / bf16-output format: 0 bf16, 1 fp16
   int out_is_f32;  // output element type of tmC
   int accumulate;  // 1: out_f32 += result (TMA reduce-add; the residual already lives in the output buffer)
+  int rev;         // 1: sweep the tiles from the last M block down (see next_sweep_reverse)
 };
 
 template <int BN, int STAGES>
@@ -100,7 +101,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tile = p.rev ? num_tiles - 1 - t : t;
         const int m0 = (tile / p.num_n_blocks) * BM;
         const int n0 = (tile % p.num_n_blocks) * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -174,7 +176,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int nchunks = (BN / 4) / CH;               // chunks per warp per tile
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tile = p.rev ? num_tiles - 1 - t : t;
       const int m0 = (tile / p.num_n_blocks) * BM + q * 32;   // first row of this warp's 32 rows
       const int n0 = (tile % p.num_n_blocks) * BN + cpart * (BN / 4);
       // TMA coordinates of the warp's rows (dense: row m0; grouped: see GemmDesc)
@@ -380,6 +383,7 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   p.fp16 = act_fp16();
   p.out_is_f32 = d.out_f32 ? 1 : 0;
   p.accumulate = d.residual ? 1 : 0;
+  p.rev = next_sweep_reverse();
   if (d.residual && d.residual != d.out_f32) {
     const long long total = (long long)d.M * (d.N / 4);
     long long blocks = (total + 255) / 256;

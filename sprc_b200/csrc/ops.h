@@ -10,6 +10,10 @@ void count_launch(int n = 1);
 // per-launch CUDA-event timing by category (bench.py roofline; off by default)
 enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ELEMWISE = 2, PROF_SCAN = 3, PROF_MERGE = 4, PROF_NCAT = 5 };
 bool prof_enabled();
+// Row-sweeping kernels (GEMM tiles, LayerNorm rows, attention items) alternate their sweep direction from launch
+// to launch, so each kernel starts on the rows its producer touched LAST, which are the ones still in the 126 MB L2
+// (activations of a 592-query step are 116-290 MB per tensor).  Results do not depend on the direction.
+int next_sweep_reverse();
 void prof_begin(cudaStream_t st);
 void prof_end(int cat, double flops, double bytes, cudaStream_t st, const char* tag = nullptr);
 int prof_dump(const char* path);

@@ -75,6 +75,15 @@ static cudaEvent_t get_event() {
 }
 
 bool prof_enabled() { return g_prof_on; }
+int next_sweep_reverse() {
+  static thread_local unsigned sweep = 0;
+  static const bool enabled = [] {
+    const char* e = getenv("SPRC_SWEEP");  // SPRC_SWEEP=0: always ascending (A/B measurements)
+    return !(e && e[0] == '0');
+  }();
+  return enabled ? static_cast<int>(sweep++ & 1u) : 0;
+}
+
 void prof_begin(cudaStream_t st) {
   if (!g_prof_on) return;
   g_pending = get_event();

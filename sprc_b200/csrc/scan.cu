@@ -4,7 +4,7 @@
 //
 // The reference expands the gallery Bq times and sorts all N scores per query.  Here one persistent
 // kernel streams the bf16 gallery [N*32, 256] from HBM exactly once per 128-query tile:
-//   warp 0      TMA producer: 64 gallery tokens (2 images) x 256 dims per stage, 3-stage ring
+//   warp 0      TMA producer: 64 gallery tokens (2 images) x 256 dims per stage, 4-stage ring
 //   warp 1      tcgen05.mma issuer: D[128 queries, 64 tokens] = Qtile[128,256] * G[64,256]^T, fp32 in TMEM
 //               (queries on TMEM lanes so that the max over an image's 32 tokens is a per-thread max
 //               over 32 accumulator columns - no shuffles)
@@ -23,15 +23,14 @@ namespace sprc {
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                    uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank);
 
-static constexpr int SQ = 128;        // queries per CTA (UMMA M)
+static constexpr int SQ = 128;        // queries per query tile (UMMA M)
 static constexpr int ST = 64;         // gallery tokens per stage (UMMA N) = 2 images
-static constexpr int SSTAGES = 3;
+static constexpr int MAX_SSTAGES = 4; // gallery ring depth (32 KB per stage), as many as fit next to the heaps
 static constexpr int KCAP = 64;       // heap capacity (fused path handles k <= 64)
+static constexpr int PEND = 8;        // per-query pending candidates between heap flushes
 static constexpr int SEG = 4096;      // segment width of the large-k path
-static constexpr int A_BYTES = SQ * 256 * 2;   // 64 KB
 static constexpr int B_BYTES = ST * 256 * 2;   // 32 KB
-static constexpr int HEAP_BYTES = KCAP * SQ * 8;  // 64 KB
-static constexpr int SCAN_SMEM = A_BYTES + SSTAGES * B_BYTES + HEAP_BYTES + 256 + 1024;
+static constexpr int SCAN_SMEM_MAX = 227 * 1024;
 
 typedef unsigned long long u64;
 
@@ -53,56 +52,69 @@ __device__ __forceinline__ void decode_key(u64 key, float& score, int32_t& idx) 
 }
 
 struct ScanParams {
+  const uint4* queries;      // [Q, 256] 16-bit, rows 512 B
   int Q;
   long long N;
   long long row_offset;
   int k;
-  int qtiles, splits;
+  int qtiles;                // 128-query tiles
+  int ctiles;                // CTA tiles = ceil(qtiles / NQ)
+  int splits;
+  int sstages;               // gallery ring depth actually allocated (2..MAX_SSTAGES)
   long long imgs_per_split;  // even
   int fp16;                  // operand format of queries / gallery
   float* out_full;           // [Q, N] or null
   u64* cand;                 // [splits][k][qtiles*128] or null
 };
 
-__global__ void __launch_bounds__(192, 1)
-scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
-                 const ScanParams p) {
+// The query tiles are the A operands of every MMA of the CTA, so they live in TENSOR MEMORY (tcgen05.mma with A in
+// TMEM): shared memory carries only the gallery stream (one TMA write + one UMMA read per byte and query tile).
+// NQ = 1: one 128-query tile per CTA, every SM pulls its own slice of the gallery from HBM (HBM-bound regime).
+// NQ = 2: two query tiles share each gallery stage.  With one tile per CTA a 592-query scan re-read the gallery
+// five times from L2 and ran at the L2 -> SM bandwidth (5.9 TB/s = 128 FLOP per L2 byte, 700 TFLOP/s:
+// profiles/r01b_*); two tiles per stage halve the L2 and TMA traffic per FLOP.
+template <int NQ>
+__global__ void __launch_bounds__(64 + NQ * 128, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
+  constexpr int AS = NQ == 1 ? 4 : 2;          // accumulator stages per query tile (64 fp32 columns each)
+  constexpr int TM_COL_D = NQ * 128;           // after the query tiles (128 columns of packed 16-bit pairs each)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + A_BYTES;
-  u64* heap = reinterpret_cast<u64*>(smem + A_BYTES + SSTAGES * B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + SSTAGES * B_BYTES + HEAP_BYTES);
-  uint64_t* full_bar = bars;                  // [SSTAGES]
-  uint64_t* empty_bar = bars + SSTAGES;       // [SSTAGES]
-  uint64_t* tfull_bar = bars + 2 * SSTAGES;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint64_t* q_bar = tempty_bar + 2;           // [1]
+  const int nst = p.sstages;
+  const int heap_slots = p.k + PEND;
+  uint8_t* sB = smem;
+  u64* heap = reinterpret_cast<u64*>(smem + nst * B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * B_BYTES + NQ * heap_slots * SQ * 8);
+  uint64_t* full_bar = bars;                           // [MAX_SSTAGES]
+  uint64_t* empty_bar = bars + MAX_SSTAGES;            // [MAX_SSTAGES]
+  uint64_t* tfull_bar = bars + 2 * MAX_SSTAGES;        // [NQ * AS]
+  uint64_t* tempty_bar = tfull_bar + NQ * AS;          // [NQ * AS]
+  uint64_t* q_bar = tempty_bar + NQ * AS;              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.qtiles;
-  const int sp = blockIdx.x / p.qtiles;
+  const int ct = blockIdx.x % p.ctiles;
+  const int sp = blockIdx.x / p.ctiles;
   const long long n_begin = static_cast<long long>(sp) * p.imgs_per_split;
   long long n_end = n_begin + p.imgs_per_split;
   if (n_end > p.N) n_end = p.N;
   const int stages_total = n_end > n_begin ? static_cast<int>((n_end - n_begin + 1) / 2) : 0;
+  const int live_tiles = (p.qtiles - ct * NQ) < NQ ? (p.qtiles - ct * NQ) : NQ;   // 1..NQ query tiles with real rows
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmG);
-    for (int s = 0; s < SSTAGES; ++s) {
+    for (int s = 0; s < MAX_SSTAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NQ * AS; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
     }
-    mbar_init(q_bar, 1);
+    mbar_init(q_bar, 4 * NQ);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,9 +122,6 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     if (elect_one()) {
-      // query tile: 4 K-blocks of [128 rows x 64 cols]
-      mbar_expect_tx(q_bar, A_BYTES);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tmQ, q_bar, sA + kb * (SQ * 128), kb * 64, qt * SQ, kEvictLast);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < stages_total; ++it) {
@@ -121,8 +130,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const long long row0 = (n_begin + 2LL * it) * 32;
         for (int kb = 0; kb < 4; ++kb)
           tma_load_2d(&tmG, &full_bar[stage], sB + stage * B_BYTES + kb * (ST * 128), kb * 64,
-                      static_cast<int>(row0), p.qtiles > 1 ? kEvictNormal : kEvictFirst);
-        if (++stage == SSTAGES) {
+                      static_cast<int>(row0), p.ctiles > 1 ? kEvictNormal : kEvictFirst);
+        if (++stage == nst) {
           stage = 0;
           phase ^= 1;
         }
@@ -130,103 +139,147 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_16(SQ, ST, p.fp16);
-    mbar_wait(q_bar, 0);
+    mbar_wait(q_bar, 0);   // the epilogue warps have written the query tiles into TMEM
     tc_fence_after();
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     for (int it = 0; it < stages_total; ++it) {
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      for (int sub = 0; sub < live_tiles; ++sub) mbar_wait(&tempty_bar[sub * AS + as], aphase ^ 1);
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * ST);
+        for (int sub = 0; sub < live_tiles; ++sub) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(TM_COL_D + (sub * AS + as) * ST);
+          const uint32_t a_tmem = tmem_base + static_cast<uint32_t>(sub * 128);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * (SQ * 128)));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES + kb * (ST * 128)));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 16; ++ks) {
+            // K step ks: dims [16 ks, 16 ks + 16) = TMEM columns [8 ks, 8 ks + 8) of the query tile; gallery K
+            // block ks / 4, +32 B per step inside the 128 B swizzle row
+            const uint64_t db =
+                umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES + (ks >> 2) * (ST * 128))) + 2 * (ks & 3);
+            umma_bf16_ts(d_tmem, a_tmem + ks * 8, db, idesc, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&tfull_bar[sub * AS + as]);
         }
         umma_commit(&empty_bar[stage]);
-        umma_commit(&tfull_bar[as]);
       }
       __syncwarp();
-      if (++stage == SSTAGES) {
+      if (++stage == nst) {
         stage = 0;
         phase ^= 1;
       }
-      if (++as == 2) {
+      if (++as == AS) {
         as = 0;
         aphase ^= 1;
       }
     }
   } else {
     // ===================== epilogue: one thread per query =====================
-    const int qw = warp & 3;
+    const int sub = (warp - 2) >> 2;       // query tile of this warp
+    const int qw = warp & 3;               // TMEM lane quarter this warp may access
     const int ql = qw * 32 + lane;         // query row inside the tile = TMEM lane
-    const int q = qt * SQ + ql;
+    const int q = (ct * NQ + sub) * SQ + ql;
     const bool q_ok = q < p.Q;
     const int k = p.k;
-    const uint32_t myheap = smem_u32(heap + ql);   // slot j at byte offset j * SQ * 8 (explicit shared-space accesses)
-    constexpr uint32_t HS = SQ * 8;
-    for (int j = 0; j < k; ++j) sts64(myheap + j * HS, static_cast<u64>(j));  // distinct sub-minimal keys, valid min-heap
-    u64 root = 0;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int it = 0; it < stages_total; ++it) {
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + static_cast<uint32_t>(as * ST);
-      tmem_ld32(taddr, r0);
-      tmem_ld32(taddr + 32, r1);
-      tmem_ld_wait();
+    const uint32_t lane_addr = static_cast<uint32_t>(qw * 32) << 16;
+    {
+      // query row -> TMEM lane ql, 4 x 32 columns (two 16-bit elements per column, memory order)
+      const uint4* src = p.queries + static_cast<size_t>(q_ok ? q : 0) * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (q_ok) v = __ldg(src + c * 8 + j);
+          r[4 * j] = v.x, r[4 * j + 1] = v.y, r[4 * j + 2] = v.z, r[4 * j + 3] = v.w;
+        }
+        tmem_st32(tmem_base + lane_addr + sub * 128 + c * 32, r);
+      }
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);  // accumulator is in registers: release TMEM early
-      float s0 = __uint_as_float(r0[0]), s1 = __uint_as_float(r1[0]);
-#pragma unroll
-      for (int j = 1; j < 32; ++j) {
-        s0 = fmaxf(s0, __uint_as_float(r0[j]));
-        s1 = fmaxf(s1, __uint_as_float(r1[j]));
+      if (lane == 0) mbar_arrive(q_bar);
+    }
+    constexpr uint32_t HS = SQ * 8;
+    // slot j of this query's heap at byte offset j * HS (slot-major: conflict-free for any mix of heap positions)
+    const uint32_t myheap = smem_u32(heap) + static_cast<uint32_t>(sub * heap_slots) * HS + ql * 8;
+    const uint32_t mypend = myheap + k * HS;    // PEND pending candidates
+    for (int j = 0; j < k; ++j) sts64(myheap + j * HS, static_cast<u64>(j));  // distinct sub-minimal keys, valid min-heap
+    u64 root = 0;
+    int pcnt = 0;
+    // A candidate that beats the heap minimum is only QUEUED; the warp drains the queues together when one of them
+    // is nearly full.  Inserting at once made the whole warp walk the sift-down loop whenever any of its 32 queries
+    // had a hit (almost every image while a split's threshold is still loose).
+    auto flush = [&]() {
+      for (int j = 0; j < pcnt; ++j) {
+        const u64 key = lds64(mypend + j * HS);
+        if (key > root) {
+          int i = 0;
+          while (true) {
+            const int l = 2 * i + 1;
+            if (l >= k) break;
+            const u64 kl = lds64(myheap + l * HS);
+            const u64 kr = (l + 1 < k) ? lds64(myheap + (l + 1) * HS) : ~0ull;
+            const int c = kr < kl ? l + 1 : l;
+            const u64 kc = kr < kl ? kr : kl;
+            if (kc >= key) break;
+            sts64(myheap + i * HS, kc);
+            i = c;
+          }
+          sts64(myheap + i * HS, key);
+          root = lds64(myheap);
+        }
       }
-      const long long n0 = n_begin + 2LL * it;
+      pcnt = 0;
+    };
+    if (sub < live_tiles) {
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int it = 0; it < stages_total; ++it) {
+        mbar_wait(&tfull_bar[sub * AS + as], aphase);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + lane_addr + static_cast<uint32_t>(TM_COL_D + (sub * AS + as) * ST);
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[sub * AS + as]);  // accumulator is in registers: release TMEM early
+        float s0 = __uint_as_float(r0[0]), s1 = __uint_as_float(r1[0]);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const long long n = n0 + e;
-        const float s = e == 0 ? s0 : s1;
-        if (q_ok && n < n_end) {
-          if (p.out_full) p.out_full[static_cast<size_t>(q) * p.N + n] = s;
-          if (p.cand) {
-            const u64 key = make_key(s, static_cast<uint32_t>(p.row_offset + n));
-            if (key > root) {
-              // replace the heap minimum and sift down
-              int i = 0;
-              while (true) {
-                const int l = 2 * i + 1;
-                if (l >= k) break;
-                const u64 kl = lds64(myheap + l * HS);
-                const u64 kr = (l + 1 < k) ? lds64(myheap + (l + 1) * HS) : ~0ull;
-                const int c = kr < kl ? l + 1 : l;
-                const u64 kc = kr < kl ? kr : kl;
-                if (kc >= key) break;
-                sts64(myheap + i * HS, kc);
-                i = c;
+        for (int j = 1; j < 32; ++j) {
+          s0 = fmaxf(s0, __uint_as_float(r0[j]));
+          s1 = fmaxf(s1, __uint_as_float(r1[j]));
+        }
+        const long long n0 = n_begin + 2LL * it;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const long long n = n0 + e;
+          const float s = e == 0 ? s0 : s1;
+          if (q_ok && n < n_end) {
+            if (p.out_full) p.out_full[static_cast<size_t>(q) * p.N + n] = s;
+            if (p.cand) {
+              const u64 key = make_key(s, static_cast<uint32_t>(p.row_offset + n));
+              if (key > root) {
+                sts64(mypend + pcnt * HS, key);
+                ++pcnt;
               }
-              sts64(myheap + i * HS, key);
-              root = lds64(myheap);
             }
           }
         }
+        if (__any_sync(0xffffffffu, pcnt > PEND - 2)) flush();
+        if (++as == AS) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
+      flush();
+      if (p.cand && q_ok) {
+        const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
+        for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = lds64(myheap + j * HS);
       }
-    }
-    if (p.cand && q_ok) {
-      const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
-      for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = lds64(myheap + j * HS);
     }
   }
 
@@ -234,7 +287,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -340,10 +393,12 @@ int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, i
 }
 
 // workspace: candidate keys of the fused path, or [full matrix +] segment candidates of the large-k path
-static void scan_plan(int Q, long long N, int k, int& qtiles, int& splits, long long& ips) {
+static void scan_plan(int Q, long long N, int k, int& qtiles, int& nq, int& splits, long long& ips) {
   qtiles = (Q + SQ - 1) / SQ;
+  nq = qtiles > 1 ? 2 : 1;  // query tiles per CTA (see scan_topk_kernel)
+  const int ctiles = (qtiles + nq - 1) / nq;
   const int sms = device_sm_count();
-  splits = sms / qtiles;
+  splits = sms / ctiles;
   if (splits < 1) splits = 1;
   const long long max_splits = (N + 1) / 2;  // at least one stage (2 images) per split
   if (splits > max_splits) splits = static_cast<int>(max_splits > 0 ? max_splits : 1);
@@ -375,22 +430,29 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
   SPRC_REQUIRE(!want_topk || (k > 0 && k <= 1024), "sim_topk: k=%d outside [1, 1024]", k);
   SPRC_REQUIRE(want_topk || out_full, "sim_topk: no output requested");
   const bool fused = want_topk && k <= KCAP;
-  int qtiles, splits;
+  int qtiles, nq, splits;
   long long ips;
-  scan_plan(Q, N, fused ? k : 1, qtiles, splits, ips);
+  scan_plan(Q, N, fused ? k : 1, qtiles, nq, splits, ips);
   const size_t qpad = static_cast<size_t>(qtiles) * SQ;
 
-  CUtensorMap tmQ, tmG;
-  SPRC_TRY(make_tmap_bf16(&tmQ, queries, 256, (uint64_t)Q, 1, 256, 0, 64, SQ, 1, 2));
+  CUtensorMap tmG;
+  SPRC_REQUIRE((reinterpret_cast<uintptr_t>(queries) & 15) == 0, "sim_topk: queries must be 16-byte aligned");
   SPRC_TRY(make_tmap_bf16(&tmG, gallery, 256, (uint64_t)N * 32, 1, 256, 0, 64, ST, 1, 2));
 
   ScanParams p;
+  p.queries = reinterpret_cast<const uint4*>(queries);
   p.Q = Q;
   p.N = N;
   p.row_offset = row_offset;
   p.k = fused ? k : 0;
   p.qtiles = qtiles;
+  p.ctiles = (qtiles + nq - 1) / nq;
   p.splits = splits;
+  const int heap_bytes = nq * (p.k + PEND) * SQ * 8;
+  p.sstages = (SCAN_SMEM_MAX - 1024 - 256 - heap_bytes) / B_BYTES;
+  if (p.sstages > MAX_SSTAGES) p.sstages = MAX_SSTAGES;
+  SPRC_REQUIRE(p.sstages >= 2, "sim_topk: k=%d leaves no room for the gallery ring", k);
+  const int smem_bytes = p.sstages * B_BYTES + heap_bytes + 256 + 1024;
   p.imgs_per_split = ips;
   p.fp16 = act_fp16();
   p.out_full = out_full;
@@ -418,11 +480,15 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
 
   static bool attr_set = false;
   if (!attr_set) {
-    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_MAX));
+    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_MAX));
     attr_set = true;
   }
   prof_begin(st);
-  scan_topk_kernel<<<qtiles * splits, 192, SCAN_SMEM, st>>>(tmQ, tmG, p);
+  if (nq == 1)
+    scan_topk_kernel<1><<<p.ctiles * splits, 64 + 128, smem_bytes, st>>>(tmG, p);
+  else
+    scan_topk_kernel<2><<<p.ctiles * splits, 64 + 256, smem_bytes, st>>>(tmG, p);
   prof_end(PROF_SCAN, 2.0 * Q * (double)N * 32 * 256, (double)N * 32 * 256 * 2 + (double)Q * 512, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
