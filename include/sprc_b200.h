@@ -140,6 +140,11 @@ int sprc_profile_dump(const char* path);
 int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
                  int grp_stride, const float* bias, const float* residual, float* out_f32, void* out_bf16,
                  int ldc, int act, int impl, void* stream);
+/* out_f32 = LayerNorm(A W^T + bias + residual) * gamma + beta over rows of N = 768, out_ln16 = the same in the 16-bit
+ * operand format (fused Q-Former post-LN sublayer, Qformer.py:291-295,373-381); residual may alias out_f32. */
+int sprc_op_gemm_ln(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
+                    int grp_stride, const float* bias, const float* residual, const float* gamma, const float* beta,
+                    float eps, float* out_f32, void* out_ln16, int ldc, void* stream);
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream);
 int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int B, int H, int dh, int Lq,

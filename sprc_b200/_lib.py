@@ -86,6 +86,11 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
          c_void_p, c_int, c_int, c_int, c_void_p],
     ),
+    "sprc_op_gemm_ln": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
+    ),
     "sprc_op_layernorm": (
         c_int,
         [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p],

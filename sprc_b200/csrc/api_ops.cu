@@ -52,6 +52,26 @@ int sprc_op_gemm(const void* A, const void* W, int M, int N, int K, int lda, int
   return impl == 0 ? gemm_bf16_tcgen05(d, st) : gemm_bf16_simt(d, st);
 }
 
+int sprc_op_gemm_ln(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int grp_rows, int grp_stride,
+                    const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
+                    float* out_f32, void* out_ln16, int ldc, void* stream) {
+  GemmDesc d;
+  d.A = static_cast<const bf16*>(A);
+  d.W = static_cast<const bf16*>(W);
+  d.M = M;
+  d.N = N;
+  d.K = K;
+  d.lda = lda;
+  d.ldw = ldw;
+  d.grp_rows = grp_rows;
+  d.grp_stride = grp_stride;
+  d.bias = bias;
+  d.residual = residual;
+  d.out_f32 = out_f32;
+  d.ldc = ldc;
+  return gemm_ln_tcgen05(d, gamma, beta, eps, static_cast<bf16*>(out_ln16), static_cast<cudaStream_t>(stream));
+}
+
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream) {
   return layernorm(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32, static_cast<bf16*>(out_bf16),

@@ -86,5 +86,9 @@ struct GemmDesc {
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)
 int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st);     // CUDA-core checker used by tests only
+// out_f32 = LayerNorm(A W^T + bias + residual) * gamma + beta over rows of N = 768 (fp32, may alias the residual),
+// out_ln16 = the same values in the 16-bit operand format (same row mapping and pitch ldc): gemm_ln.cu
+int gemm_ln_tcgen05(const GemmDesc& d, const float* gamma, const float* beta, float eps, bf16* out_ln16,
+                    cudaStream_t st);
 
 }  // namespace sprc

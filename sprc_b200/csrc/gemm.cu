@@ -315,6 +315,11 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int esz, uint64_t d0, uin
   return 0;
 }
 
+int make_tmap_any(CUtensorMap* tm, const void* ptr, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                  uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank, int swizzle_bytes) {
+  return make_tmap(tm, ptr, esz, d0, d1, d2, stride1, stride2, b0, b1, b2, rank, swizzle_bytes);
+}
+
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                    uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank) {
   return make_tmap(tm, ptr, 2, d0, d1, d2, stride1, stride2, b0, b1, b2, rank, 128);

@@ -7,6 +7,7 @@
 //   heads        blip2_models/blip2_qformer_cir_align_prompt.py:348-350,385 ; rerank: blip2_qformer_cir_rerank.py:399-445
 // Data layout in HBM: activations are row-major [tokens, features]; the residual stream and every
 // LayerNorm input are fp32, GEMM operands are bf16 copies written by the producing kernel's epilogue.
+#include <stdlib.h>
 #include "model.h"
 
 #include <string.h>
@@ -401,6 +402,42 @@ static int linear(const bf16* A, int M, int K, int lda, const bf16* W, int N, co
   return gemm_bf16_tcgen05(d, st);
 }
 
+// dense + residual + LayerNorm of a post-LN Q-Former sublayer (Qformer.py:291-295, 373-381): x (fp32, in place) and
+// xb (16-bit copy) <- LayerNorm(A W^T + bias + x).  Default: GEMM with TMA reduce-add into x, then the LayerNorm
+// kernel.  SPRC_FUSED_LN=1 selects the single cluster kernel of gemm_ln.cu: bit-compatible (tests/test_ops_gpu.py)
+// and 44 % less HBM traffic per sublayer, but measured SLOWER on B200 (137 us against 71 + 53 us at M = 37888,
+// K = 768: its extra 64-byte TMA store requests land on the per-SM TMA request rate that already paces the 768-wide
+// GEMMs, profiles/r01c_gemm_ln_*), so it stays opt-in until the mainloop moves to CTA pairs.
+static bool fused_ln_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPRC_FUSED_LN");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+static int linear_ln(const bf16* A, int M, int K, int lda, const bf16* W, const float* bias, const float* gamma,
+                     const float* beta, float eps, float* x, bf16* xb, int grp_rows, int grp_stride, cudaStream_t st) {
+  if (!fused_ln_enabled()) {
+    SPRC_TRY(linear(A, M, K, lda, W, 768, bias, ACT_NONE, x, x, nullptr, 768, grp_rows, grp_stride, st));
+    return layernorm(x, M, 768, gamma, beta, eps, grp_rows, grp_stride, x, xb, st);
+  }
+  GemmDesc d;
+  d.A = A;
+  d.W = W;
+  d.M = M;
+  d.N = 768;
+  d.K = K;
+  d.lda = lda;
+  d.ldw = K;
+  d.grp_rows = grp_rows;
+  d.grp_stride = grp_stride;
+  d.bias = bias;
+  d.residual = x;
+  d.out_f32 = x;
+  d.ldc = 768;
+  return gemm_ln_tcgen05(d, gamma, beta, eps, xb, st);
+}
+
 int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_bf16, cudaStream_t st) {
   SPRC_REQUIRE(B > 0 && B <= vit_cap, "vit_forward: B=%d outside (0, %d]", B, vit_cap);
   const int T = B * 257;
@@ -476,16 +513,14 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
     SPRC_TRY(attention(a, st));
     // post-LN residual sublayers (Qformer.py:291-295): qh += dense(ctx) by TMA reduce-add, then LayerNorm in place
     if (live == QF_OUT_ALL) {
-      SPRC_TRY(linear(qctx, rows, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
-      SPRC_TRY(layernorm(qh, rows, 768, L.so_g, L.so_beta, 1e-12f, 0, 0, qh, qhb, st));
+      SPRC_TRY(linear_ln(qctx, rows, 768, 768, L.so_w, L.so_b, L.so_g, L.so_beta, 1e-12f, qh, qhb, 0, 0, st));
     } else {
       // QF_OUT_QUERY_ROWS: rows [0,32) of each sample; QF_OUT_TEXT_CLS: row 32 of each sample
       const int gr = live == QF_OUT_QUERY_ROWS ? 32 : 1;
       const size_t o = live == QF_OUT_QUERY_ROWS ? 0 : 32;
       const int m = B * gr;
-      SPRC_TRY(linear(qctx + o * 768, m, 768, 768, L.so_w, 768, L.so_b, ACT_NONE, qh + o * 768, qh + o * 768, nullptr,
-                      768, gr, 64, st));
-      SPRC_TRY(layernorm(qh + o * 768, m, 768, L.so_g, L.so_beta, 1e-12f, gr, 64, qh + o * 768, qhb + o * 768, st));
+      SPRC_TRY(linear_ln(qctx + o * 768, m, 768, 768, L.so_w, L.so_b, L.so_g, L.so_beta, 1e-12f, qh + o * 768,
+                         qhb + o * 768, gr, 64, st));
     }
     if (with_enc) {
       if (L.has_cross) {
@@ -512,34 +547,28 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         c.kv_idx1 = kv_idx1;
         c.Lk1 = 257;
         SPRC_TRY(attention(c, st));
-        SPRC_TRY(linear(qctx, B * 32, 768, 768, L.co_w, 768, L.co_b, ACT_NONE, qh, qh, nullptr, 768, g, gs, st));
-        SPRC_TRY(layernorm(qh, B * 32, 768, L.co_g, L.co_beta, 1e-12f, g, gs, qh, qhb, st));
+        SPRC_TRY(linear_ln(qctx, B * 32, 768, 768, L.co_w, L.co_b, L.co_g, L.co_beta, 1e-12f, qh, qhb, g, gs, st));
       }
       // query rows -> *_query FFN; text rows -> text FFN (Qformer.py:455-468)
       SPRC_TRY(linear(qhb, B * 32, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, g, gs, st));
-      SPRC_TRY(linear(qffn, B * 32, 3072, 3072, L.qo_w, 768, L.qo_b, ACT_NONE, qh, qh, nullptr, 768, g, gs, st));
-      SPRC_TRY(layernorm(qh, B * 32, 768, L.qo_g, L.qo_beta, 1e-12f, g, gs, qh, qhb, st));
+      SPRC_TRY(linear_ln(qffn, B * 32, 3072, 3072, L.qo_w, L.qo_b, L.qo_g, L.qo_beta, 1e-12f, qh, qhb, g, gs, st));
       if (S == 64 && live == QF_OUT_ALL) {
         const size_t o = 32;
         SPRC_TRY(linear(qhb + o * 768, B * 32, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
                         qffn + o * 3072, 3072, g, gs, st));
-        SPRC_TRY(linear(qffn + o * 3072, B * 32, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh + o * 768,
-                        qh + o * 768, nullptr, 768, g, gs, st));
-        SPRC_TRY(layernorm(qh + o * 768, B * 32, 768, L.to_g, L.to_beta, 1e-12f, g, gs, qh + o * 768,
-                           qhb + o * 768, st));
+        SPRC_TRY(linear_ln(qffn + o * 3072, B * 32, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f,
+                           qh + o * 768, qhb + o * 768, g, gs, st));
       }
     } else if (live == QF_OUT_TEXT_CLS) {
       const size_t o = 32;
       SPRC_TRY(linear(qhb + o * 768, B, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn + o * 3072,
                       3072, 1, 64, st));
-      SPRC_TRY(linear(qffn + o * 3072, B, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh + o * 768, qh + o * 768,
-                      nullptr, 768, 1, 64, st));
-      SPRC_TRY(layernorm(qh + o * 768, B, 768, L.to_g, L.to_beta, 1e-12f, 1, 64, qh + o * 768, qhb + o * 768, st));
+      SPRC_TRY(linear_ln(qffn + o * 3072, B, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f, qh + o * 768,
+                         qhb + o * 768, 1, 64, st));
     } else {
       // no encoder states: every row takes the text FFN (Qformer.py:469-475, the "baiyang change" at :434-435)
       SPRC_TRY(linear(qhb, rows, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
-      SPRC_TRY(linear(qffn, rows, 3072, 3072, L.to_w, 768, L.to_b, ACT_NONE, qh, qh, nullptr, 768, 0, 0, st));
-      SPRC_TRY(layernorm(qh, rows, 768, L.to_g, L.to_beta, 1e-12f, 0, 0, qh, qhb, st));
+      SPRC_TRY(linear_ln(qffn, rows, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f, qh, qhb, 0, 0, st));
     }
   }
   return 0;

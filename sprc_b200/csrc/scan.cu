@@ -4,8 +4,8 @@
 //
 // The reference expands the gallery Bq times and sorts all N scores per query.  Here one persistent
 // kernel streams the bf16 gallery [N*32, 256] from HBM exactly once per 128-query tile:
-//   warp 0      TMA producer: 64 gallery tokens (2 images) x 256 dims per stage, 4-stage ring
-//   warp 1      tcgen05.mma issuer: D[128 queries, 64 tokens] = Qtile[128,256] * G[64,256]^T, fp32 in TMEM
+//   warp 0      TMA producer: 64 gallery tokens (2 images) x 256 dims per ring slot, 4 slots
+//   warp 1      tcgen05.mma issuer: D[128 queries, 128 tokens] = Qtile[128,256] (TMEM) * G[128,256]^T (slot pair), fp32 in TMEM
 //               (queries on TMEM lanes so that the max over an image's 32 tokens is a per-thread max
 //               over 32 accumulator columns - no shuffles)
 //   warps 2..5  epilogue: one thread per query; keeps that query's running top-k as a binary min-heap in
@@ -23,14 +23,19 @@ namespace sprc {
 int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                    uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2, int rank);
 
-static constexpr int SQ = 128;        // queries per query tile (UMMA M)
-static constexpr int ST = 64;         // gallery tokens per stage (UMMA N) = 2 images
-static constexpr int MAX_SSTAGES = 4; // gallery ring depth (32 KB per stage), as many as fit next to the heaps
+static constexpr int SQ = 128;        // queries per CTA (UMMA M)
+static constexpr int ST = 64;         // gallery tokens per ring slot = 2 images (one TMA transaction group)
+static constexpr int PT = 2 * ST;     // gallery tokens per MMA (UMMA N) = one PAIR of adjacent ring slots = 4 images
+static constexpr int SSLOTS = 4;      // ring slots (32 KB each): one pair being consumed, one being filled
+static constexpr int AS = 3;          // accumulator stages in TMEM (128 fp32 columns each)
 static constexpr int KCAP = 64;       // heap capacity (fused path handles k <= 64)
 static constexpr int PEND = 8;        // per-query pending candidates between heap flushes
 static constexpr int SEG = 4096;      // segment width of the large-k path
-static constexpr int B_BYTES = ST * 256 * 2;   // 32 KB
-static constexpr int SCAN_SMEM_MAX = 227 * 1024;
+static constexpr int SLOT_BYTES = ST * 256 * 2;     // 32 KB
+static constexpr int SLAB_BYTES = ST * 128;         // one K block (64 dims) of one slot: 64 rows x 128 B
+static constexpr int KB_STRIDE = SSLOTS * SLAB_BYTES;  // K-block regions hold the slabs of all slots back to back
+static constexpr int TM_COL_A = 0;    // query tile: 128 lanes x 128 columns of packed 16-bit pairs (K = 256)
+static constexpr int TM_COL_D = 128;  // AS x 128 fp32 accumulator columns
 
 typedef unsigned long long u64;
 
@@ -57,61 +62,58 @@ struct ScanParams {
   long long N;
   long long row_offset;
   int k;
-  int qtiles;                // 128-query tiles
-  int ctiles;                // CTA tiles = ceil(qtiles / NQ)
-  int splits;
-  int sstages;               // gallery ring depth actually allocated (2..MAX_SSTAGES)
-  long long imgs_per_split;  // even
+  int qtiles, splits;
+  long long imgs_per_split;  // multiple of 4
   int fp16;                  // operand format of queries / gallery
   float* out_full;           // [Q, N] or null
   u64* cand;                 // [splits][k][qtiles*128] or null
 };
 
-// The query tiles are the A operands of every MMA of the CTA, so they live in TENSOR MEMORY (tcgen05.mma with A in
-// TMEM): shared memory carries only the gallery stream (one TMA write + one UMMA read per byte and query tile).
-// NQ = 1: one 128-query tile per CTA, every SM pulls its own slice of the gallery from HBM (HBM-bound regime).
-// NQ = 2: two query tiles share each gallery stage.  With one tile per CTA a 592-query scan re-read the gallery
-// five times from L2 and ran at the L2 -> SM bandwidth (5.9 TB/s = 128 FLOP per L2 byte, 700 TFLOP/s:
-// profiles/r01b_*); two tiles per stage halve the L2 and TMA traffic per FLOP.
-template <int NQ>
-__global__ void __launch_bounds__(64 + NQ * 128, 1)
+// Design notes (measured, profiles/r01b_* and the exp1/exp2 bench logs):
+//  * The query tile is the A operand of every MMA of the CTA, so it lives in TENSOR MEMORY (tcgen05.mma with A in
+//    TMEM) and shared memory carries only the gallery stream.
+//  * The 16 K-step MMAs of a score tile accumulate into the same TMEM columns, i.e. they form a dependent chain: with
+//    N = 64 every MMA took ~73 cycles (twice its 32-cycle issue floor) and the tensor pipe, not HBM or L2, paced the
+//    scan at 44 % activity for 1 and for 2 query tiles per CTA alike.  The ring therefore stores the K-block slabs of
+//    ADJACENT slots back to back (slot s, K block kb at kb * KB_STRIDE + s * SLAB_BYTES), so that two 64-token slots
+//    form one contiguous 128-row K-major operand and each MMA is 128 x 128 x 16 (64-cycle floor): half the
+//    instructions per gallery byte while TMA transactions stay 32 KB.
+//  * A candidate that beats the heap minimum is only QUEUED; the warp drains the queues together when one of them is
+//    nearly full.  Inserting at once made the whole warp walk the sift-down loop whenever any of its 32 queries had
+//    a hit (almost every image while a split's threshold is still loose).
+__global__ void __launch_bounds__(192, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
-  constexpr int AS = NQ == 1 ? 4 : 2;          // accumulator stages per query tile (64 fp32 columns each)
-  constexpr int TM_COL_D = NQ * 128;           // after the query tiles (128 columns of packed 16-bit pairs each)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nst = p.sstages;
-  const int heap_slots = p.k + PEND;
   uint8_t* sB = smem;
-  u64* heap = reinterpret_cast<u64*>(smem + nst * B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * B_BYTES + NQ * heap_slots * SQ * 8);
-  uint64_t* full_bar = bars;                           // [MAX_SSTAGES]
-  uint64_t* empty_bar = bars + MAX_SSTAGES;            // [MAX_SSTAGES]
-  uint64_t* tfull_bar = bars + 2 * MAX_SSTAGES;        // [NQ * AS]
-  uint64_t* tempty_bar = tfull_bar + NQ * AS;          // [NQ * AS]
-  uint64_t* q_bar = tempty_bar + NQ * AS;              // [1]
+  u64* heap = reinterpret_cast<u64*>(smem + SSLOTS * SLOT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SSLOTS * SLOT_BYTES + (p.k + PEND) * SQ * 8);
+  uint64_t* full_bar = bars;                   // [SSLOTS]
+  uint64_t* empty_bar = bars + SSLOTS;         // [SSLOTS]
+  uint64_t* tfull_bar = bars + 2 * SSLOTS;     // [AS]
+  uint64_t* tempty_bar = tfull_bar + AS;       // [AS]
+  uint64_t* q_bar = tempty_bar + AS;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ct = blockIdx.x % p.ctiles;
-  const int sp = blockIdx.x / p.ctiles;
+  const int qt = blockIdx.x % p.qtiles;
+  const int sp = blockIdx.x / p.qtiles;
   const long long n_begin = static_cast<long long>(sp) * p.imgs_per_split;
   long long n_end = n_begin + p.imgs_per_split;
   if (n_end > p.N) n_end = p.N;
-  const int stages_total = n_end > n_begin ? static_cast<int>((n_end - n_begin + 1) / 2) : 0;
-  const int live_tiles = (p.qtiles - ct * NQ) < NQ ? (p.qtiles - ct * NQ) : NQ;   // 1..NQ query tiles with real rows
+  const int pairs_total = n_end > n_begin ? static_cast<int>((n_end - n_begin + 3) / 4) : 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmG);
-    for (int s = 0; s < MAX_SSTAGES; ++s) {
+    for (int s = 0; s < SSLOTS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < NQ * AS; ++s) {
+    for (int s = 0; s < AS; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
     }
-    mbar_init(q_bar, 4 * NQ);
+    mbar_init(q_bar, 4);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -122,50 +124,51 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
 
   if (warp == 0) {
     if (elect_one()) {
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < stages_total; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], B_BYTES);
+      // rows past the end of the gallery (odd tails) are zero-filled by the TMA and never scored
+      for (int it = 0; it < 2 * pairs_total; ++it) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        mbar_expect_tx(&full_bar[slot], SLOT_BYTES);
         const long long row0 = (n_begin + 2LL * it) * 32;
         for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d(&tmG, &full_bar[stage], sB + stage * B_BYTES + kb * (ST * 128), kb * 64,
-                      static_cast<int>(row0), p.ctiles > 1 ? kEvictNormal : kEvictFirst);
-        if (++stage == nst) {
-          stage = 0;
+          tma_load_2d(&tmG, &full_bar[slot], sB + kb * KB_STRIDE + slot * SLAB_BYTES, kb * 64,
+                      static_cast<int>(row0), p.qtiles > 1 ? kEvictNormal : kEvictFirst);
+        if (++slot == SSLOTS) {
+          slot = 0;
           phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_16(SQ, ST, p.fp16);
-    mbar_wait(q_bar, 0);   // the epilogue warps have written the query tiles into TMEM
+    const uint32_t idesc = umma_idesc_16(SQ, PT, p.fp16);
+    mbar_wait(q_bar, 0);   // the epilogue warps have written the query tile into TMEM
     tc_fence_after();
-    int stage = 0, as = 0;
+    int slot = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
-    for (int it = 0; it < stages_total; ++it) {
-      for (int sub = 0; sub < live_tiles; ++sub) mbar_wait(&tempty_bar[sub * AS + as], aphase ^ 1);
-      mbar_wait(&full_bar[stage], phase);
+    for (int pr = 0; pr < pairs_total; ++pr) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      mbar_wait(&full_bar[slot], phase);
+      mbar_wait(&full_bar[slot + 1], phase);
       tc_fence_after();
       if (elect_one()) {
-        for (int sub = 0; sub < live_tiles; ++sub) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(TM_COL_D + (sub * AS + as) * ST);
-          const uint32_t a_tmem = tmem_base + static_cast<uint32_t>(sub * 128);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(TM_COL_D + as * PT);
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks) {
-            // K step ks: dims [16 ks, 16 ks + 16) = TMEM columns [8 ks, 8 ks + 8) of the query tile; gallery K
-            // block ks / 4, +32 B per step inside the 128 B swizzle row
-            const uint64_t db =
-                umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES + (ks >> 2) * (ST * 128))) + 2 * (ks & 3);
-            umma_bf16_ts(d_tmem, a_tmem + ks * 8, db, idesc, ks != 0 ? 1u : 0u);
-          }
-          umma_commit(&tfull_bar[sub * AS + as]);
+        for (int ks = 0; ks < 16; ++ks) {
+          // K step ks: dims [16 ks, 16 ks + 16) = TMEM columns [8 ks, 8 ks + 8) of the query tile; gallery K block
+          // ks / 4 (rows of both slots contiguous), +32 B per step inside the 128 B swizzle row
+          const uint64_t db =
+              umma_desc_k_sw128(smem_u32(sB + (ks >> 2) * KB_STRIDE + slot * SLAB_BYTES)) + 2 * (ks & 3);
+          umma_bf16_ts(d_tmem, tmem_base + TM_COL_A + ks * 8, db, idesc, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
+        umma_commit(&empty_bar[slot]);
+        umma_commit(&empty_bar[slot + 1]);
+        umma_commit(&tfull_bar[as]);
       }
       __syncwarp();
-      if (++stage == nst) {
-        stage = 0;
+      slot += 2;
+      if (slot == SSLOTS) {
+        slot = 0;
         phase ^= 1;
       }
       if (++as == AS) {
@@ -175,10 +178,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
     }
   } else {
     // ===================== epilogue: one thread per query =====================
-    const int sub = (warp - 2) >> 2;       // query tile of this warp
     const int qw = warp & 3;               // TMEM lane quarter this warp may access
     const int ql = qw * 32 + lane;         // query row inside the tile = TMEM lane
-    const int q = (ct * NQ + sub) * SQ + ql;
+    const int q = qt * SQ + ql;
     const bool q_ok = q < p.Q;
     const int k = p.k;
     const uint32_t lane_addr = static_cast<uint32_t>(qw * 32) << 16;
@@ -194,7 +196,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
           if (q_ok) v = __ldg(src + c * 8 + j);
           r[4 * j] = v.x, r[4 * j + 1] = v.y, r[4 * j + 2] = v.z, r[4 * j + 3] = v.w;
         }
-        tmem_st32(tmem_base + lane_addr + sub * 128 + c * 32, r);
+        tmem_st32(tmem_base + lane_addr + TM_COL_A + c * 32, r);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -203,14 +205,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
     }
     constexpr uint32_t HS = SQ * 8;
     // slot j of this query's heap at byte offset j * HS (slot-major: conflict-free for any mix of heap positions)
-    const uint32_t myheap = smem_u32(heap) + static_cast<uint32_t>(sub * heap_slots) * HS + ql * 8;
+    const uint32_t myheap = smem_u32(heap) + ql * 8;
     const uint32_t mypend = myheap + k * HS;    // PEND pending candidates
     for (int j = 0; j < k; ++j) sts64(myheap + j * HS, static_cast<u64>(j));  // distinct sub-minimal keys, valid min-heap
     u64 root = 0;
     int pcnt = 0;
-    // A candidate that beats the heap minimum is only QUEUED; the warp drains the queues together when one of them
-    // is nearly full.  Inserting at once made the whole warp walk the sift-down loop whenever any of its 32 queries
-    // had a hit (almost every image while a split's threshold is still loose).
     auto flush = [&]() {
       for (int j = 0; j < pcnt; ++j) {
         const u64 key = lds64(mypend + j * HS);
@@ -233,27 +232,30 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
       }
       pcnt = 0;
     };
-    if (sub < live_tiles) {
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int it = 0; it < stages_total; ++it) {
-        mbar_wait(&tfull_bar[sub * AS + as], aphase);
-        tc_fence_after();
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int pr = 0; pr < pairs_total; ++pr) {
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_addr + static_cast<uint32_t>(TM_COL_D + as * PT);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + lane_addr + static_cast<uint32_t>(TM_COL_D + (sub * AS + as) * ST);
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + half * 64, r0);
+        tmem_ld32(taddr + half * 64 + 32, r1);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[sub * AS + as]);  // accumulator is in registers: release TMEM early
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);  // accumulator is in registers: release TMEM early
+        }
         float s0 = __uint_as_float(r0[0]), s1 = __uint_as_float(r1[0]);
 #pragma unroll
         for (int j = 1; j < 32; ++j) {
           s0 = fmaxf(s0, __uint_as_float(r0[j]));
           s1 = fmaxf(s1, __uint_as_float(r1[j]));
         }
-        const long long n0 = n_begin + 2LL * it;
+        const long long n0 = n_begin + 4LL * pr + 2 * half;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const long long n = n0 + e;
@@ -270,16 +272,16 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmG, const ScanParams p) {
           }
         }
         if (__any_sync(0xffffffffu, pcnt > PEND - 2)) flush();
-        if (++as == AS) {
-          as = 0;
-          aphase ^= 1;
-        }
       }
-      flush();
-      if (p.cand && q_ok) {
-        const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
-        for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = lds64(myheap + j * HS);
+      if (++as == AS) {
+        as = 0;
+        aphase ^= 1;
       }
+    }
+    flush();
+    if (p.cand && q_ok) {
+      const size_t qpad = static_cast<size_t>(p.qtiles) * SQ;
+      for (int j = 0; j < k; ++j) p.cand[(static_cast<size_t>(sp) * k + j) * qpad + q] = lds64(myheap + j * HS);
     }
   }
 
@@ -393,20 +395,18 @@ int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, i
 }
 
 // workspace: candidate keys of the fused path, or [full matrix +] segment candidates of the large-k path
-static void scan_plan(int Q, long long N, int k, int& qtiles, int& nq, int& splits, long long& ips) {
+static void scan_plan(int Q, long long N, int k, int& qtiles, int& splits, long long& ips) {
   qtiles = (Q + SQ - 1) / SQ;
-  nq = qtiles > 1 ? 2 : 1;  // query tiles per CTA (see scan_topk_kernel)
-  const int ctiles = (qtiles + nq - 1) / nq;
   const int sms = device_sm_count();
-  splits = sms / ctiles;
+  splits = sms / qtiles;
   if (splits < 1) splits = 1;
-  const long long max_splits = (N + 1) / 2;  // at least one stage (2 images) per split
+  const long long max_splits = (N + 3) / 4;  // at least one slot pair (4 images) per split
   if (splits > max_splits) splits = static_cast<int>(max_splits > 0 ? max_splits : 1);
   // keep the merge within capacity (splits * k <= 16384)
   while (static_cast<long long>(splits) * k > 16384 && splits > 1) --splits;
   ips = (N + splits - 1) / splits;
-  if (ips & 1) ++ips;
-  if (ips < 2) ips = 2;
+  ips = (ips + 3) & ~3LL;
+  if (ips < 4) ips = 4;
   splits = static_cast<int>((N + ips - 1) / ips);
   if (splits < 1) splits = 1;
 }
@@ -430,9 +430,9 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
   SPRC_REQUIRE(!want_topk || (k > 0 && k <= 1024), "sim_topk: k=%d outside [1, 1024]", k);
   SPRC_REQUIRE(want_topk || out_full, "sim_topk: no output requested");
   const bool fused = want_topk && k <= KCAP;
-  int qtiles, nq, splits;
+  int qtiles, splits;
   long long ips;
-  scan_plan(Q, N, fused ? k : 1, qtiles, nq, splits, ips);
+  scan_plan(Q, N, fused ? k : 1, qtiles, splits, ips);
   const size_t qpad = static_cast<size_t>(qtiles) * SQ;
 
   CUtensorMap tmG;
@@ -446,13 +446,8 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
   p.row_offset = row_offset;
   p.k = fused ? k : 0;
   p.qtiles = qtiles;
-  p.ctiles = (qtiles + nq - 1) / nq;
   p.splits = splits;
-  const int heap_bytes = nq * (p.k + PEND) * SQ * 8;
-  p.sstages = (SCAN_SMEM_MAX - 1024 - 256 - heap_bytes) / B_BYTES;
-  if (p.sstages > MAX_SSTAGES) p.sstages = MAX_SSTAGES;
-  SPRC_REQUIRE(p.sstages >= 2, "sim_topk: k=%d leaves no room for the gallery ring", k);
-  const int smem_bytes = p.sstages * B_BYTES + heap_bytes + 256 + 1024;
+  const int smem_bytes = SSLOTS * SLOT_BYTES + (p.k + PEND) * SQ * 8 + 256 + 1024;
   p.imgs_per_split = ips;
   p.fp16 = act_fp16();
   p.out_full = out_full;
@@ -480,15 +475,12 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
 
   static bool attr_set = false;
   if (!attr_set) {
-    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_MAX));
-    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_MAX));
+    SPRC_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SSLOTS * SLOT_BYTES + (KCAP + PEND) * SQ * 8 + 256 + 1024));
     attr_set = true;
   }
   prof_begin(st);
-  if (nq == 1)
-    scan_topk_kernel<1><<<p.ctiles * splits, 64 + 128, smem_bytes, st>>>(tmG, p);
-  else
-    scan_topk_kernel<2><<<p.ctiles * splits, 64 + 256, smem_bytes, st>>>(tmG, p);
+  scan_topk_kernel<<<qtiles * splits, 192, smem_bytes, st>>>(tmG, p);
   prof_end(PROF_SCAN, 2.0 * Q * (double)N * 32 * 256, (double)N * 32 * 256 * 2 + (double)Q * 512, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());

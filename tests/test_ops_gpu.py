@@ -1,0 +1,130 @@
+"""Single-kernel parity (GPU, through the C ABI): tcgen05 GEMM epilogues, LayerNorm and the fused
+GEMM + residual + LayerNorm sublayer kernel against torch fp32 on the same bf16-rounded operands.
+
+Reference semantics: nn.Linear / LayerNorm as used by Qformer.py:291-295,373-381 (post-LN sublayers, eps 1e-12)
+and eva_vit.py:55-59 (bias + GELU).  Tolerances are stated per test; fp32 outputs differ from torch only by
+accumulation order (fp32 accumulate in TMEM), 16-bit outputs by one rounding.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sprc_b200 import _lib as L
+
+    return L, L.load()
+
+
+def _phys_rows(M, grp_rows, grp_stride, device):
+    m = torch.arange(M, device=device)
+    if grp_rows == 0:
+        return m
+    return (m // grp_rows) * grp_stride + (m % grp_rows)
+
+
+@pytest.mark.parametrize("M,K,grp", [(128, 768, (0, 0)), (300, 768, (0, 0)), (1000, 3072, (0, 0)),
+                                     (37888, 768, (0, 0)), (4 * 32, 768, (32, 64)), (37 * 32, 3072, (32, 64)),
+                                     (592, 3072, (1, 64)), (18944, 3072, (32, 64))])
+def test_gemm_ln_fused_matches_torch(lib, M, K, grp):
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    gr, gs = grp
+    rows = M if gr == 0 else (M // gr) * gs
+    A = torch.randn(rows, K, device=dev, generator=g).bfloat16()
+    W = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(768, device=dev, generator=g)
+    gamma = 1 + 0.1 * torch.randn(768, device=dev, generator=g)
+    beta = 0.1 * torch.randn(768, device=dev, generator=g)
+    # residual stream with a per-row offset and scale (so mean/variance handling is exercised)
+    x = torch.randn(rows, 768, device=dev, generator=g) * (0.5 + torch.rand(rows, 1, device=dev, generator=g) * 2) \
+        + torch.randn(rows, 1, device=dev, generator=g)
+    x0 = x.clone()
+    xb = torch.full((rows, 768), float("nan"), device=dev).bfloat16()
+    pr = _phys_rows(M, gr, gs, dev)
+    ref = torch.nn.functional.layer_norm(A[pr].float() @ W.float().T + bias + x0[pr], (768,), gamma, beta, 1e-12)
+    L.check(so.sprc_op_gemm_ln(L.ptr(A), L.ptr(W), M, 768, K, K, K, gr, gs, L.ptr(bias), L.ptr(x), L.ptr(gamma),
+                               L.ptr(beta), 1e-12, L.ptr(x), L.ptr(xb), 768, L.cur_stream()))
+    torch.cuda.synchronize()
+    got = x[pr]
+    err = (got - ref).abs().max().item()
+    assert torch.isfinite(got).all() and err < 2e-3, err          # fp32 out: accumulation-order differences only
+    errb = (xb[pr].float() - ref).abs().max().item()
+    assert errb < 4e-2, errb                                       # one bf16 rounding of |values| <~ 5
+    if gr:  # rows outside the groups are untouched
+        mask = torch.ones(rows, dtype=torch.bool, device=dev)
+        mask[pr] = False
+        assert torch.equal(x[mask], x0[mask])
+        assert torch.isnan(xb[mask].float()).all()
+
+
+def test_gemm_ln_equals_unfused_pair(lib):
+    """Same inputs through the two-kernel form (GEMM reduce-add + LayerNorm kernel): max difference at fp32 noise."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    M, K = 4096, 3072
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    W = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(768, device=dev, generator=g)
+    gamma = torch.rand(768, device=dev, generator=g) + 0.5
+    beta = torch.randn(768, device=dev, generator=g)
+    x = torch.randn(M, 768, device=dev, generator=g)
+    x1, x2 = x.clone(), x.clone()
+    b1 = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    b2 = torch.empty_like(b1)
+    L.check(so.sprc_op_gemm_ln(L.ptr(A), L.ptr(W), M, 768, K, K, K, 0, 0, L.ptr(bias), L.ptr(x1), L.ptr(gamma),
+                               L.ptr(beta), 1e-12, L.ptr(x1), L.ptr(b1), 768, L.cur_stream()))
+    L.check(so.sprc_op_gemm(L.ptr(A), L.ptr(W), M, 768, K, K, K, 0, 0, L.ptr(bias), L.ptr(x2), L.ptr(x2), None, 768, 0,
+                            0, L.cur_stream()))
+    L.check(so.sprc_op_layernorm(L.ptr(x2), M, 768, L.ptr(gamma), L.ptr(beta), 1e-12, 0, 0, L.ptr(x2), L.ptr(b2),
+                                 L.cur_stream()))
+    torch.cuda.synchronize()
+    assert (x1 - x2).abs().max().item() < 1e-4
+    assert (b1.float() - b2.float()).abs().max().item() <= 4e-2
+
+
+@pytest.mark.parametrize("M,N,K,act,res,f32", [(300, 384, 1024, 1, False, False), (1028, 1024, 4096, 0, True, True),
+                                               (771, 1408, 1408, 2, False, False), (512, 1024, 592, 0, False, True)])
+def test_gemm_epilogues_match_torch(lib, M, N, K, act, res, f32):
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    W = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    R = torch.randn(M, N, device=dev, generator=g) if res else None
+    ref = A.float() @ W.float().T + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if res:
+        ref = ref + R
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    L.check(so.sprc_op_gemm(L.ptr(A), L.ptr(W), M, N, K, K, K, 0, 0, L.ptr(bias), L.ptr(R), L.ptr(out) if f32 else None,
+                            None if f32 else L.ptr(out), N, act, 0, L.cur_stream()))
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < (5e-4 if f32 else 5e-2), err     # GELU uses the approx-MUFU erf (<= 2e-4 abs) on the GPU
+
+
+@pytest.mark.parametrize("rows,width", [(257, 1024), (1000, 1408), (4096, 768)])
+def test_layernorm_matches_torch(lib, rows, width):
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(rows)
+    x = torch.randn(rows, width, device=dev, generator=g) * 3 + 1
+    gamma = torch.rand(width, device=dev, generator=g) + 0.5
+    beta = torch.randn(width, device=dev, generator=g)
+    of = torch.empty_like(x)
+    ob = torch.empty(rows, width, device=dev, dtype=torch.bfloat16)
+    L.check(so.sprc_op_layernorm(L.ptr(x), rows, width, L.ptr(gamma), L.ptr(beta), 1e-5, 0, 0, L.ptr(of), L.ptr(ob),
+                                 L.cur_stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (width,), gamma, beta, 1e-5)
+    assert (of - ref).abs().max().item() < 2e-5
+    assert (ob.float() - ref).abs().max().item() < 4e-2
