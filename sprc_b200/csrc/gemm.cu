@@ -421,6 +421,9 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   return 0;
 }
 
+bool gemm_2cta_enabled();
+int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st);   // gemm2.cu
+
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   SPRC_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem %dx%dx%d", d.M, d.N, d.K);
   SPRC_REQUIRE(d.N % 32 == 0, "gemm: N=%d must be a multiple of 32", d.N);
@@ -432,6 +435,10 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   SPRC_REQUIRE(d.grp_rows == 0 || (BM % d.grp_rows == 0 && d.M % d.grp_rows == 0 && d.grp_stride >= d.grp_rows),
                "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
+  // CTA pairs (256 x 256 tiles) whenever every pair gets work; the single-CTA kernels cover ragged N and small problems
+  if (gemm_2cta_enabled() && d.N % 256 == 0 && tiles256 >= device_sm_count() &&
+      (!d.residual || d.residual == d.out_f32))
+    return launch_gemm_2cta(d, st);
   if (d.N % 256 == 0 && tiles256 >= device_sm_count()) return launch_gemm<256, 4>(d, st);
   return launch_gemm<128, 6>(d, st);
 }

@@ -59,11 +59,6 @@ struct LnParams {
   int rev;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ uint32_t cluster_id_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
@@ -73,9 +68,6 @@ __device__ __forceinline__ uint32_t num_clusters_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
   return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;

@@ -128,3 +128,43 @@ def test_layernorm_matches_torch(lib, rows, width):
     ref = torch.nn.functional.layer_norm(x, (width,), gamma, beta, 1e-5)
     assert (of - ref).abs().max().item() < 2e-5
     assert (ob.float() - ref).abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize("M,N,K,act,res,f32,grp", [
+    (32896, 3072, 1024, 0, False, False, (0, 0)),     # ViT-L qkv: 128.5 pair tiles in M (last pair half empty)
+    (32896, 1024, 4096, 0, True, True, (0, 0)),       # ViT-L fc2 + residual (TMA reduce-add)
+    (19000, 4096, 1024, 1, False, False, (0, 0)),     # ragged M, GELU
+    (37888, 768, 768, 0, True, True, (0, 0)),         # Q-Former output dense
+    (592 * 32, 3072, 768, 1, False, False, (32, 64)),  # grouped "query rows only" FFN
+    (592 * 32, 768, 3072, 0, True, True, (32, 64)),
+    (8192, 8192, 1024, 0, False, False, (0, 0)),
+])
+def test_gemm_cta_pair_kernel_matches_torch(lib, M, N, K, act, res, f32, grp):
+    """Shapes large enough for the cta_group::2 kernel (256 x 256 tiles per CTA pair, gemm2.cu)."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    gr, gs = grp
+    rows = M if gr == 0 else (M // gr) * gs
+    A = torch.randn(rows, K, device=dev, generator=g).bfloat16()
+    W = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    pr = _phys_rows(M, gr, gs, dev)
+    out = (torch.randn(rows, N, device=dev, generator=g) if f32 else
+           torch.zeros(rows, N, device=dev, dtype=torch.bfloat16))
+    out0 = out.clone()
+    ref = A[pr].float() @ W.float().T + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if res:
+        ref = ref + out0[pr]
+    L.check(so.sprc_op_gemm(L.ptr(A), L.ptr(W), M, N, K, K, K, gr, gs, L.ptr(bias), L.ptr(out) if res else None,
+                            L.ptr(out) if f32 else None, None if f32 else L.ptr(out), N, act, 0, L.cur_stream()))
+    torch.cuda.synchronize()
+    got = out[pr].float()
+    err = (got - ref).abs().max().item()
+    assert torch.isfinite(got).all() and err < (1e-3 if f32 else 6e-2), err
+    if gr:
+        mask = torch.ones(rows, dtype=torch.bool, device=dev)
+        mask[pr] = False
+        assert torch.equal(out[mask], out0[mask])
