@@ -436,8 +436,10 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
                "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
   // CTA pairs (256 x 256 tiles) whenever every pair gets work; the single-CTA kernels cover ragged N and small problems
-  if (gemm_2cta_enabled() && d.N % 256 == 0 && tiles256 >= device_sm_count() &&
-      (!d.residual || d.residual == d.out_f32))
+  // (a ragged last N block - ViT-g's 1408 = 5.5 x 256, 4224 = 16.5 x 256 - runs as a half-empty 256-column tile: its
+  // missing W rows are zero-filled by the TMA and its stores are clipped, 3-9 % padded MMA work against the ~25 %
+  // slower single-CTA kernel)
+  if (gemm_2cta_enabled() && d.N >= 256 && tiles256 >= device_sm_count() && (!d.residual || d.residual == d.out_f32))
     return launch_gemm_2cta(d, st);
   if (d.N % 256 == 0 && tiles256 >= device_sm_count()) return launch_gemm<256, 4>(d, st);
   return launch_gemm<128, 6>(d, st);

@@ -280,7 +280,7 @@ bool gemm_2cta_enabled() {
   return on;
 }
 
-// Caller (gemm_bf16_tcgen05) has validated the descriptor; requires N % 256 == 0.
+// Caller (gemm_bf16_tcgen05) has validated the descriptor (N % 32 == 0); the last N block may be ragged.
 int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmC;
   {
@@ -310,7 +310,7 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   p.N = d.N;
   p.K = d.K;
   p.num_m_pairs = (d.M + 2 * BM - 1) / (2 * BM);
-  p.num_n_blocks = d.N / BN;
+  p.num_n_blocks = (d.N + BN - 1) / BN;
   p.num_k_blocks = (d.K + BK - 1) / BK;
   p.grp_rows = d.grp_rows;
   p.grp_stride = d.grp_stride;

@@ -138,6 +138,9 @@ def test_layernorm_matches_torch(lib, rows, width):
     (592 * 32, 3072, 768, 1, False, False, (32, 64)),  # grouped "query rows only" FFN
     (592 * 32, 768, 3072, 0, True, True, (32, 64)),
     (8192, 8192, 1024, 0, False, False, (0, 0)),
+    (32896, 1408, 6144, 0, True, True, (0, 0)),       # ViT-g fc2: ragged last N block (5.5 x 256)
+    (16448, 4224, 1408, 0, False, False, (0, 0)),     # ViT-g qkv (16.5 x 256)
+    (16448, 1312, 1408, 2, False, False, (0, 0)),     # N = 41 x 32: last block holds 32 columns
 ])
 def test_gemm_cta_pair_kernel_matches_torch(lib, M, N, K, act, res, f32, grp):
     """Shapes large enough for the cta_group::2 kernel (256 x 256 tiles per CTA pair, gemm2.cu)."""
@@ -156,6 +159,8 @@ def test_gemm_cta_pair_kernel_matches_torch(lib, M, N, K, act, res, f32, grp):
     ref = A[pr].float() @ W.float().T + bias
     if act == 1:
         ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = ref * torch.sigmoid(1.702 * ref)
     if res:
         ref = ref + out0[pr]
     L.check(so.sprc_op_gemm(L.ptr(A), L.ptr(W), M, N, K, K, K, gr, gs, L.ptr(bias), L.ptr(out) if res else None,
