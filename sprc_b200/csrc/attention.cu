@@ -223,6 +223,7 @@ int attention(const AttnDesc& a, cudaStream_t st) {
   SPRC_REQUIRE(a.B <= 65535, "attention: B=%d exceeds grid limit", a.B);
   static const bool legacy = getenv("SPRC_ATTN_MMA_SYNC") != nullptr;  // A/B switch for tests
   if (!legacy && attention_qf_eligible(a)) return attention_qf(a, st);  // Q-Former self / cross: tcgen05
+  SPRC_REQUIRE(a.kv_head_stride == 0, "attention: head-major K/V is only read by the tcgen05 cross-attention kernel");
   if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // remaining small shapes (rerank two-segment keys)
   if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT: tcgen05
   if (act_fp16()) return a.dh <= 64 ? launch_attention<64, true>(a, st) : launch_attention<96, true>(a, st);

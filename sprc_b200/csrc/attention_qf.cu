@@ -373,10 +373,11 @@ qf_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         for (int rep = 0; rep < 4; ++rep)
           tma_load_2d(&tmQ, &full[s], st + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
         const int kr = b * p.kv_batch_rows;
-        tma_load_2d(&tmK, &full[s], st + QC_QBYTES, h * 64, kr, kEvictFirst);
-        tma_load_2d(&tmK, &full[s], st + QC_QBYTES + QC_HALF * 128, h * 64, kr + QC_HALF, kEvictFirst);
-        tma_load_2d(&tmV, &full[s], st + QC_QBYTES + QC_KBYTES, h * 64, kr, kEvictFirst);
-        tma_load_2d(&tmV, &full[s], st + QC_QBYTES + QC_KBYTES + QC_HALF * 128, h * 64, kr + QC_HALF, kEvictFirst);
+        // K/V maps are (d, row, head): heads are column slices of wide rows or contiguous [rows, 64] blocks
+        tma_load_3d(&tmK, &full[s], st + QC_QBYTES, 0, kr, h, kEvictFirst);
+        tma_load_3d(&tmK, &full[s], st + QC_QBYTES + QC_HALF * 128, 0, kr + QC_HALF, h, kEvictFirst);
+        tma_load_3d(&tmV, &full[s], st + QC_QBYTES + QC_KBYTES, 0, kr, h, kEvictFirst);
+        tma_load_3d(&tmV, &full[s], st + QC_QBYTES + QC_KBYTES + QC_HALF * 128, 0, kr + QC_HALF, h, kEvictFirst);
       }
     }
   } else if (warp == 1) {
@@ -533,8 +534,9 @@ static int launch_qf_cross(const AttnDesc& a, cudaStream_t st) {
   const uint64_t qrows = (uint64_t)(a.B - 1) * a.q_batch_rows + a.Lq;
   const uint64_t krows = (uint64_t)(a.B - 1) * a.kv_batch_rows + a.Lk;
   SPRC_TRY(make_tmap_bf16(&tmQ, a.Q, w, qrows, 1, a.ldq, 0, 64, 32, 1, 2));
-  SPRC_TRY(make_tmap_bf16(&tmK, a.K, w, krows, 1, a.ldk, 0, 64, QC_HALF, 1, 2));
-  SPRC_TRY(make_tmap_bf16(&tmV, a.V, w, krows, 1, a.ldv, 0, 64, QC_HALF, 1, 2));
+  const uint64_t hstride = a.kv_head_stride > 0 ? (uint64_t)a.kv_head_stride : 64;
+  SPRC_TRY(make_tmap_bf16(&tmK, a.K, 64, krows, a.H, a.ldk, hstride, 64, QC_HALF, 1, 3));
+  SPRC_TRY(make_tmap_bf16(&tmV, a.V, 64, krows, a.H, a.ldv, hstride, 64, QC_HALF, 1, 3));
   SPRC_TRY(make_tmap_bf16(&tmO, a.O, w, qrows, 1, a.ldo, 0, 64, 32, 1, 2));
   QfCrossParams p;
   p.B = a.B;

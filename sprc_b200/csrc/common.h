@@ -82,6 +82,10 @@ struct GemmDesc {
   bf16* out_bf16 = nullptr;
   int ldc = 0;
   int act = ACT_NONE;
+  // out_col_block = 64: the 16-bit output is written column-blocked, element (m, n) at
+  // out + (n / 64) * (M * 64) + m * 64 + (n % 64)  (ldc ignored): every 64-column block - one attention head of a
+  // packed K/V projection - becomes a contiguous [M, 64] matrix.  Dense rows only.
+  int out_col_block = 0;
 };
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)

@@ -42,6 +42,7 @@ struct GemmKernelParams {
   int out_is_f32;  // output element type of tmC
   int accumulate;  // 1: out_f32 += result (TMA reduce-add; the residual already lives in the output buffer)
   int rev;         // 1: sweep the tiles from the last M block down (see next_sweep_reverse)
+  int col_block;   // 1: column-blocked 16-bit output (GemmDesc::out_col_block = 64)
 };
 
 template <int BN, int STAGES>
@@ -226,7 +227,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
               float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
               if (p.act == ACT_GELU) {
-                v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
+                const float2 g0 = gelu_erf2(make_float2(v0, v1)), g1 = gelu_erf2(make_float2(v2, v3));
+                v0 = g0.x, v1 = g0.y, v2 = g1.x, v3 = g1.y;
               } else if (p.act == ACT_QUICKGELU) {
                 v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
               }
@@ -252,6 +254,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (lane == 0) {
             if (p.accumulate)
               tma_reduce_add_3d(&tmC, stile, n, c1, c2);
+            else if (p.col_block)
+              tma_store_3d(&tmC, stile, n & 63, c1, n >> 6);
             else
               tma_store_3d(&tmC, stile, n, c1, c2);
             bulk_commit();
@@ -354,6 +358,8 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
       const uint32_t br = d.grp_rows < 32 ? d.grp_rows : 32;
       SPRC_TRY(make_tmap(&tmC, out, esz, d.N, d.grp_rows, d.M / d.grp_rows, d.ldc, (uint64_t)d.grp_stride * d.ldc,
                          ch, br, 32 / br, 3, 64));
+    } else if (d.out_col_block) {
+      SPRC_TRY(make_tmap(&tmC, out, esz, 64, d.M, d.N / 64, 64, (uint64_t)d.M * 64, ch, 32, 1, 3, 64));
     } else {
       SPRC_TRY(make_tmap(&tmC, out, esz, d.N, d.M, 1, d.ldc, (uint64_t)d.M * d.ldc, ch, 32, 1, 3, 64));
     }
@@ -389,6 +395,7 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
   p.out_is_f32 = d.out_f32 ? 1 : 0;
   p.accumulate = d.residual ? 1 : 0;
   p.rev = next_sweep_reverse();
+  p.col_block = d.out_col_block ? 1 : 0;
   if (d.residual && d.residual != d.out_f32) {
     const long long total = (long long)d.M * (d.N / 4);
     long long blocks = (total + 255) / 256;
@@ -434,6 +441,8 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   SPRC_REQUIRE(!d.residual || d.act == ACT_NONE, "gemm: activation with a residual is not supported");
   SPRC_REQUIRE(d.grp_rows == 0 || (BM % d.grp_rows == 0 && d.M % d.grp_rows == 0 && d.grp_stride >= d.grp_rows),
                "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
+  SPRC_REQUIRE(d.out_col_block == 0 || (d.out_col_block == 64 && d.out_bf16 && d.grp_rows == 0 && d.N % 64 == 0),
+               "gemm: out_col_block needs 64, a 16-bit output, dense rows and N %% 64 == 0");
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
   // CTA pairs (256 x 256 tiles) whenever every pair gets work; the single-CTA kernels cover ragged N and small problems
   // (a ragged last N block - ViT-g's 1408 = 5.5 x 256, 4224 = 16.5 x 256 - runs as a half-empty 256-column tile: its
@@ -464,7 +473,8 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
   if (p.bias) acc += p.bias[n];
   if (p.act == ACT_GELU) acc = gelu_erf(acc);
   if (p.act == ACT_QUICKGELU) acc = quick_gelu(acc);
-  const size_t off = (size_t)prow * p.ldc + n;
+  size_t off = (size_t)prow * p.ldc + n;
+  if (p.col_block) off = (size_t)(n >> 6) * ((size_t)p.M * 64) + (size_t)m * 64 + (n & 63);
   if (p.residual) acc += p.residual[off];
   if (p.out_f32)
     p.out_f32[off] = acc;
@@ -486,6 +496,7 @@ int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st) {
   p.ldc = d.ldc;
   p.act = d.act;
   p.fp16 = act_fp16();
+  p.col_block = d.out_col_block ? 1 : 0;
   dim3 grid((d.N + 127) / 128, d.M);
   gemm_simt_kernel<<<grid, 128, 0, st>>>(d.A, d.W, p, d.lda, d.ldw);
   SPRC_CUDA(cudaGetLastError());

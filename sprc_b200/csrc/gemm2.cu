@@ -52,6 +52,7 @@ struct Gemm2Params {
   int out_is_f32;
   int accumulate;
   int rev;
+  int col_block;   // 1: column-blocked 16-bit output (GemmDesc::out_col_block = 64)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -222,7 +223,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
               float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
               if (p.act == ACT_GELU) {
-                v0 = gelu_erf(v0), v1 = gelu_erf(v1), v2 = gelu_erf(v2), v3 = gelu_erf(v3);
+                const float2 g0 = gelu_erf2(make_float2(v0, v1)), g1 = gelu_erf2(make_float2(v2, v3));
+                v0 = g0.x, v1 = g0.y, v2 = g1.x, v3 = g1.y;
               } else if (p.act == ACT_QUICKGELU) {
                 v0 = quick_gelu(v0), v1 = quick_gelu(v1), v2 = quick_gelu(v2), v3 = quick_gelu(v3);
               }
@@ -247,6 +249,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           if (lane == 0) {
             if (p.accumulate)
               tma_reduce_add_3d(&tmC, stile, n, c1, c2);
+            else if (p.col_block)
+              tma_store_3d(&tmC, stile, n & 63, c1, n >> 6);
             else
               tma_store_3d(&tmC, stile, n, c1, c2);
             bulk_commit();
@@ -292,6 +296,8 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
       const uint32_t br = d.grp_rows < 32 ? d.grp_rows : 32;
       SPRC_TRY(make_tmap_any(&tmC, out, esz, d.N, d.grp_rows, d.M / d.grp_rows, d.ldc, (uint64_t)d.grp_stride * d.ldc,
                              ch, br, 32 / br, 3, 64));
+    } else if (d.out_col_block) {
+      SPRC_TRY(make_tmap_any(&tmC, out, esz, 64, d.M, d.N / 64, 64, (uint64_t)d.M * 64, ch, 32, 1, 3, 64));
     } else {
       SPRC_TRY(make_tmap_any(&tmC, out, esz, d.N, d.M, 1, d.ldc, (uint64_t)d.M * d.ldc, ch, 32, 1, 3, 64));
     }
@@ -322,6 +328,7 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   p.out_is_f32 = d.out_f32 ? 1 : 0;
   p.accumulate = d.residual ? 1 : 0;
   p.rev = next_sweep_reverse();
+  p.col_block = d.out_col_block ? 1 : 0;
 
   static bool attr_set = false;
   if (!attr_set) {

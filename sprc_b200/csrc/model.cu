@@ -474,14 +474,29 @@ int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_b
   return 0;
 }
 
-int Model::cross_kv(const bf16* raws_bf16, int n_img, cudaStream_t st) {
+// K/V projections of all cross-attention layers in one GEMM.  head_major: every (layer, K|V, head) block is written as
+// a contiguous [n_img * 257, 64] matrix (GemmDesc::out_col_block), which the tcgen05 cross-attention kernel reads as
+// whole 33 KB blocks per (sample, head) instead of 128-byte pieces of 18 KB-pitch rows; the rerank path (two-segment
+// keys through sample index tables, attention_small) keeps plain rows.
+int Model::cross_kv(const bf16* raws_bf16, int n_img, bool head_major, cudaStream_t st) {
   SPRC_REQUIRE(n_img > 0 && n_img <= enc_cap, "cross_kv: %d images outside (0, %d]", n_img, enc_cap);
-  return linear(raws_bf16, n_img * 257, Dv, Dv, kv_w, n_cross * 1536, kv_b, ACT_NONE, nullptr, nullptr, kv,
-                n_cross * 1536, 0, 0, st);
+  GemmDesc d;
+  d.A = raws_bf16;
+  d.W = kv_w;
+  d.M = n_img * 257;
+  d.N = n_cross * 1536;
+  d.K = Dv;
+  d.lda = Dv;
+  d.ldw = Dv;
+  d.bias = kv_b;
+  d.out_bf16 = kv;
+  d.ldc = n_cross * 1536;
+  d.out_col_block = head_major ? 64 : 0;
+  return gemm_bf16_tcgen05(d, st);
 }
 
 int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
-                          const float* key_mask, int live_out, cudaStream_t st) {
+                          const float* key_mask, int live_out, long long kv_rows, cudaStream_t st) {
   const int rows = B * S;
   SPRC_REQUIRE(rows <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows, qf_rows);
   SPRC_REQUIRE(live_out == QF_OUT_ALL || S == 64, "qformer: row-restricted output needs S = 64");
@@ -529,8 +544,14 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         SPRC_TRY(linear(qhb, B * 32, 768, 768, L.cq_w, 768, L.cq_b, ACT_NONE, nullptr, nullptr, qcq, 768, g, gs, st));
         AttnDesc c;
         c.Q = qcq;
-        c.K = kv + (size_t)ci * 1536;
-        c.V = kv + (size_t)ci * 1536 + 768;
+        if (kv_rows > 0) {  // head-major blocks (cross_kv): block index = ci * 24 + {K: 0, V: 12} + head
+          c.K = kv + (size_t)ci * 24 * kv_rows * 64;
+          c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
+          c.kv_head_stride = kv_rows * 64;
+        } else {
+          c.K = kv + (size_t)ci * 1536;
+          c.V = kv + (size_t)ci * 1536 + 768;
+        }
         c.O = qctx;
         c.B = B;
         c.H = 12;
@@ -538,7 +559,7 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         c.Lq = 32;
         c.Lk = Lk;
         c.ldq = 768;
-        c.ldk = c.ldv = ldkv;
+        c.ldk = c.ldv = kv_rows > 0 ? 64 : ldkv;
         c.ldo = 768;
         c.q_batch_rows = S;
         c.kv_batch_rows = 257;
@@ -580,11 +601,11 @@ int Model::encode_gallery(const float* images, int B, float* feats_f32, bf16* fe
   bf16* rb = raws_bf16 ? raws_bf16 : raws;
   SPRC_TRY(vit_forward(images, B, raws_f32, rb, st));
   if (!feats_f32 && !feats_bf16) return 0;
-  SPRC_TRY(cross_kv(rb, B, st));
+  SPRC_TRY(cross_kv(rb, B, true, st));
   // embeddings = LayerNorm(query_tokens)  (Qformer.py:110-112), broadcast over the batch
   SPRC_TRY(qformer_embed_rows(query_tokens, 0, nullptr, 1, word_emb, pos_emb, vocab, B, qt, st));
   SPRC_TRY(layernorm(qt, B * 32, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(B, 32, true, 257, nullptr, nullptr, nullptr, QF_OUT_ALL, st));
+  SPRC_TRY(qformer_layers(B, 32, true, 257, nullptr, nullptr, nullptr, QF_OUT_ALL, (long long)B * 257, st));
   SPRC_TRY(linear(qhb, B * 32, 768, 768, vproj_w, 256, vproj_b, ACT_NONE, nullptr, qproj, nullptr, 256, 0, 0, st));
   SPRC_TRY(l2norm_rows256(qproj, 256, B * 32, feats_f32, feats_bf16, st));
   return 0;
@@ -605,16 +626,16 @@ int Model::encode_query(const void* ref_raws, int ref_dtype, const int32_t* ref_
   } else {
     rb = static_cast<const bf16*>(ref_raws);
   }
-  SPRC_TRY(cross_kv(rb, Bq, st));
+  SPRC_TRY(cross_kv(rb, Bq, true, st));
   SPRC_TRY(qformer_key_mask(mask, 1, Bq, qmask, st));
   // pass 1: fusion = Qformer(text, query_tokens, enc = reference embeds)   (align_prompt.py:332-339)
   SPRC_TRY(qformer_embed_rows(query_tokens, 0, ids, 1, word_emb, pos_emb, vocab, Bq, qt, st));
   SPRC_TRY(layernorm(qt, Bq * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(Bq, 64, true, 257, nullptr, nullptr, qmask, QF_OUT_QUERY_ROWS, st));
+  SPRC_TRY(qformer_layers(Bq, 64, true, 257, nullptr, nullptr, qmask, QF_OUT_QUERY_ROWS, (long long)Bq * 257, st));
   // pass 2: text = Qformer(text, query_embeds = fusion[:, :32])  with no encoder states (:341-346)
   SPRC_TRY(qformer_embed_rows(qh, 64, ids, 1, word_emb, pos_emb, vocab, Bq, qt, st));
   SPRC_TRY(layernorm(qt, Bq * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers(Bq, 64, false, 0, nullptr, nullptr, qmask, QF_OUT_TEXT_CLS, st));
+  SPRC_TRY(qformer_layers(Bq, 64, false, 0, nullptr, nullptr, qmask, QF_OUT_TEXT_CLS, 0, st));
   // fusion_feats = normalize(text_proj(h[:, 32]))   (:348-350): row 32 of every 64-row sample
   SPRC_TRY(linear(qhb + (size_t)32 * 768, Bq, 768, 768, tproj_w, 256, tproj_b, ACT_NONE, nullptr, qproj, nullptr, 256,
                   1, 64, st));
@@ -640,7 +661,7 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_TRY(gather_rows_bf16(raws_table, SPRC_BF16, ref_rows + r0, r, row_elems, raws, st));
     SPRC_TRY(gather_rows_bf16(raws_table, SPRC_BF16, cand_rows + (size_t)r0 * T, pairs, row_elems,
                               raws + (size_t)r * row_elems, st));
-    SPRC_TRY(cross_kv(raws, n_img, st));
+    SPRC_TRY(cross_kv(raws, n_img, false, st));
     idx0.resize(pairs);
     idx1.resize(pairs);
     for (int i = 0; i < pairs; ++i) {
@@ -653,7 +674,7 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_TRY(qformer_key_mask(mask + (size_t)r0 * 32, T, pairs, qmask, st));
     SPRC_TRY(qformer_embed_rows(query_tokens, 0, ids + (size_t)r0 * 32, T, word_emb, pos_emb, vocab, pairs, qt, st));
     SPRC_TRY(layernorm(qt, pairs * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-    SPRC_TRY(qformer_layers(pairs, 64, true, 514, d_rows, d_rows2, qmask, QF_OUT_QUERY_ROWS, st));
+    SPRC_TRY(qformer_layers(pairs, 64, true, 514, d_rows, d_rows2, qmask, QF_OUT_QUERY_ROWS, 0, st));
     SPRC_TRY(itm_head_prob(qh, 64, pairs, itm_w, itm_b, p + (size_t)r0 * T, st));
   }
   return 0;

@@ -112,12 +112,12 @@ struct Model {
   // ViT + ln_vision: images fp32 [B,3,224,224] -> raws (fp32 and/or bf16 [B*257, Dv])
   int vit_forward(const float* images, int B, float* raws_f32, bf16* raws_bf16, cudaStream_t st);
   // packed cross-attention K/V of all cross layers for n_img images' raw embeds
-  int cross_kv(const bf16* raws_bf16, int n_img, cudaStream_t st);
+  int cross_kv(const bf16* raws_bf16, int n_img, bool head_major, cudaStream_t st);
   // 12 BertLayers over B samples of S rows (S = 32: query rows only; S = 64: 32 query + 32 text rows).
   // with_enc: cross-attention + dual FFN (Qformer.py:435-468); else text FFN on every row (:469-475).
   // live_out: which rows of the LAST layer's output the caller reads (dead rows are not computed there).
   int qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
-                     const float* key_mask, int live_out, cudaStream_t st);
+                     const float* key_mask, int live_out, long long kv_rows, cudaStream_t st);
   int encode_gallery(const float* images, int B, float* feats_f32, bf16* feats_bf16, float* raws_f32,
                      bf16* raws_bf16, cudaStream_t st);
   int encode_query(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,

@@ -83,6 +83,9 @@ struct AttnDesc {
   const int32_t* kv_idx0 = nullptr;
   const int32_t* kv_idx1 = nullptr;
   int Lk1 = 0;
+  // > 0: K and V are head-major (GemmDesc::out_col_block layout): head h starts kv_head_stride elements after head
+  // h - 1 and its rows are ldk = ldv = 64 elements apart.  0: heads are 64-column slices of ldk/ldv-pitch rows.
+  long long kv_head_stride = 0;
 };
 int attention(const AttnDesc& a, cudaStream_t st);
 
