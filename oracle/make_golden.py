@@ -98,7 +98,36 @@ def run_rerank(cfg, sd, raws, ids, mask):
     return dict(R=R, T=T, ref_rows=torch.tensor([0, 1]), cand_rows=torch.tensor([2, 3, 1, 2]), p=p.clone())
 
 
+def run_cat(name="tiny_L_cat", base="tiny_L"):
+    """The scripts' default model `blip2_cir_cat` (blip2_qformer_cir_cat.py:282-336, 401-428) on the checkpoint and
+    inputs of `base`: same fusion / text passes, similarity divided by the learned temperature."""
+    cfg = CASES[base]
+    sd = synth.make_state_dict(cfg["vit"], cfg["vit_depth"], cfg["qf_layers"], seed=0)
+    sd = {k: v for k, v in sd.items() if k != "prompt_tokens"}   # Blip2QformerCirCat has no prompt tokens
+    model = ref_loader.build_reference_model(cfg["vit"], seed=0, vit_depth=cfg["vit_depth"],
+                                             qf_layers=cfg["qf_layers"], kind="cat")
+    ref_keys = {k for k in model.state_dict() if not k.startswith("Qformer.cls.") and "position_ids" not in k}
+    assert ref_keys == set(sd), (sorted(ref_keys - set(sd))[:5], sorted(set(sd) - ref_keys)[:5])
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys
+    images = synth.make_images(cfg["n_images"])
+    ids, mask = synth.make_token_ids(cfg["n_queries"])
+    ref_rows = torch.arange(cfg["n_queries"]) % cfg["n_images"]
+    with torch.no_grad(), ref_loader.no_cuda_moves():
+        feats, raws = model.extract_target_features(images)
+        sim = ref_loader.call_inference(model, raws[ref_rows], feats, ids, mask)
+    out = dict(case=dict(cfg, name=name, seed=0, kind="cat"), feats=feats.clone(),
+               sim=sim.reshape(cfg["n_queries"], -1).clone(), temp=float(sd["temp"]), ref_rows=ref_rows, input_ids=ids,
+               attention_mask=mask)
+    torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"[golden] {name}: sim {tuple(out['sim'].shape)} temp {out['temp']}", flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + ["tiny_L_cat"])
     for n in names:
-        run_case(n, CASES[n])
+        if n == "tiny_L_cat":
+            run_cat()
+        else:
+            run_case(n, CASES[n])

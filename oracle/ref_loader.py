@@ -188,6 +188,11 @@ def load_reference_class(kind="align_prompt"):
     if kind == "rerank":
         m = importlib.import_module("lavis.models.blip2_models.blip2_qformer_cir_rerank")
         return m.Blip2QformerCirRerank
+    if kind == "cat":
+        if "skimage" not in sys.modules:   # imported at blip2_qformer_cir_cat.py:23, never used
+            _mod("skimage", transform=_mod("skimage.transform"))
+        m = importlib.import_module("lavis.models.blip2_models.blip2_qformer_cir_cat")
+        return m.Blip2QformerCirCat
     raise ValueError(kind)
 
 
@@ -208,6 +213,20 @@ def build_reference_model(vit="clip_L", seed=0, vit_depth=None, qf_layers=None, 
 def call_inference(model, reference_embeds, target_feats, input_ids, attention_mask):
     """model.inference(...) with pre-tokenised text (blip2_qformer_cir_align_prompt.py:312-361)."""
     return model.inference(reference_embeds, target_feats, TokenBatch(input_ids, attention_mask))
+
+
+class no_cuda_moves:
+    """`Blip2QformerCirCat.inference` moves its inputs with `.cuda()` (blip2_qformer_cir_cat.py:283-284); the oracle
+    runs the reference on the CPU, so inside this context `Tensor.cuda()` returns the tensor unchanged."""
+
+    def __enter__(self):
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._orig
+        return False
 
 
 def load_caption_processor():

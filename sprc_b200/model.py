@@ -339,7 +339,44 @@ class Blip2QformerCirRerank(Blip2QformerCirAlignPrompt):
         super().__init__(*a, max_pairs=max_pairs, **kw)
 
 
-MODEL_REGISTRY = {"blip2_cir_align_prompt": Blip2QformerCirAlignPrompt, "blip2_cir_rerank": Blip2QformerCirRerank}
+class Blip2QformerCirCat(Blip2QformerCirAlignPrompt):
+    """`blip2_cir_cat`, the DEFAULT --blip-model-name of cirr_test_submission.py:206 (checkpoint key
+    `Blip2QformerCirCat`) — blip2_qformer_cir_cat.py:282-336, 401-428.
+    Same ViT, Q-Former passes, ITC heads and kernels as align_prompt; differences kept here on the host:
+      * `inference` returns sim / temp (:331) — the ranking is unchanged, the full matrix is scaled;
+      * `extract_target_features` returns CPU tensors and takes target_only / ref_only (:401-428);
+      * the model has no `prompt_tokens` parameter."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._temp = 0.07  # nn.Parameter(0.07 * torch.ones([])), blip2_qformer_cir_cat.py:84
+
+    def load_state_dict(self, state_dict, strict=False):
+        if "temp" in state_dict:
+            self._temp = float(state_dict["temp"])
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @torch.no_grad()
+    def inference(self, reference_embeds, target_feats, text, return_attns=False):
+        if return_attns:
+            raise NotImplementedError("return_attns (cross-attention maps for visualisation) is outside the hot path")
+        return super().inference(reference_embeds, target_feats, text) / self._temp
+
+    @torch.no_grad()
+    def extract_target_features(self, image, mode="mean", target_only=False, ref_only=False):
+        feats, raws = super().extract_target_features(image, mode)
+        if target_only:
+            return feats.cpu()
+        if ref_only:
+            return raws
+        return feats.cpu(), raws.cpu()
+
+    def inference_rerank(self, refereence_embeds, target_embeds, text):
+        raise NotImplementedError("blip2_cir_cat.inference_rerank (:338-398) is not wired; use blip2_cir_rerank")
+
+
+MODEL_REGISTRY = {"blip2_cir_align_prompt": Blip2QformerCirAlignPrompt, "blip2_cir_rerank": Blip2QformerCirRerank,
+                  "blip2_cir_cat": Blip2QformerCirCat}
 
 
 def load_model_and_preprocess(name, model_type, is_eval=False, device="cpu", **kw):

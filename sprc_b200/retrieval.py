@@ -18,6 +18,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 
@@ -298,3 +299,154 @@ def compute_fiq_val_metrics(relative_val_dataset, blip_model, index_features, in
     if not bool((top >= 0).all()) and index.n_total >= 50:
         raise AssertionError("top-k returned unfilled slots")
     return fiq_recalls_from_topk(top, tgt_rows)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CIRR test-split submission on integer rows  (cirr_test_submission.py:60-132)
+# ---------------------------------------------------------------------------------------------------
+def cirr_submission_from_topk(top_rows: torch.Tensor, ref_rows: torch.Tensor, group_rows: torch.Tensor,
+                              group_scores: torch.Tensor, index_names: Sequence[str], pairs_id: Sequence,
+                              k_global: int = 50, k_group: int = 3):
+    """top_rows [Q, >= k_global + 1]: ranking by similarity (ties: lower row), reference possibly included;
+    group_rows / group_scores [Q, m]: the query's group members and their similarities.
+    Returns (pairid_to_predictions, pairid_to_group_predictions) exactly as generate_cirr_test_dicts builds them:
+    the reference row is deleted from the ranking (:115-119), the subset ranking is the global order restricted
+    to the group members (:121-123), then top-50 / top-3 names (:126-129)."""
+    top_rows = top_rows.cpu().to(torch.int64)
+    ref_rows = ref_rows.cpu().to(torch.int64)
+    names = np.asarray(list(index_names), dtype=object)
+    Q = top_rows.shape[0]
+    glob, grp = {}, {}
+    g_rows = group_rows.cpu().to(torch.int64)
+    g_sc = group_scores.cpu().float()
+    for j in range(Q):
+        row = top_rows[j]
+        ranked = row[(row != ref_rows[j]) & (row >= 0)][:k_global]
+        glob[str(int(pairs_id[j]))] = names[ranked.numpy()].tolist()
+        members = [(-float(g_sc[j, i]), int(g_rows[j, i])) for i in range(g_rows.shape[1])
+                   if int(g_rows[j, i]) >= 0 and int(g_rows[j, i]) != int(ref_rows[j])]
+        members.sort()  # score descending, ties by lower row: the order argsort(1 - sim) gives the full ranking
+        seen, sub = set(), []
+        for _, r in members:
+            if r not in seen:
+                seen.add(r)
+                sub.append(r)
+        grp[str(int(pairs_id[j]))] = names[np.asarray(sub[:k_group], dtype=np.int64)].tolist()
+    return glob, grp
+
+
+@torch.no_grad()
+def generate_cirr_test_dicts(relative_test_dataset, blip_model, index_features, index_names, txt_processors,
+                             rerank=False, top: int = 50):
+    """Same signature and result as cirr_test_submission.py:60-132, computed from the fused scan's integer rows:
+    one pass of top-(50+1) per query batch + 6 gathered subset scores instead of a [Q, N] similarity matrix, a full
+    argsort and object-array string compares.  rerank=True re-orders each query's first `top` candidates by
+    `inference_rerank` probabilities (:87-112; the reference hard-codes top = 50)."""
+    index = index_features.index if isinstance(index_features, IndexFeatures) else as_index(index_features,
+                                                                                            index_names)
+    pairs_id, ref_names, caps, groups = [], [], [], []
+    for i in range(len(relative_test_dataset)):
+        item = relative_test_dataset[i]
+        if item is None:
+            continue
+        pid, r, c, g = item
+        pairs_id.append(pid)
+        ref_names.append(r)
+        caps.append(txt_processors["eval"](c))
+        groups.append(list(g))
+    ref_rows = index.rows_of(ref_names)
+    group_rows = torch.tensor([[index.name_to_row.get(n, -1) for n in g] for g in groups], dtype=torch.int64)
+    ids, mask = _tokenize(blip_model, caps)
+    k = min(max(top, 50) + 1, index.n_total)
+    tops, subs = [], []
+    B = max(1, blip_model.max_queries)
+    for s in range(0, len(caps), B):
+        sl = slice(s, s + B)
+        _, ix, sub = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=k, subset_rows=group_rows[sl])
+        tops.append(ix.cpu().to(torch.int64))
+        subs.append(sub.cpu())
+    top_rows, sub_scores = torch.cat(tops), torch.cat(subs)
+    if rerank:
+        if _dist()[2] > 1:
+            raise NotImplementedError("rerank over a sharded index: candidates' raw embeds live on their owner ranks")
+        T = min(top, top_rows.shape[1])
+        step = max(1, getattr(blip_model, "max_pairs", 0) // T)
+        if step < 1 or getattr(blip_model, "max_pairs", 0) < T:
+            raise ValueError("rerank needs a model built with max_pairs >= top (Blip2QformerCirRerank)")
+        dev = blip_model.device
+        for s in range(0, len(caps), step):
+            sl = slice(s, s + step)
+            cand = top_rows[sl, :T]
+            p = blip_model.rerank_rows(index.raws, (ref_rows[sl] - index.lo).to(dev), (cand - index.lo).reshape(-1).to(dev),
+                                       ids[sl], mask[sl], T).reshape(-1, T).cpu()
+            order = torch.argsort(1 - p, dim=-1, stable=True)
+            top_rows[sl, :T] = torch.gather(cand, 1, order)
+    return cirr_submission_from_topk(top_rows, ref_rows, group_rows, sub_scores, index.names, pairs_id)
+
+
+# ---------------------------------------------------------------------------------------------------
+# on-disk gallery index  (SURVEY §8f N3: the reference recomputes the index on every run,
+# blip_validate.py:80,119)
+# ---------------------------------------------------------------------------------------------------
+INDEX_MAGIC = b"SPRCIDX1"
+
+
+def save_index(index: GalleryIndex, path: str) -> None:
+    """One file: magic, u64 header length, JSON header, then the feature block [N,32,256] and (optionally) the raw
+    embedding block [N,257,Dv], both in the 16-bit format they are resident in.  Blocks start on 4096-byte
+    boundaries so a rank can map exactly its row range.  Only a whole (unsharded) index is written."""
+    import json
+
+    if index.lo != 0 or index.hi != index.n_total:
+        raise ValueError("save_index needs the whole index (gather the shards first)")
+    feats = index.feats.contiguous()
+    raws = index.raws.contiguous() if index.raws is not None else None
+    dt = {torch.bfloat16: "bf16", torch.float16: "fp16"}[feats.dtype]
+    hdr = {"version": 1, "n": index.n_total, "dtype": dt, "tokens": 32, "dim": 256,
+           "raw_tokens": 257 if raws is not None else 0, "raw_dim": int(raws.shape[-1]) if raws is not None else 0,
+           "names": list(index.names)}
+    blob = json.dumps(hdr).encode()
+    off_feats = (len(INDEX_MAGIC) + 8 + len(blob) + 4095) // 4096 * 4096
+    feats_bytes = feats.numel() * 2
+    off_raws = (off_feats + feats_bytes + 4095) // 4096 * 4096
+    with open(path, "wb") as f:
+        f.write(INDEX_MAGIC)
+        f.write(len(blob).to_bytes(8, "little"))
+        f.write(blob)
+        f.seek(off_feats)
+        f.write(feats.cpu().view(torch.int16).numpy().tobytes())
+        if raws is not None:
+            f.seek(off_raws)
+            for s0 in range(0, raws.shape[0], 1024):   # bounded host staging
+                f.write(raws[s0:s0 + 1024].cpu().view(torch.int16).numpy().tobytes())
+
+
+def load_index(path: str, device, rank: int = 0, world: int = 1, with_raws: bool = True) -> GalleryIndex:
+    """Maps rows [lo, hi) of rank `rank` straight from the file to `device` (no full-index host copy)."""
+    import json
+
+    with open(path, "rb") as f:
+        if f.read(len(INDEX_MAGIC)) != INDEX_MAGIC:
+            raise ValueError(f"{path}: not a sprc-b200 gallery index")
+        n_hdr = int.from_bytes(f.read(8), "little")
+        hdr = json.loads(f.read(n_hdr).decode())
+    if hdr.get("version") != 1:
+        raise ValueError(f"{path}: unsupported index version {hdr.get('version')}")
+    n = int(hdr["n"])
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[hdr["dtype"]]
+    lo, hi = shard_range(n, rank, world)
+    off_feats = (len(INDEX_MAGIC) + 8 + n_hdr + 4095) // 4096 * 4096
+    row_f = hdr["tokens"] * hdr["dim"]
+    off_raws = (off_feats + n * row_f * 2 + 4095) // 4096 * 4096
+
+    def block(offset, row_elems, shape_tail):
+        if hi == lo:
+            return torch.empty((0,) + shape_tail, dtype=dt, device=device)
+        m = np.memmap(path, dtype=np.int16, mode="r", offset=offset + lo * row_elems * 2, shape=((hi - lo) * row_elems,))
+        return torch.from_numpy(np.ascontiguousarray(m)).view(dt).reshape((hi - lo,) + shape_tail).to(device)
+
+    feats = block(off_feats, row_f, (hdr["tokens"], hdr["dim"]))
+    raws = None
+    if with_raws and hdr["raw_tokens"]:
+        raws = block(off_raws, hdr["raw_tokens"] * hdr["raw_dim"], (hdr["raw_tokens"], hdr["raw_dim"]))
+    return GalleryIndex(feats=feats, raws=raws, names=list(hdr["names"]), lo=lo, hi=hi, n_total=n)

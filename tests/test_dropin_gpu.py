@@ -73,7 +73,8 @@ def staged_tree(tmp_path_factory):
     # ---- checkpoint (truncated ViT-L, synthetic weights) ----
     sd = synth.make_state_dict("clip_L", 2, 2, seed=0)
     ckpt = os.path.join(root, "ckpt.pt")
-    torch.save({"epoch": 0, "Blip2QformerCirAlignPrompt": sd}, ckpt)
+    torch.save({"epoch": 0, "Blip2QformerCirAlignPrompt": sd,
+                "Blip2QformerCirCat": {k: v for k, v in sd.items() if k != "prompt_tokens"}}, ckpt)
     # ---- plant targets from OUR ranking over the images as the reference's data pipeline decodes them ----
     sys.path.insert(0, os.path.join(root, "src"))
     try:
@@ -182,6 +183,19 @@ def test_blip_validate_cirr_unchanged_script(staged_tree, fast):
         assert res[f"group_recall_at{k}"] == pytest.approx(_pct(e["granks"], k), abs=0.05), (k, res)
 
 
+def test_blip_validate_default_model_name_cir_cat(staged_tree):
+    """`blip2_cir_cat` (the default --blip-model-name of cirr_test_submission.py:206) resolves to our
+    Blip2QformerCirCat; dividing by temp does not change the ranking, so the recalls are the same."""
+    out = _run(staged_tree, "blip_validate.py", ["--dataset", "CIRR", "--blip-model-name", "blip2_cir_cat",
+                                                 "--backbone", "pretrain_vitL", "--model-path", staged_tree["ckpt"]],
+               False)
+    assert "Missing keys []" in out
+    res = _last_json(out)
+    e = staged_tree["expected"]
+    for k in (1, 5, 10, 50):
+        assert res[f"recall_at{k}"] == pytest.approx(_pct(e["ranks"], k), abs=0.05), (k, res)
+
+
 @pytest.mark.parametrize("fast", [False, True], ids=["modeA_reference_loops", "modeB_fused_scan"])
 def test_blip_validate_fashioniq_unchanged_script(staged_tree, fast):
     out = _run(staged_tree, "blip_validate.py", ["--dataset", "fashionIQ", "--blip-model-name",
@@ -210,3 +224,43 @@ def test_cirr_test_submission_unchanged_script(staged_tree):
         want = 3 if d["metric"] == "recall_subset" else 50
         for v in rows.values():
             assert set(v) <= set(staged_tree["names"]) and len(set(v)) == len(v) == want
+
+
+def test_cirr_submission_on_integer_rows_equals_reference_script(staged_tree):
+    """`retrieval.generate_cirr_test_dicts` (top-51 rows + 6 subset scores, no [Q,N] matrix, no string
+    compares) must write the same two dicts as the reference's unchanged cirr_test_submission.py (Mode A above)."""
+    sub_dir = os.path.join(staged_tree["root"], "submission", "CIRR")
+    if not os.path.isdir(sub_dir) or len(os.listdir(sub_dir)) != 2:
+        _run(staged_tree, "cirr_test_submission.py",
+             ["--blip-model-name", "blip2_cir_align_prompt", "--backbone", "pretrain_vitL", "--model-path",
+              staged_tree["ckpt"]], False)
+    want = {}
+    for f in os.listdir(sub_dir):
+        with open(os.path.join(sub_dir, f)) as fh:
+            d = json.load(fh)
+        want[d["metric"]] = {k: v for k, v in d.items() if k not in ("version", "metric")}
+    import importlib
+
+    from sprc_b200 import retrieval as R
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+    from sprc_b200.tokenizer import BlipCaptionProcessor
+
+    src = os.path.join(staged_tree["root"], "src")
+    sys.path.insert(0, src)
+    try:
+        du = importlib.import_module("data_utils")
+        importlib.reload(du)
+        pre = du.targetpad_transform(1.25, 224)
+        classic = du.CIRRDataset("test1", "classic", pre)
+        relative = du.CIRRDataset("test1", "relative", pre)
+        model = Blip2QformerCirAlignPrompt(vit_model="clip_L", device="cuda:0", max_images=64, max_queries=32,
+                                           vit_depth=2, qf_layers=2)
+        model.load_state_dict(torch.load(staged_tree["ckpt"])["Blip2QformerCirAlignPrompt"])
+        feats, names = R.extract_index_blip_features(classic, model)
+        txt = {"eval": BlipCaptionProcessor()}
+        got_g, got_s = R.generate_cirr_test_dicts(relative, model, feats, names, txt, rerank=False)
+    finally:
+        sys.path.remove(src)
+        sys.modules.pop("data_utils", None)
+    assert got_g == want["recall"]
+    assert got_s == want["recall_subset"]

@@ -127,3 +127,76 @@ def test_recalls_from_topk_match_oracle_full_sort():
     assert RT.fiq_recalls_from_topk(order[:, :50], tgt) == pytest.approx(R.fiq_recalls(order, tgt), abs=1e-9)
     with pytest.raises(AssertionError):
         RT.cirr_recalls_from_topk(order[:, :51], ref, ref, members, torch.gather(sim, 1, members))
+
+
+def test_index_file_roundtrip_and_sharded_load(tmp_path):
+    """the on-disk index returns exactly the resident tensors, whole or per rank shard."""
+    import torch
+
+    from sprc_b200 import retrieval as R
+
+    g = torch.Generator().manual_seed(3)
+    n = 37
+    feats = torch.randn(n, 32, 256, generator=g).bfloat16()
+    raws = torch.randn(n, 257, 64, generator=g).bfloat16()
+    names = [f"img{i:04d}" for i in range(n)]
+    idx = R.GalleryIndex(feats=feats, raws=raws, names=names)
+    path = str(tmp_path / "gallery.sprcidx")
+    R.save_index(idx, path)
+    whole = R.load_index(path, "cpu")
+    assert whole.names == names and whole.n_total == n and (whole.lo, whole.hi) == (0, n)
+    assert torch.equal(whole.feats.view(torch.int16), feats.view(torch.int16))
+    assert torch.equal(whole.raws.view(torch.int16), raws.view(torch.int16))
+    got_f, got_r = [], []
+    for r in range(4):
+        sh = R.load_index(path, "cpu", rank=r, world=4)
+        assert (sh.lo, sh.hi) == R.shard_range(n, r, 4) and sh.name_to_row["img0005"] == 5
+        got_f.append(sh.feats)
+        got_r.append(sh.raws)
+    assert torch.equal(torch.cat(got_f).view(torch.int16), feats.view(torch.int16))
+    assert torch.equal(torch.cat(got_r).view(torch.int16), raws.view(torch.int16))
+    no_raws = R.load_index(path, "cpu", with_raws=False)
+    assert no_raws.raws is None
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    import pytest
+
+    with pytest.raises(ValueError):
+        R.load_index(path, "cpu")
+    with pytest.raises(ValueError):
+        R.save_index(R.GalleryIndex(feats=feats[:5], raws=None, names=names, lo=3, hi=8, n_total=n), path)
+
+
+def test_cirr_submission_from_topk_matches_reference_semantics():
+    """cirr_test_submission.py:115-129 restated on names (argsort over the full similarity, string masks) must give
+    the dicts `cirr_submission_from_topk` builds from top-51 rows + 6 subset scores."""
+    import numpy as np
+    import torch
+
+    from sprc_b200 import retrieval as R
+
+    g = torch.Generator().manual_seed(11)
+    N, Q = 80, 9
+    names = [f"n{i:03d}" for i in range(N)]
+    sim = torch.randn(Q, N, generator=g)
+    ref = torch.randint(0, N, (Q,), generator=g)
+    # real CIRR groups: the reference + 5 other distinct images
+    groups = torch.stack([torch.cat([ref[j:j + 1], torch.tensor([x for x in torch.randperm(N, generator=g).tolist()
+                                                                 if x != int(ref[j])][:5])]) for j in range(Q)])
+    pairs = list(range(100, 100 + Q))
+    # --- reference semantics on strings ---
+    order = torch.argsort(1 - sim, dim=-1)
+    sorted_names = np.array(names)[order]
+    ref_names = np.array(names)[ref]
+    mask = sorted_names != np.repeat(ref_names, N).reshape(Q, -1)
+    sorted_names = sorted_names[mask].reshape(Q, N - 1)
+    gm = np.array(names)[groups]
+    gmask = (sorted_names[..., None] == gm[:, None, :]).sum(-1).astype(bool)
+    sorted_group = sorted_names[gmask].reshape(Q, -1)
+    want_g = {str(p): r[:50].tolist() for p, r in zip(pairs, sorted_names)}
+    want_s = {str(p): r[:3].tolist() for p, r in zip(pairs, sorted_group)}
+    # --- ours ---
+    top = order[:, :51]
+    sub = torch.gather(sim, 1, groups)
+    got_g, got_s = R.cirr_submission_from_topk(top, ref, groups, sub, names, pairs)
+    assert got_g == want_g and got_s == want_s

@@ -126,3 +126,17 @@ def test_restatement_matches_live_reference_and_key_layout():
     assert (f - f_ref).abs().max().item() < 2e-6
     assert (r - r_ref).abs().max().item() < 5e-5
     assert (s - s_ref).abs().max().item() < 2e-6
+
+
+def test_cir_cat_golden_is_align_prompt_similarity_over_temp():
+    """blip2_cir_cat differs from align_prompt in `inference` only by `/ self.temp` (blip2_qformer_cir_cat.py:331):
+    the two reference runs on the same checkpoint must agree to fp32 noise."""
+    import os
+
+    import torch
+
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    a = torch.load(os.path.join(gd, "tiny_L.pt"))
+    c = torch.load(os.path.join(gd, "tiny_L_cat.pt"))
+    assert torch.allclose(c["feats"], a["feats"], atol=2e-6)
+    assert torch.allclose(c["sim"] * c["temp"], a["sim"], atol=2e-6)
