@@ -135,6 +135,15 @@ int sprc_profile_read(double* out, int ncat);
 /* CSV of per-(category, shape tag) aggregates of the recorded launches: cat,tag,launches,total_ms,flops,bytes */
 int sprc_profile_dump(const char* path);
 
+/* Gallery-side image preprocessing on the GPU (replaces data_utils.py:52-72,91-105 `targetpad_transform` = TargetPad,
+ * Resize(dim, BICUBIC), CenterCrop(dim), ToTensor, Normalize on PIL images; bit-exact with Pillow's 8-bit resampler).
+ * pixels: packed decoded RGB uint8 images (device); desc: [n][16] int64 per-image descriptors and tables: int32
+ * fixed-point coefficient tables (device), both produced by sprc_b200/preprocess.py; tmp: uint8 workspace of
+ * sum(rows_i) * dim * 3 bytes; mean3/std3: host pointers; out: [n,3,dim,dim] fp32 (device). */
+int sprc_preprocess_targetpad(const uint8_t* pixels, const int64_t* desc, const int32_t* tables, int n, int dim,
+                              int max_rows, uint8_t* tmp, const float* mean3, const float* std3, float* out,
+                              void* stream);
+
 /* ---- single-op entry points (tests and micro-benchmarks) ------------------------------------- */
 /* C = act(A[M,K] W[N,K]^T + bias) (+ residual); impl 0 = tcgen05 product kernel, 1 = CUDA-core checker. */
 int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,

@@ -72,6 +72,13 @@ int sprc_op_gemm_ln(const void* A, const void* W, int M, int N, int K, int lda, 
   return gemm_ln_tcgen05(d, gamma, beta, eps, static_cast<bf16*>(out_ln16), static_cast<cudaStream_t>(stream));
 }
 
+int sprc_preprocess_targetpad(const uint8_t* pixels, const int64_t* desc, const int32_t* tables, int n, int dim,
+                              int max_rows, uint8_t* tmp, const float* mean3, const float* std3, float* out,
+                              void* stream) {
+  return preprocess_targetpad(pixels, reinterpret_cast<const long long*>(desc), tables, n, dim, max_rows, tmp, mean3,
+                              std3, out, static_cast<cudaStream_t>(stream));
+}
+
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream) {
   return layernorm(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32, static_cast<bf16*>(out_bf16),

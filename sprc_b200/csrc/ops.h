@@ -64,6 +64,12 @@ int l2norm_rows256(const float* in, size_t in_row_stride, int rows, float* out_f
 int itm_head_prob(const float* h, int rows_per_pair, int pairs, const float* w, const float* b, float* p,
                   cudaStream_t st);
 
+// ---- preprocess.cu ---------------------------------------------------------------------------
+// TargetPad + bicubic Resize + CenterCrop + ToTensor + Normalize (data_utils.py:52-72, 91-105) on decoded RGB uint8
+// images, bit-exact with PIL/torchvision; descriptors and coefficient tables come from sprc_b200/preprocess.py.
+int preprocess_targetpad(const uint8_t* pixels, const long long* desc, const int* tables, int n, int dim, int max_rows,
+                         uint8_t* tmp, const float* mean, const float* stdv, float* out, cudaStream_t st);
+
 // ---- attention.cu ----------------------------------------------------------------------------
 // softmax(Q K^T * scale + key_mask) V for B samples x H heads, bf16 in/out, fp32 softmax:
 // ViT MHSA (eva_vit.py:128-145, clip_vit.py:134), Q-Former self- and cross-attention

@@ -69,17 +69,37 @@ def _dist():
 # indexing  (utils.py:46-77)
 # ---------------------------------------------------------------------------------------------------
 @torch.no_grad()
+def raw_rgb(image):
+    """`preprocess` callable for the reference's dataset classes (data_utils.py CIRRDataset / FashionIQDataset take
+    any callable): hands the decoded image to `build_index(..., gpu_preprocess=...)` as an RGB uint8 array instead
+    of running the PIL transform chain in the DataLoader worker."""
+    if image.mode != "RGB":
+        raise NotImplementedError(f"image mode {image.mode!r}: the GPU preprocessor takes RGB images")
+    return np.asarray(image)
+
+
+def _collate_raw(batch):
+    batch = [b for b in batch if b is not None]      # utils.py:141-148 drops unreadable images
+    return [b[0] for b in batch], [b[1] for b in batch]
+
+
 def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, collate_fn=None,
-                keep_raws: bool = True, progress: bool = False) -> GalleryIndex:
-    """Encode this rank's row shard of `dataset` ('classic' mode: items are (name, image))."""
+                keep_raws: bool = True, progress: bool = False, gpu_preprocess=None) -> GalleryIndex:
+    """Encode this rank's row shard of `dataset` ('classic' mode: items are (name, image)).
+    gpu_preprocess: a `sprc_b200.preprocess.TargetPadPreprocessor`; the dataset must then be built with
+    `preprocess=retrieval.raw_rgb` so that items are (name, uint8 [H,W,3]) and resize/crop/normalise run on the GPU
+     — workers only decode."""
     from torch.utils.data import DataLoader, Subset
+
+    if gpu_preprocess is not None:
+        collate_fn = _collate_raw
 
     dist, rank, world = _dist()
     n = len(dataset)
     lo, hi = shard_range(n, rank, world)
     sub = Subset(dataset, range(lo, hi)) if world > 1 else dataset
-    loader = DataLoader(dataset=sub, batch_size=batch_size, num_workers=num_workers, pin_memory=True,
-                        collate_fn=collate_fn)
+    loader = DataLoader(dataset=sub, batch_size=batch_size, num_workers=num_workers,
+                        pin_memory=gpu_preprocess is None, collate_fn=collate_fn)
     feats, raws, names = [], [], []
     it = loader
     if progress:
@@ -87,6 +107,8 @@ def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, co
 
         it = tqdm(loader)
     for batch_names, images in it:
+        if gpu_preprocess is not None:
+            images = gpu_preprocess(images)
         o = backend.encode_gallery(images.to(backend.device, non_blocking=True), want_f32=False, want_bf16=True,
                                    want_raws_f32=False, want_raws_bf16=keep_raws)
         feats.append(o["feats_bf16"])

@@ -264,3 +264,30 @@ def test_cirr_submission_on_integer_rows_equals_reference_script(staged_tree):
         sys.modules.pop("data_utils", None)
     assert got_g == want["recall"]
     assert got_s == want["recall_subset"]
+
+
+def test_index_build_with_gpu_preprocess_equals_pil_path(staged_tree):
+    """the reference's CIRRDataset with `preprocess=retrieval.raw_rgb` + the GPU preprocessor builds the
+    same index (bit-identical features) as with the reference's own `targetpad_transform` in the DataLoader workers."""
+    import importlib
+
+    from sprc_b200 import retrieval as R
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+    from sprc_b200.preprocess import TargetPadPreprocessor
+
+    src = os.path.join(staged_tree["root"], "src")
+    sys.path.insert(0, src)
+    try:
+        du = importlib.import_module("data_utils")
+        importlib.reload(du)
+        model = Blip2QformerCirAlignPrompt(vit_model="clip_L", device="cuda:0", max_images=64, max_queries=32,
+                                           vit_depth=2, qf_layers=2)
+        model.load_state_dict(torch.load(staged_tree["ckpt"])["Blip2QformerCirAlignPrompt"])
+        a = R.build_index(du.CIRRDataset("val", "classic", du.targetpad_transform(1.25, 224)), model, num_workers=0)
+        b = R.build_index(du.CIRRDataset("val", "classic", R.raw_rgb), model, num_workers=0,
+                          gpu_preprocess=TargetPadPreprocessor(1.25, 224, device="cuda:0"))
+    finally:
+        sys.path.remove(src)
+        sys.modules.pop("data_utils", None)
+    assert a.names == b.names == staged_tree["names"]
+    assert torch.equal(a.feats, b.feats) and torch.equal(a.raws, b.raws)
