@@ -254,6 +254,9 @@ def main():
         ids_h[p_], mask_h[p_] = i, m
         rows_h[p_] = torch.randint(0, n_index, (Bq,), generator=torch.Generator().manual_seed(7 + 100 * rank + p_))
     ids_d, mask_d, rows_d = ids_h.to(dev), mask_h.to(dev), rows_h.to(dev)
+    # caption lengths stay on the host, where the tokenizer produced them (sprc_encode_query_lens)
+    lens_h = mask_h.sum(dim=2).to(torch.int32).contiguous()
+    ragged = os.environ.get("SPRC_RAGGED", "1") != "0"
     out_sc_h = torch.empty(Bq, k, dtype=torch.float32).pin_memory()
     out_ix_h = torch.empty(Bq, k, dtype=torch.int32).pin_memory()
 
@@ -268,8 +271,12 @@ def main():
 
     def step_device(i):
         p_ = i % pool
-        L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]), L.ptr(mask_d[p_]),
-                                      Bq, None, L.ptr(fusion), st()))
+        if ragged:
+            L.check(lib.sprc_encode_query_lens(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]),
+                                               L.ptr(lens_h[p_]), Bq, None, L.ptr(fusion), st()))
+        else:
+            L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]),
+                                          L.ptr(mask_d[p_]), Bq, None, L.ptr(fusion), st()))
         if world == 1:
             L.check(lib.sprc_sim_topk(h, L.ptr(fusion), Bq, L.ptr(feats), n_local, 0, k, L.ptr(sc), L.ptr(ix), None,
                                       st()))
@@ -419,7 +426,11 @@ def main():
                        "l2": "inputs_exceed_l2 (gallery %.0f MB + weights; query batches rotate)" % (
                            n_local * 32 * 256 * 2 / 1e6),
                        "parallelism": "gallery rows sharded x%d, queries data-parallel" % world,
-                       "weights": "synthetic seed 0, full depth (oracle/synth.py)"},
+                       "weights": "synthetic seed 0, full depth (oracle/synth.py)",
+                       "captions": "32-token rows, %.1f live tokens on average (SURVEY 8d: L~U{3..20} + [CLS],[SEP]); "
+                                   "%s" % (float(lens_h.float().mean()),
+                                           "query passes over live text rows only (ragged layout)" if ragged
+                                           else "all 64 padded rows per query computed")},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * Bq * (32 * 8 * 2 + 4),
                     "d2h_bytes_per_step": world * Bq * k * 8, "ms_per_step": ms_e2e / K,

@@ -90,6 +90,16 @@ int sprc_encode_query(sprc_handle* h, const void* ref_raws, int ref_dtype, const
                       const int64_t* input_ids, const int64_t* attention_mask, int Bq, float* fusion_f32,
                       void* fusion_bf16, void* stream);
 
+/* Same result as sprc_encode_query, computed over the live text rows only: the reference pads every caption to 32
+ * tokens and runs the padded rows through both Q-Former passes although nothing ever reads them (padded keys have
+ * softmax weight exp(-10000) = 0, align_prompt.py:343,348 keep the query rows / row 32).  text_len_host[b] (HOST
+ * memory, int32 [Bq]) = number of live tokens of caption b = sum of its attention-mask row, which must be a prefix
+ * mask (tokens, then padding: what BertTokenizer(padding="max_length") produces).  The tokenizer runs on the host, so
+ * the lengths are known there without a device round trip. */
+int sprc_encode_query_lens(sprc_handle* h, const void* ref_raws, int ref_dtype, const int32_t* ref_rows,
+                           const int64_t* input_ids, const int32_t* text_len_host, int Bq, float* fusion_f32,
+                           void* fusion_bf16, void* stream);
+
 /* The similarity half of `inference` (:353-358) fused with the ranking of validate_blip.py:44-46,253-255:
  * sim[q,n] = max_t <query[q], gallery[n,t]>, top-k by (sim desc, row asc).  gallery is bf16 [N,32,256],
  * queries bf16 [Q,256].  out_full (optional) receives the whole fp32 [Q,N] matrix (what `inference`
@@ -154,6 +164,10 @@ int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, in
 int sprc_op_gemm_ln(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
                     int grp_stride, const float* bias, const float* residual, const float* gamma, const float* beta,
                     float eps, float* out_f32, void* out_ln16, int ldc, void* stream);
+/* Q-Former self-attention over the ragged row layout (csrc/attention_qfr.cu): qkv [rows_total, 3*768] packed
+ * Q|K|V, rows [0,32B) query rows, then per-sample text slots; pairs_dev int32 [ceil(B/2)][4] = {toff, L0, L1, L8_0}. */
+int sprc_op_attention_ragged(const void* qkv, int ldqkv, void* out, int ldo, int B, int rows_total,
+                             const int32_t* pairs_dev, float scale, void* stream);
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream);
 int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int B, int H, int dh, int Lq,

@@ -58,6 +58,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     ),
+    "sprc_encode_query_lens": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    ),
     "sprc_sim_topk": (
         c_int,
         [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -95,6 +99,8 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
          c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
     ),
+    "sprc_op_attention_ragged": (
+        c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
     "sprc_op_layernorm": (
         c_int,
         [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -1,5 +1,6 @@
 // C-ABI: model-level entry points (handle, weights, gallery/query encoders, scan, rerank).
 // Each function documents, in include/sprc_b200.h, the reference function it stands in for.
+#include <vector>
 #include <new>
 
 #include "../../include/sprc_b200.h"
@@ -28,6 +29,10 @@ int ensure_global_ws(size_t bytes) {
 }
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 }  // namespace
+
+namespace sprc {
+bool ragged_query_enabled();   // model.cu (SPRC_RAGGED=0 disables the ragged query path)
+}
 
 extern "C" {
 
@@ -92,6 +97,17 @@ int sprc_encode_query(sprc_handle* h, const void* ref_raws, int ref_dtype, const
                            static_cast<bf16*>(fusion_bf16), S(stream));
 }
 
+int sprc_encode_query_lens(sprc_handle* h, const void* ref_raws, int ref_dtype, const int32_t* ref_rows,
+                           const int64_t* input_ids, const int32_t* text_len_host, int Bq, float* fusion_f32,
+                           void* fusion_bf16, void* stream) {
+  if (!h || !ref_raws || !input_ids || !text_len_host) return set_error(-22, "sprc_encode_query_lens: null argument");
+  if (h->m.count_missing() != 0)
+    return set_error(-61, "sprc_encode_query_lens: %d weights missing (first: %s)", (int)h->m.missing_cache.size(),
+                     h->m.missing_cache[0].c_str());
+  return h->m.encode_query_ragged(ref_raws, ref_dtype, ref_rows, input_ids, text_len_host, Bq, fusion_f32,
+                                  static_cast<bf16*>(fusion_bf16), S(stream));
+}
+
 int sprc_sim_topk(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N, int64_t row_offset,
                   int k, float* out_score, int32_t* out_idx, float* out_full, void* stream) {
   if (!queries || !gallery) return set_error(-22, "sprc_sim_topk: null argument");
@@ -149,9 +165,23 @@ int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gall
   SPRC_REQUIRE(k > 0 && k <= 256, "sprc_query_topk_host: k=%d outside [1, 256]", k);
   cudaStream_t st = S(stream);
   SPRC_CUDA(cudaMemcpyAsync(m.d_ids, ids_host, (size_t)Bq * 32 * 8, cudaMemcpyHostToDevice, st));
-  SPRC_CUDA(cudaMemcpyAsync(m.d_mask, mask_host, (size_t)Bq * 32 * 8, cudaMemcpyHostToDevice, st));
   SPRC_CUDA(cudaMemcpyAsync(m.d_rows, ref_rows_host, (size_t)Bq * 4, cudaMemcpyHostToDevice, st));
-  SPRC_TRY(sprc_encode_query(h, raws_bf16, SPRC_BF16, m.d_rows, m.d_ids, m.d_mask, Bq, nullptr, m.d_fusion, stream));
+  // caption lengths from the host mask: prefix masks (tokens then padding), as BertTokenizer(padding="max_length") makes
+  bool prefix = true;
+  std::vector<int32_t> lens((size_t)Bq);
+  for (int b = 0; b < Bq && prefix; ++b) {
+    int L = 0;
+    while (L < 32 && mask_host[(size_t)b * 32 + L] != 0) ++L;
+    for (int t = L; t < 32; ++t) prefix = prefix && mask_host[(size_t)b * 32 + t] == 0;
+    lens[b] = L;
+  }
+  if (prefix && ragged_query_enabled()) {
+    SPRC_TRY(sprc_encode_query_lens(h, raws_bf16, SPRC_BF16, m.d_rows, m.d_ids, lens.data(), Bq, nullptr, m.d_fusion,
+                                    stream));
+  } else {
+    SPRC_CUDA(cudaMemcpyAsync(m.d_mask, mask_host, (size_t)Bq * 32 * 8, cudaMemcpyHostToDevice, st));
+    SPRC_TRY(sprc_encode_query(h, raws_bf16, SPRC_BF16, m.d_rows, m.d_ids, m.d_mask, Bq, nullptr, m.d_fusion, stream));
+  }
   SPRC_TRY(sprc_sim_topk(h, m.d_fusion, Bq, gallery_bf16, N, 0, k, m.d_topk_score, m.d_topk_idx, nullptr, stream));
   SPRC_CUDA(cudaMemcpyAsync(out_score_host, m.d_topk_score, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
   SPRC_CUDA(cudaMemcpyAsync(out_idx_host, m.d_topk_idx, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));

@@ -79,6 +79,12 @@ int sprc_preprocess_targetpad(const uint8_t* pixels, const int64_t* desc, const 
                               std3, out, static_cast<cudaStream_t>(stream));
 }
 
+int sprc_op_attention_ragged(const void* qkv, int ldqkv, void* out, int ldo, int B, int rows_total,
+                             const int32_t* pairs_dev, float scale, void* stream) {
+  return attention_qf_ragged(static_cast<const bf16*>(qkv), ldqkv, static_cast<bf16*>(out), ldo, B, rows_total,
+                             reinterpret_cast<const int4*>(pairs_dev), scale, static_cast<cudaStream_t>(stream));
+}
+
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, float* out_f32, void* out_bf16, void* stream) {
   return layernorm(x, rows, width, gamma, beta, eps, grp_rows, grp_stride, out_f32, static_cast<bf16*>(out_bf16),

@@ -205,6 +205,70 @@ int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_
   return 0;
 }
 
+// Ragged layout (attention_qfr.cu): rows [0, 32 B) query rows, rows [32 B + toff[b], + L8[b]) text rows of sample b.
+// One block per query row, then one block per text slot row; slack rows (t >= L[b]) are zero.
+__global__ void __launch_bounds__(192)
+qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, const int64_t* __restrict__ ids,
+                            const int* __restrict__ slot_sample, const int* __restrict__ toff,
+                            const int* __restrict__ len, const float4* __restrict__ word,
+                            const float4* __restrict__ pos, int vocab, int B, float4* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int c = threadIdx.x;
+  float4 v;
+  if (r < 32 * B) {
+    v = q_is_batched ? qe[(size_t)r * 192 + c] : __ldg(qe + (size_t)(r & 31) * 192 + c);
+  } else {
+    const int slot = r - 32 * B;            // row inside the text region
+    const int b = slot_sample[slot >> 3];   // sample owning this 8-row group
+    const int t = slot - toff[b];
+    if (t < len[b]) {
+      long long id = ids[(size_t)b * 32 + t];
+      if (id < 0) id = 0;
+      if (id >= vocab) id = vocab - 1;
+      const float4 w = __ldg(word + (size_t)id * 192 + c);
+      const float4 p = __ldg(pos + (size_t)t * 192 + c);
+      v = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, w.w + p.w);
+    } else {
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  out[(size_t)r * 192 + c] = v;
+}
+
+int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, const int* slot_sample,
+                         const int* toff, const int* len, const float* word_emb, const float* pos_emb, int vocab, int B,
+                         int rows_total, float* out, cudaStream_t st) {
+  if (B <= 0) return 0;
+  qformer_embed_ragged_kernel<<<rows_total, 192, 0, st>>>(
+      reinterpret_cast<const float4*>(query_embeds), q_is_batched, ids, slot_sample, toff, len,
+      reinterpret_cast<const float4*>(word_emb), reinterpret_cast<const float4*>(pos_emb), vocab, B,
+      reinterpret_cast<float4*>(out));
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dst[i, :] = src[base + rows[i], :] for 768-wide rows: fp32 and (optionally) the 16-bit copy in one launch
+__global__ void __launch_bounds__(192)
+gather_rows768_kernel(const float4* __restrict__ src32, const uint2* __restrict__ src16, const int* __restrict__ rows,
+                      int base, float4* __restrict__ dst32, uint2* __restrict__ dst16) {
+  const size_t r = (size_t)(base + rows[blockIdx.x]);
+  const int c = threadIdx.x;
+  if (src32) dst32[(size_t)blockIdx.x * 192 + c] = src32[r * 192 + c];
+  if (src16) dst16[(size_t)blockIdx.x * 192 + c] = src16[r * 192 + c];
+}
+
+int gather_rows768(const float* src32, const bf16* src16, const int* rows, int base, int n, float* dst32, bf16* dst16,
+                   cudaStream_t st) {
+  if (n <= 0) return 0;
+  gather_rows768_kernel<<<n, 192, 0, st>>>(reinterpret_cast<const float4*>(src32),
+                                           reinterpret_cast<const uint2*>(src16), rows, base,
+                                           reinterpret_cast<float4*>(dst32), reinterpret_cast<uint2*>(dst16));
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void qformer_key_mask_kernel(const int64_t* __restrict__ am, int div, int B, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 64) return;

@@ -7,6 +7,7 @@
 //   heads        blip2_models/blip2_qformer_cir_align_prompt.py:348-350,385 ; rerank: blip2_qformer_cir_rerank.py:399-445
 // Data layout in HBM: activations are row-major [tokens, features]; the residual stream and every
 // LayerNorm input are fp32, GEMM operands are bf16 copies written by the producing kernel's epilogue.
+#include <vector>
 #include <stdlib.h>
 #include "model.h"
 
@@ -283,6 +284,7 @@ int Model::init(int kind, int vit_depth, int qf_layers_, int max_images_, int ma
   SPRC_TRY(alloc_t(&d_mask, nq * 32));
   SPRC_TRY(alloc_t(&d_rows, nq + 16));
   SPRC_TRY(alloc_t(&d_rows2, nq + 16));
+  SPRC_TRY(alloc_t(&d_meta, nq * 9 + 64));
   SPRC_TRY(alloc_t(&d_fusion, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_score, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_idx, nq * 256));
@@ -640,6 +642,163 @@ int Model::encode_query(const void* ref_raws, int ref_dtype, const int32_t* ref_
   SPRC_TRY(linear(qhb + (size_t)32 * 768, Bq, 768, 768, tproj_w, 256, tproj_b, ACT_NONE, nullptr, qproj, nullptr, 256,
                   1, 64, st));
   SPRC_TRY(l2norm_rows256(qproj, (size_t)64 * 256, Bq, fusion_f32, fusion_bf16, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// composed-query fusion over the ragged row layout
+// ------------------------------------------------------------------------------------------------
+bool ragged_query_enabled();
+static bool ragged_enabled() { return ragged_query_enabled(); }
+bool ragged_query_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPRC_RAGGED");   // SPRC_RAGGED=0: always run the padded 64-rows-per-sample passes
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// One Q-Former pass over rows [0, 32 B) (query rows) + [32 B, 32 B + T8) (live text rows, attention_qfr.cu).
+// with_enc: fusion pass (cross-attention + query FFN on the query rows, text FFN on the text rows; the last layer
+// computes the query rows only, align_prompt.py:343).  !with_enc: text pass (text FFN on every row, Qformer.py:434-435,
+// 469-475; the last layer computes the [CLS] rows only, gathered into dense [B, 768] buffers: qt = fp32, qcq = 16-bit,
+// align_prompt.py:348).
+int Model::qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st) {
+  const int qrows = 32 * B, rows_all = qrows + T8;
+  SPRC_REQUIRE(rows_all <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows_all, qf_rows);
+  const size_t to = (size_t)qrows;   // first text row
+  float* x_cls = qt;
+  bf16* ctx_cls = qcq;
+  bf16* x_cls_b = qcq + (size_t)B * 768;
+  for (int l = 0; l < qf_layers; ++l) {
+    const QfLayer& L = layers[l];
+    const bool last = l == qf_layers - 1;
+    SPRC_TRY(linear(qhb, rows_all, 768, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, nullptr, nullptr, qqkv, 2304, 0, 0, st));
+    SPRC_TRY(attention_qf_ragged(qqkv, 2304, qctx, 768, B, rows_all, static_cast<const int4*>(m_pairs), 0.125f, st));
+    if (!last) {
+      SPRC_TRY(linear_ln(qctx, rows_all, 768, 768, L.so_w, L.so_b, L.so_g, L.so_beta, 1e-12f, qh, qhb, 0, 0, st));
+    } else if (with_enc) {
+      SPRC_TRY(linear_ln(qctx, qrows, 768, 768, L.so_w, L.so_b, L.so_g, L.so_beta, 1e-12f, qh, qhb, 0, 0, st));
+    } else {
+      SPRC_TRY(gather_rows768(qh, qctx, m_cls, qrows, B, x_cls, ctx_cls, st));
+      SPRC_TRY(linear_ln(ctx_cls, B, 768, 768, L.so_w, L.so_b, L.so_g, L.so_beta, 1e-12f, x_cls, x_cls_b, 0, 0, st));
+    }
+    if (with_enc) {
+      if (L.has_cross) {
+        const int ci = l / 2;
+        const long long kv_rows = (long long)B * 257;
+        SPRC_TRY(linear(qhb, qrows, 768, 768, L.cq_w, 768, L.cq_b, ACT_NONE, nullptr, nullptr, qcq, 768, 0, 0, st));
+        AttnDesc c;
+        c.Q = qcq;
+        c.K = kv + (size_t)ci * 24 * kv_rows * 64;
+        c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
+        c.kv_head_stride = kv_rows * 64;
+        c.O = qctx;
+        c.B = B;
+        c.H = 12;
+        c.dh = 64;
+        c.Lq = 32;
+        c.Lk = 257;
+        c.ldq = 768;
+        c.ldk = c.ldv = 64;
+        c.ldo = 768;
+        c.q_batch_rows = 32;
+        c.kv_batch_rows = 257;
+        c.scale = 0.125f;
+        c.Lk1 = 257;
+        SPRC_TRY(attention(c, st));
+        SPRC_TRY(linear_ln(qctx, qrows, 768, 768, L.co_w, L.co_b, L.co_g, L.co_beta, 1e-12f, qh, qhb, 0, 0, st));
+      }
+      SPRC_TRY(linear(qhb, qrows, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
+      SPRC_TRY(linear_ln(qffn, qrows, 3072, 3072, L.qo_w, L.qo_b, L.qo_g, L.qo_beta, 1e-12f, qh, qhb, 0, 0, st));
+      if (!last) {
+        SPRC_TRY(linear(qhb + to * 768, T8, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
+                        qffn + to * 3072, 3072, 0, 0, st));
+        SPRC_TRY(linear_ln(qffn + to * 3072, T8, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f,
+                           qh + to * 768, qhb + to * 768, 0, 0, st));
+      }
+    } else if (!last) {
+      SPRC_TRY(linear(qhb, rows_all, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
+      SPRC_TRY(linear_ln(qffn, rows_all, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f, qh, qhb, 0, 0, st));
+    } else {
+      SPRC_TRY(linear(x_cls_b, B, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
+      SPRC_TRY(linear_ln(qffn, B, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f, x_cls, x_cls_b, 0, 0, st));
+    }
+  }
+  return 0;
+}
+
+int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
+                               const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16,
+                               cudaStream_t st) {
+  SPRC_REQUIRE(Bq > 0 && Bq <= max_queries, "encode_query: Bq=%d outside (0, %d]", Bq, max_queries);
+  SPRC_REQUIRE(ref_dtype == SPRC_F32 || ref_dtype == SPRC_BF16, "encode_query: ref dtype %d unsupported", ref_dtype);
+  // ---- row tables: toff[B] | len[B] | cls[B] | slot_sample[T8 / 8] | pairs int4 [ceil(B / 2)] ----
+  const int B = Bq, P = (B + 1) / 2;
+  h_meta.assign((size_t)B * 3, 0);
+  int T8 = 0;
+  std::vector<int32_t> slot;
+  slot.reserve((size_t)B * 4);
+  for (int b = 0; b < B; ++b) {
+    int L = text_len_host[b];
+    SPRC_REQUIRE(L >= 0 && L <= 32, "encode_query: caption %d has %d live tokens", b, L);
+    if (L < 1) L = 1;   // an all-masked caption still owns its [CLS] row (the padded path reads row 32 regardless)
+    const int L8 = (L + 7) & ~7;
+    h_meta[b] = T8;
+    h_meta[B + b] = L;
+    h_meta[2 * B + b] = T8;   // [CLS] = first text row of the sample
+    for (int i = 0; i < L8 / 8; ++i) slot.push_back(b);
+    T8 += L8;
+  }
+  const size_t off_slot = (size_t)B * 3;
+  size_t off_pairs = off_slot + slot.size();
+  off_pairs = (off_pairs + 3) & ~size_t(3);   // int4 alignment
+  h_meta.resize(off_pairs + (size_t)P * 4, 0);
+  for (size_t i = 0; i < slot.size(); ++i) h_meta[off_slot + i] = slot[i];
+  for (int g = 0; g < P; ++g) {
+    const int b0 = 2 * g, b1 = 2 * g + 1;
+    const int L0 = h_meta[B + b0], L1 = b1 < B ? h_meta[B + b1] : 0;
+    h_meta[off_pairs + 4 * g] = h_meta[b0];
+    h_meta[off_pairs + 4 * g + 1] = L0;
+    h_meta[off_pairs + 4 * g + 2] = L1;
+    h_meta[off_pairs + 4 * g + 3] = (L0 + 7) & ~7;
+  }
+  SPRC_REQUIRE(h_meta.size() <= (size_t)max_queries * 9 + 64, "encode_query: row tables exceed their buffer");
+  // pageable source: the copy is staged before the call returns, so h_meta may be rebuilt for the next batch
+  SPRC_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), h_meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  m_toff = d_meta;
+  m_len = d_meta + B;
+  m_cls = d_meta + 2 * B;
+  m_slot = d_meta + off_slot;
+  m_pairs = d_meta + off_pairs;
+
+  const size_t row_elems = (size_t)257 * Dv;
+  const bf16* rb;
+  if (ref_rows) {
+    SPRC_TRY(gather_rows_bf16(ref_raws, ref_dtype, ref_rows, Bq, row_elems, raws, st));
+    rb = raws;
+  } else if (ref_dtype == SPRC_F32) {
+    SPRC_TRY(convert_f32_to_bf16(static_cast<const float*>(ref_raws), raws, (size_t)Bq * row_elems, st));
+    rb = raws;
+  } else {
+    rb = static_cast<const bf16*>(ref_raws);
+  }
+  SPRC_TRY(cross_kv(rb, Bq, true, st));
+  const int rows_all = 32 * B + T8;
+  // pass 1: fusion = Qformer(text, query_tokens, enc = reference embeds)   (align_prompt.py:332-339)
+  SPRC_TRY(qformer_embed_ragged(query_tokens, 0, ids, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all, qt,
+                                st));
+  SPRC_TRY(layernorm(qt, rows_all, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
+  SPRC_TRY(qformer_layers_ragged(B, T8, true, st));
+  // pass 2: text = Qformer(text, query_embeds = fusion[:, :32]) with no encoder states (:341-346); the query rows of
+  // pass 1's output are rows [0, 32 B) of qh
+  SPRC_TRY(qformer_embed_ragged(qh, 1, ids, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all, qt, st));
+  SPRC_TRY(layernorm(qt, rows_all, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
+  SPRC_TRY(qformer_layers_ragged(B, T8, false, st));
+  // fusion_feats = normalize(text_proj(h[:, 32]))   (:348-350): the gathered [CLS] rows (dense [B, 768] in qcq + B*768)
+  SPRC_TRY(linear(qcq + (size_t)B * 768, Bq, 768, 768, tproj_w, 256, tproj_b, ACT_NONE, nullptr, qproj, nullptr, 256, 0,
+                  0, st));
+  SPRC_TRY(l2norm_rows256(qproj, (size_t)256, Bq, fusion_f32, fusion_bf16, st));
   return 0;
 }
 

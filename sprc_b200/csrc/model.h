@@ -87,6 +87,10 @@ struct Model {
   int64_t* d_mask = nullptr;
   int32_t* d_rows = nullptr;
   int32_t* d_rows2 = nullptr;
+  int32_t* d_meta = nullptr;     // ragged layout tables (see encode_query_ragged)
+  std::vector<int32_t> h_meta;
+  const int32_t *m_toff = nullptr, *m_len = nullptr, *m_slot = nullptr, *m_cls = nullptr;
+  const void* m_pairs = nullptr;
   bf16* d_fusion = nullptr;
   float* d_topk_score = nullptr;
   int32_t* d_topk_idx = nullptr;
@@ -122,6 +126,11 @@ struct Model {
                      bf16* raws_bf16, cudaStream_t st);
   int encode_query(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
                    const int64_t* mask, int Bq, float* fusion_f32, bf16* fusion_bf16, cudaStream_t st);
+  // Same result over the RAGGED row layout (attention_qfr.cu): only the live text rows of every caption are
+  // computed.  text_len_host[b] = number of live tokens of caption b (sum of its attention mask), host memory.
+  int encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
+                          const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16, cudaStream_t st);
+  int qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st);
   int rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t* cand_rows, const int64_t* ids,
              const int64_t* mask, int R, int T, float* p, cudaStream_t st);
 };

@@ -43,6 +43,15 @@ int vit_assemble_tokens(const float* patch_out, const float* cls, const float* p
 int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_t* ids, int ids_div,
                        const float* word_emb, const float* pos_emb, int vocab, int B, float* out, cudaStream_t st);
 
+// Ragged Q-Former layout (attention_qfr.cu): pre-LayerNorm embedding rows and row gathers
+int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, const int* slot_sample,
+                         const int* toff, const int* len, const float* word_emb, const float* pos_emb, int vocab, int B,
+                         int rows_total, float* out, cudaStream_t st);
+int gather_rows768(const float* src32, const bf16* src16, const int* rows, int base, int n, float* dst32, bf16* dst16,
+                   cudaStream_t st);
+int attention_qf_ragged(const bf16* qkv, int ldqkv, bf16* out, int ldo, int B, int rows_total, const int4* pairs_dev,
+                        float scale, cudaStream_t st);
+
 // additive self-attention mask (Qformer.py:807): out[b, j] = 0 for j < 32, (1 - mask[b, j-32]) * -10000 after
 // (sample b reads attention_mask row b / div)
 int qformer_key_mask(const int64_t* attention_mask, int div, int B, float* out, cudaStream_t st);

@@ -10,6 +10,8 @@ without the library or without a CUDA device raises.
 """
 from __future__ import annotations
 
+import os
+
 from collections import namedtuple
 from typing import List, Optional, Sequence
 
@@ -78,6 +80,7 @@ class Blip2QformerCirAlignPrompt:
             L.check(self._lib.sprc_create(L.ctypes.byref(cfg), L.ctypes.byref(h)))
         self._h = h
         self._gallery_cache = None
+        self._ragged = os.environ.get("SPRC_RAGGED", "1") != "0"   # A/B switch, see encode_query
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -211,7 +214,14 @@ class Blip2QformerCirAlignPrompt:
             ref = ref.float()
         ref = ref.to(self._device).contiguous()
         ids = input_ids.to(self._device, torch.int64).contiguous()
-        am = attention_mask.to(self._device, torch.int64).contiguous()
+        # Caption lengths are known on the host (the tokenizer runs there): with a prefix mask on the CPU the query
+        # passes run over the live text rows only (sprc_encode_query_lens); otherwise over all 64 padded rows.
+        lens = None
+        if attention_mask.device.type == "cpu" and self._ragged:
+            m = attention_mask.to(torch.int64)
+            if bool((m[:, :-1] >= m[:, 1:]).all()) and bool(((m == 0) | (m == 1)).all()):
+                lens = m.sum(dim=1).to(torch.int32).contiguous()
+        am = attention_mask.to(self._device, torch.int64).contiguous() if lens is None else None
         Bq = ids.shape[0]
         rows = None if ref_rows is None else ref_rows.to(self._device, torch.int32).contiguous()
         out = torch.empty(Bq, 256, device=self._device, dtype=out_dtype)
@@ -221,9 +231,14 @@ class Blip2QformerCirAlignPrompt:
                 of = L.ptr(out[s:e]) if out_dtype == torch.float32 else L.c_void_p(0)
                 ob = L.ptr(out[s:e]) if out_dtype != torch.float32 else L.c_void_p(0)
                 rp = L.ptr(ref) if rows is not None else L.ptr(ref[s:e])
-                L.check(self._lib.sprc_encode_query(self._h, rp, L.F32 if ref.dtype == torch.float32 else L.BF16,
-                                                    L.ptr(rows[s:e]) if rows is not None else L.c_void_p(0),
-                                                    L.ptr(ids[s:e]), L.ptr(am[s:e]), e - s, of, ob, self._stream()))
+                rdt = L.F32 if ref.dtype == torch.float32 else L.BF16
+                rw = L.ptr(rows[s:e]) if rows is not None else L.c_void_p(0)
+                if lens is not None:
+                    L.check(self._lib.sprc_encode_query_lens(self._h, rp, rdt, rw, L.ptr(ids[s:e]), L.ptr(lens[s:e]),
+                                                             e - s, of, ob, self._stream()))
+                else:
+                    L.check(self._lib.sprc_encode_query(self._h, rp, rdt, rw, L.ptr(ids[s:e]), L.ptr(am[s:e]), e - s,
+                                                        of, ob, self._stream()))
         return out
 
     def sim_topk(self, queries_bf16: torch.Tensor, gallery_bf16: torch.Tensor, k: int = 0, row_offset: int = 0,
