@@ -165,7 +165,7 @@ int sprc_op_gemm_ln(const void* A_bf16, const void* W_bf16, int M, int N, int K,
                     int grp_stride, const float* bias, const float* residual, const float* gamma, const float* beta,
                     float eps, float* out_f32, void* out_ln16, int ldc, void* stream);
 /* Q-Former self-attention over the ragged row layout (csrc/attention_qfr.cu): qkv [rows_total, 3*768] packed
- * Q|K|V, rows [0,32B) query rows, then per-sample text slots; pairs_dev int32 [ceil(B/2)][4] = {toff, L0, L1, L8_0}. */
+ * Q|K|V, rows [0,32B) query rows, then per-sample text slots; pairs_dev int32 [ceil(B/2)][4] = {toff0, L0, toff1, L1}. */
 int sprc_op_attention_ragged(const void* qkv, int ldqkv, void* out, int ldo, int B, int rows_total,
                              const int32_t* pairs_dev, float scale, void* stream);
 int sprc_op_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,

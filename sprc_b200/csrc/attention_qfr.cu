@@ -9,12 +9,14 @@
 //     rows [32 B, 32 B + T8)         live text rows, sample b at toff[b] .. toff[b] + L[b]   (slots of L8[b] =
 //                                    round_up(L[b], 8) rows; the <= 7 slack rows hold finite don't-care values)
 // so every GEMM / LayerNorm of the Q-Former becomes a plain dense row range, and only this kernel has to know
-// which rows belong together.  One work item = (pair of samples, head): a 128-row tile made of the pair's 64 query
-// rows and the (up to) 64 rows starting at the pair's first text row.  As in attention_qf.cu ONE 128x128x64 MMA forms
-// all scores, each softmax thread owns one row and reads only the two column ranges of its own sample (32 query keys +
-// L text keys), P is written to TMEM as a sparse bf16 matrix and O = P V is a TMEM-A MMA with V MN-major.  Rows past
-// the pair's slots belong to other samples: they are computed (finite) but never stored - the text part of the tile
-// is stored in 8-row boxes.
+// which rows belong together.  One work item = (pair of samples, head): a 128-row tile of four 32-row quarters =
+// query rows of sample 0 | query rows of sample 1 | 32 rows from sample 0's first text row | 32 rows from sample 1's,
+// so that each of the four softmax warps (= TMEM lane quarters) serves ONE sample (tcgen05.ld/.st take one address per
+// warp).  As in attention_qf.cu ONE 128x128x64 MMA forms all scores, each softmax thread owns one row and reads only
+// the two 32-column blocks of its own sample (32 query keys + L live text keys), P is written to TMEM as a sparse
+// bf16 matrix (the other sample's blocks stay zero) and O = P V is a TMEM-A MMA with V MN-major.  Text rows past a
+// sample's slot belong to other samples: they are loaded and computed (finite) but never stored - text quarters are
+// stored in 8-row boxes.
 #include <math.h>
 #include <stdio.h>
 
@@ -31,7 +33,7 @@ namespace {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int THREADS = 6 * 32;
 constexpr int TILE = 128 * 128;        // 128 rows x 64 x 16-bit
-constexpr int HALF = 64 * 128;
+constexpr int QUARTER = 32 * 128;   // bytes of a 32-row quarter of a tile
 constexpr int STAGE = 3 * TILE;        // Q, K, V
 constexpr int COL_S = 0, COL_P = 128, COL_O = 192;   // TMEM columns (256 allocated)
 constexpr int SMEM = 2 * STAGE + 256 + 1024;
@@ -39,7 +41,7 @@ constexpr int SMEM = 2 * STAGE + 256 + 1024;
 struct RaggedParams {
   int n_pairs, H;
   int text_base;          // first text row = 32 * B
-  const int4* pairs;      // per pair: {toff (relative to text_base), L0, L1, L8_0}
+  const int4* pairs;      // per pair: {toff0, L0, toff1, L1} (text row offsets relative to text_base; L1 = 0: no sample 1)
   float scale_log2;
   int fp16;
   int rev;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO32,
                                 const __grid_constant__ CUtensorMap tmO8, const RaggedParams p) {
+  // tmQ / tmK / tmV / tmO32: 32-row boxes; tmO8: 8-row boxes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
@@ -96,18 +99,18 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
         const uint32_t ph = (it >> 1) & 1;
         const int itm = p.rev ? n_items - 1 - item : item;
         const int g = itm / p.H, h = itm % p.H;
-        const int trow = p.text_base + __ldg(&p.pairs[g]).x;
+        const int4 pr = __ldg(&p.pairs[g]);
+        const int r[4] = {g * 64, g * 64 + 32, p.text_base + pr.x, p.text_base + pr.z};
         uint8_t* st = smem + s * STAGE;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], STAGE);
-        // rows 0..63: the pair's query rows; rows 64..127: 64 rows from the pair's first text row (rows past the
-        // end of the activation are zero-filled)
-        tma_load_2d(&tmQ, &full[s], st, h * 64, g * 64, kEvictFirst);
-        tma_load_2d(&tmQ, &full[s], st + HALF, h * 64, trow, kEvictFirst);
-        tma_load_2d(&tmK, &full[s], st + TILE, h * 64, g * 64, kEvictFirst);
-        tma_load_2d(&tmK, &full[s], st + TILE + HALF, h * 64, trow, kEvictFirst);
-        tma_load_2d(&tmV, &full[s], st + 2 * TILE, h * 64, g * 64, kEvictFirst);
-        tma_load_2d(&tmV, &full[s], st + 2 * TILE + HALF, h * 64, trow, kEvictFirst);
+        // (rows past the end of the activation are zero-filled)
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          tma_load_2d(&tmQ, &full[s], st + qd * QUARTER, h * 64, r[qd], kEvictFirst);
+          tma_load_2d(&tmK, &full[s], st + TILE + qd * QUARTER, h * 64, r[qd], kEvictFirst);
+          tma_load_2d(&tmV, &full[s], st + 2 * TILE + qd * QUARTER, h * 64, r[qd], kEvictFirst);
+        }
       }
     }
   } else if (warp == 1) {
@@ -144,77 +147,60 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
     }
   } else {
     // ===================== softmax + epilogue (warps 2..5): one thread per tile row =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter = tile quarter: 0/1 query rows, 2/3 text rows
     const int row = q * 32 + lane;
+    const int smp = q & 1;                  // the sample (of the pair) this warp serves
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + COL_S;
+    const uint32_t p_addr = tmem_base + lane_addr + COL_P;
+    {
+      // P row = 64 packed columns (128 keys): this row only ever writes [16 smp, +16) (query keys) and
+      // [32 + 16 smp, +16) (text keys); the other sample's blocks stay zero for the whole kernel
+      uint32_t z[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = 0u;
+      tmem_st16(p_addr + (smp ^ 1) * 16, z);
+      tmem_st16(p_addr + 32 + (smp ^ 1) * 16, z);
+      tmem_st_wait();
+    }
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1;
       const int itm = p.rev ? n_items - 1 - item : item;
       const int g = itm / p.H, h = itm % p.H;
-      const int4 pr = __ldg(&p.pairs[g]);             // {toff, L0, L1, L8_0}
-      // sample (0 / 1 of the pair) this row belongs to, first text column of that sample, its live text length
-      const int smp = row < 64 ? (row >> 5) : ((row - 64) < pr.w ? 0 : 1);
-      const int t0 = smp ? pr.w : 0;
-      const int L = smp ? pr.z : pr.y;
+      const int4 pr = __ldg(&p.pairs[g]);             // {toff0, L0, toff1, L1}
+      const int L = smp ? pr.w : pr.y;                // live text keys of this row's sample
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      // The row's keys: the 32 query rows of its sample (score columns [32 smp, +32)) and the sample's live text rows
-      // (columns [64 + t0, 64 + t1)).  tcgen05.ld / .st are warp-collective with ONE address per warp, while rows of
-      // both samples can share a warp (text slots start on 8-row boundaries): every thread walks all four 32-column
-      // chunks at warp-uniform addresses and masks per thread.  Two passes (max, then exp/sum/P) keep registers low.
-      const int t1 = t0 + L;
-      const uint32_t s_addr = tmem_base + lane_addr + COL_S;
-      const uint32_t p_addr = tmem_base + lane_addr + COL_P;
-      // chunk c holds keys of this row?  (c = 0, 1: query rows of sample c; c = 2, 3: text columns [32 (c-2), +32))
-      // Chunks no row of the warp needs are skipped (warp-uniform): query-row warps touch 2-3 of the 4 chunks.
-      bool use[4];
-      use[0] = smp == 0;
-      use[1] = smp == 1;
-      use[2] = t0 < 32 && t1 > 0;
-      use[3] = t1 > 32;
-      unsigned need = 0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) need |= __any_sync(0xffffffffu, use[c]) ? (1u << c) : 0u;
+      uint32_t sq[32], stx[32];
+      tmem_ld32(s_addr + smp * 32, sq);               // scores against the sample's query rows
+      tmem_ld32(s_addr + 64 + smp * 32, stx);         // ... against its text quarter (first L columns live)
+      tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (!(need & (1u << c))) continue;
-        uint32_t a[32];
-        tmem_ld32(s_addr + c * 32, a);
-        tmem_ld_wait();
-        const int lo = t0 - (c - 2) * 32, hi = t1 - (c - 2) * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = use[c] && (c < 2 || (j >= lo && j < hi));
-          if (ok) mx = fmaxf(mx, __uint_as_float(a[j]));
-        }
+      for (int j = 0; j < 32; ++j) {
+        mx = fmaxf(mx, __uint_as_float(sq[j]));
+        if (j < L) mx = fmaxf(mx, __uint_as_float(stx[j]));
       }
       mx *= p.scale_log2;   // scale > 0
       float sum = 0.f;
+      uint32_t pq[16], pt[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (need & (1u << c)) {
-          uint32_t a[32];
-          tmem_ld32(s_addr + c * 32, a);
-          tmem_ld_wait();
-          const int lo = t0 - (c - 2) * 32, hi = t1 - (c - 2) * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const bool ok0 = use[c] && (c < 2 || (j >= lo && j < hi));
-            const bool ok1 = use[c] && (c < 2 || (j + 1 >= lo && j + 1 < hi));
-            const float e0 = ok0 ? ex2_approx(fmaf(__uint_as_float(a[j]), p.scale_log2, -mx)) : 0.f;
-            const float e1 = ok1 ? ex2_approx(fmaf(__uint_as_float(a[j + 1]), p.scale_log2, -mx)) : 0.f;
-            sum += e0 + e1;
-            pk[j / 2] = pack_act(e0, e1, p.fp16);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        }
-        tmem_st16(p_addr + c * 16, pk);   // P row: 64 packed columns = 128 keys, zero where masked
+      for (int j = 0; j < 32; j += 2) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(sq[j]), p.scale_log2, -mx));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(sq[j + 1]), p.scale_log2, -mx));
+        sum += e0 + e1;
+        pq[j / 2] = pack_act(e0, e1, p.fp16);
       }
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float f0 = j < L ? ex2_approx(fmaf(__uint_as_float(stx[j]), p.scale_log2, -mx)) : 0.f;
+        const float f1 = j + 1 < L ? ex2_approx(fmaf(__uint_as_float(stx[j + 1]), p.scale_log2, -mx)) : 0.f;
+        sum += f0 + f1;
+        pt[j / 2] = pack_act(f0, f1, p.fp16);
+      }
+      tmem_st16(p_addr + smp * 16, pq);
+      tmem_st16(p_addr + 32 + smp * 16, pt);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -248,11 +234,12 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
         const uint32_t base = smem_u32(smem + s * STAGE);
         // query rows of sample 0 and (if it exists) sample 1: 32-row boxes
         tma_store_2d(&tmO32, base, h * 64, g * 64);
-        if (pr.z > 0) tma_store_2d(&tmO32, base + 32 * 128, h * 64, g * 64 + 32);
-        // the pair's text slots, 8 rows at a time (nothing beyond them: those rows belong to other samples)
-        const int n8 = (pr.w + ((pr.z + 7) & ~7)) >> 3;
-        const int trow = p.text_base + pr.x;
-        for (int i = 0; i < n8; ++i) tma_store_2d(&tmO8, base + HALF + i * 8 * 128, h * 64, trow + 8 * i);
+        if (pr.w > 0) tma_store_2d(&tmO32, base + QUARTER, h * 64, g * 64 + 32);
+        // each sample's text slot, 8 rows at a time (nothing beyond it: those rows belong to other samples)
+        for (int i = 0; i < (pr.y + 7) >> 3; ++i)
+          tma_store_2d(&tmO8, base + 2 * QUARTER + i * 8 * 128, h * 64, p.text_base + pr.x + 8 * i);
+        for (int i = 0; i < (pr.w + 7) >> 3; ++i)
+          tma_store_2d(&tmO8, base + 3 * QUARTER + i * 8 * 128, h * 64, p.text_base + pr.z + 8 * i);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(&empty[s]);  // Q (staging), K, V of this stage may be refilled
@@ -272,16 +259,16 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
 }  // namespace
 
 // qkv: packed [rows, 3 * 768] activation (Q | K | V, head-major columns); out: [rows, 768]; rows = 32 B + T8.
-// pairs_dev: [ceil(B / 2)] int4 {toff, L0, L1 (0 if the pair has one sample), L8_0}.
+// pairs_dev: [ceil(B / 2)] int4 {toff0, L0, toff1, L1 (0 if the pair has one sample)}.
 int attention_qf_ragged(const bf16* qkv, int ldqkv, bf16* out, int ldo, int B, int rows_total, const int4* pairs_dev,
                         float scale, cudaStream_t st) {
   SPRC_REQUIRE(B > 0 && rows_total >= 32 * B, "ragged attention: B=%d rows=%d", B, rows_total);
   const int H = 12;
   CUtensorMap tmQ, tmK, tmV, tmO32, tmO8;
   const uint64_t w = (uint64_t)H * 64, rows = (uint64_t)rows_total;
-  SPRC_TRY(make_tmap_bf16(&tmQ, qkv, w, rows, 1, ldqkv, 0, 64, 64, 1, 2));
-  SPRC_TRY(make_tmap_bf16(&tmK, qkv + 768, w, rows, 1, ldqkv, 0, 64, 64, 1, 2));
-  SPRC_TRY(make_tmap_bf16(&tmV, qkv + 1536, w, rows, 1, ldqkv, 0, 64, 64, 1, 2));
+  SPRC_TRY(make_tmap_bf16(&tmQ, qkv, w, rows, 1, ldqkv, 0, 64, 32, 1, 2));
+  SPRC_TRY(make_tmap_bf16(&tmK, qkv + 768, w, rows, 1, ldqkv, 0, 64, 32, 1, 2));
+  SPRC_TRY(make_tmap_bf16(&tmV, qkv + 1536, w, rows, 1, ldqkv, 0, 64, 32, 1, 2));
   SPRC_TRY(make_tmap_bf16(&tmO32, out, w, rows, 1, ldo, 0, 64, 32, 1, 2));
   SPRC_TRY(make_tmap_bf16(&tmO8, out, w, rows, 1, ldo, 0, 64, 8, 1, 2));
   RaggedParams p;

@@ -760,8 +760,8 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
     const int L0 = h_meta[B + b0], L1 = b1 < B ? h_meta[B + b1] : 0;
     h_meta[off_pairs + 4 * g] = h_meta[b0];
     h_meta[off_pairs + 4 * g + 1] = L0;
-    h_meta[off_pairs + 4 * g + 2] = L1;
-    h_meta[off_pairs + 4 * g + 3] = (L0 + 7) & ~7;
+    h_meta[off_pairs + 4 * g + 2] = b1 < B ? h_meta[b1] : h_meta[b0];
+    h_meta[off_pairs + 4 * g + 3] = L1;
   }
   SPRC_REQUIRE(h_meta.size() <= (size_t)max_queries * 9 + 64, "encode_query: row tables exceed their buffer");
   // pageable source: the copy is staged before the call returns, so h_meta may be rebuilt for the next batch

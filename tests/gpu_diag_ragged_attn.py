@@ -23,7 +23,7 @@ def run(lens):
     pairs = []
     for g in range((B + 1) // 2):
         b0, b1 = 2 * g, 2 * g + 1
-        pairs += [toff[b0], lens[b0], lens[b1] if b1 < B else 0, L8[b0]]
+        pairs += [toff[b0], lens[b0], toff[b1] if b1 < B else toff[b0], lens[b1] if b1 < B else 0]
     pd = torch.tensor(pairs, dtype=torch.int32, device=dev)
     L.check(lib.sprc_op_attention_ragged(L.ptr(qkv), 2304, L.ptr(out), 768, B, rows, L.ptr(pd), 0.125, L.cur_stream()))
     torch.cuda.synchronize()
