@@ -6,8 +6,9 @@
 // :348 row 32), so they are dead work: 19 of 64 rows per sample for CIRR-length captions.  The ragged layout
 // drops them.  Hidden-state rows of a B-sample batch:
 //     rows [0, 32 B)                 the 32 query rows of sample 0, 1, ...
-//     rows [32 B, 32 B + T8)         live text rows, sample b at toff[b] .. toff[b] + L[b]   (slots of L8[b] =
-//                                    round_up(L[b], 8) rows; the <= 7 slack rows hold finite don't-care values)
+//     rows [32 B, 32 B + T8)         live text rows, sample b at toff[b] .. toff[b] + L[b]; the two samples of a
+//                                    pair are adjacent and each PAIR owns a slot of round_up(L0 + L1, 8) rows (the
+//                                    <= 7 slack rows at its end hold finite don't-care values)
 // so every GEMM / LayerNorm of the Q-Former becomes a plain dense row range, and only this kernel has to know
 // which rows belong together.  One work item = (pair of samples, head): a 128-row tile of four 32-row quarters =
 // query rows of sample 0 | query rows of sample 1 | 32 rows from sample 0's first text row | 32 rows from sample 1's,
@@ -15,8 +16,8 @@
 // warp).  As in attention_qf.cu ONE 128x128x64 MMA forms all scores, each softmax thread owns one row and reads only
 // the two 32-column blocks of its own sample (32 query keys + L live text keys), P is written to TMEM as a sparse
 // bf16 matrix (the other sample's blocks stay zero) and O = P V is a TMEM-A MMA with V MN-major.  Text rows past a
-// sample's slot belong to other samples: they are loaded and computed (finite) but never stored - text quarters are
-// stored in 8-row boxes.
+// sample's rows belong to other samples: they are loaded and computed (finite) but never stored - the epilogue
+// compacts the two text quarters into the pair's slot order in the staging tile and stores the slot in 8-row boxes.
 #include <math.h>
 #include <stdio.h>
 
@@ -220,14 +221,26 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       const float inv = 1.0f / sum;
-      const uint32_t stg = smem_u32(smem + s * STAGE) + row * 128;
+      // staging row: query quarters in place; text rows in slot order = sample 0's L0 live rows, then sample 1's rows
+      // (its L1 live rows followed by whatever fills the slot up to a multiple of 8)
+      const int slot8 = (pr.y + pr.w + 7) & ~7;
+      int srow = row;
+      bool wr = true;
+      if (q == 2) wr = lane < pr.y;
+      if (q == 3) {
+        srow = 64 + pr.y + lane;
+        wr = pr.y + lane < slot8;
+      }
+      const uint32_t stg = smem_u32(smem + s * STAGE) + srow * 128;
+      if (wr) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        sts128(stg + ((c ^ (row & 7)) << 4),
-               pack_act(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv, p.fp16),
-               pack_act(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv, p.fp16),
-               pack_act(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv, p.fp16),
-               pack_act(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv, p.fp16));
+        for (int c = 0; c < 8; ++c)
+          sts128(stg + ((c ^ (srow & 7)) << 4),
+                 pack_act(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv, p.fp16),
+                 pack_act(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv, p.fp16),
+                 pack_act(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv, p.fp16),
+                 pack_act(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv, p.fp16));
+      }
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && lane == 0) {
@@ -235,11 +248,9 @@ qf_self_attention_ragged_kernel(const __grid_constant__ CUtensorMap tmQ, const _
         // query rows of sample 0 and (if it exists) sample 1: 32-row boxes
         tma_store_2d(&tmO32, base, h * 64, g * 64);
         if (pr.w > 0) tma_store_2d(&tmO32, base + QUARTER, h * 64, g * 64 + 32);
-        // each sample's text slot, 8 rows at a time (nothing beyond it: those rows belong to other samples)
-        for (int i = 0; i < (pr.y + 7) >> 3; ++i)
+        // the pair's text slot, 8 rows at a time (nothing beyond it: those rows belong to other pairs)
+        for (int i = 0; i < (slot8 >> 3); ++i)
           tma_store_2d(&tmO8, base + 2 * QUARTER + i * 8 * 128, h * 64, p.text_base + pr.x + 8 * i);
-        for (int i = 0; i < (pr.w + 7) >> 3; ++i)
-          tma_store_2d(&tmO8, base + 3 * QUARTER + i * 8 * 128, h * 64, p.text_base + pr.z + 8 * i);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(&empty[s]);  // Q (staging), K, V of this stage may be refilled

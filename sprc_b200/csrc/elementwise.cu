@@ -205,8 +205,9 @@ int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_
   return 0;
 }
 
-// Ragged layout (attention_qfr.cu): rows [0, 32 B) query rows, rows [32 B + toff[b], + L8[b]) text rows of sample b.
-// One block per query row, then one block per text slot row; slack rows (t >= L[b]) are zero.
+// Ragged layout (attention_qfr.cu): rows [0, 32 B) query rows, rows [32 B + toff[b], + L[b]) text rows of sample b.
+// One block per query row, then one block per text row (row_sample[slot] = owning sample); slack rows (t >= L[b]) are
+// zero.
 __global__ void __launch_bounds__(192)
 qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, const int64_t* __restrict__ ids,
                             const int* __restrict__ slot_sample, const int* __restrict__ toff,
@@ -219,7 +220,7 @@ qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, con
     v = q_is_batched ? qe[(size_t)r * 192 + c] : __ldg(qe + (size_t)(r & 31) * 192 + c);
   } else {
     const int slot = r - 32 * B;            // row inside the text region
-    const int b = slot_sample[slot >> 3];   // sample owning this 8-row group
+    const int b = slot_sample[slot];        // sample owning this row (slack rows: the pair's second sample)
     const int t = slot - toff[b];
     if (t < len[b]) {
       long long id = ids[(size_t)b * 32 + t];

@@ -284,7 +284,7 @@ int Model::init(int kind, int vit_depth, int qf_layers_, int max_images_, int ma
   SPRC_TRY(alloc_t(&d_mask, nq * 32));
   SPRC_TRY(alloc_t(&d_rows, nq + 16));
   SPRC_TRY(alloc_t(&d_rows2, nq + 16));
-  SPRC_TRY(alloc_t(&d_meta, nq * 9 + 64));
+  SPRC_TRY(alloc_t(&d_meta, nq * 40 + 64));
   SPRC_TRY(alloc_t(&d_fusion, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_score, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_idx, nq * 256));
@@ -733,37 +733,44 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
                                cudaStream_t st) {
   SPRC_REQUIRE(Bq > 0 && Bq <= max_queries, "encode_query: Bq=%d outside (0, %d]", Bq, max_queries);
   SPRC_REQUIRE(ref_dtype == SPRC_F32 || ref_dtype == SPRC_BF16, "encode_query: ref dtype %d unsupported", ref_dtype);
-  // ---- row tables: toff[B] | len[B] | cls[B] | slot_sample[T8 / 8] | pairs int4 [ceil(B / 2)] ----
+  // ---- row tables: toff[B] | len[B] | cls[B] | row_sample[T8] | pairs int4 [ceil(B / 2)] ----
+  // text rows: the two samples of a pair are adjacent, each pair's slot is rounded up to 8 rows
   const int B = Bq, P = (B + 1) / 2;
   h_meta.assign((size_t)B * 3, 0);
   int T8 = 0;
-  std::vector<int32_t> slot;
-  slot.reserve((size_t)B * 4);
-  for (int b = 0; b < B; ++b) {
-    int L = text_len_host[b];
-    SPRC_REQUIRE(L >= 0 && L <= 32, "encode_query: caption %d has %d live tokens", b, L);
-    if (L < 1) L = 1;   // an all-masked caption still owns its [CLS] row (the padded path reads row 32 regardless)
-    const int L8 = (L + 7) & ~7;
-    h_meta[b] = T8;
-    h_meta[B + b] = L;
-    h_meta[2 * B + b] = T8;   // [CLS] = first text row of the sample
-    for (int i = 0; i < L8 / 8; ++i) slot.push_back(b);
-    T8 += L8;
+  std::vector<int32_t> rsmp;
+  rsmp.reserve((size_t)B * 20);
+  for (int g = 0; g < P; ++g) {
+    int used = 0;
+    for (int b = 2 * g; b < 2 * g + 2 && b < B; ++b) {
+      int L = text_len_host[b];
+      SPRC_REQUIRE(L >= 0 && L <= 32, "encode_query: caption %d has %d live tokens", b, L);
+      if (L < 1) L = 1;   // an all-masked caption still owns its [CLS] row (the padded path reads row 32 regardless)
+      h_meta[b] = T8 + used;
+      h_meta[B + b] = L;
+      h_meta[2 * B + b] = T8 + used;   // [CLS] = first text row of the sample
+      for (int i = 0; i < L; ++i) rsmp.push_back(b);
+      used += L;
+    }
+    const int slot8 = (used + 7) & ~7;
+    const int last = (2 * g + 1 < B) ? 2 * g + 1 : 2 * g;
+    for (int i = used; i < slot8; ++i) rsmp.push_back(last);   // slack rows (t >= L: written as zeros)
+    T8 += slot8;
   }
   const size_t off_slot = (size_t)B * 3;
-  size_t off_pairs = off_slot + slot.size();
+  size_t off_pairs = off_slot + rsmp.size();
   off_pairs = (off_pairs + 3) & ~size_t(3);   // int4 alignment
   h_meta.resize(off_pairs + (size_t)P * 4, 0);
-  for (size_t i = 0; i < slot.size(); ++i) h_meta[off_slot + i] = slot[i];
+  for (size_t i = 0; i < rsmp.size(); ++i) h_meta[off_slot + i] = rsmp[i];
   for (int g = 0; g < P; ++g) {
     const int b0 = 2 * g, b1 = 2 * g + 1;
     const int L0 = h_meta[B + b0], L1 = b1 < B ? h_meta[B + b1] : 0;
     h_meta[off_pairs + 4 * g] = h_meta[b0];
     h_meta[off_pairs + 4 * g + 1] = L0;
-    h_meta[off_pairs + 4 * g + 2] = b1 < B ? h_meta[b1] : h_meta[b0];
+    h_meta[off_pairs + 4 * g + 2] = h_meta[b0] + L0;   // sample 1 follows sample 0 directly
     h_meta[off_pairs + 4 * g + 3] = L1;
   }
-  SPRC_REQUIRE(h_meta.size() <= (size_t)max_queries * 9 + 64, "encode_query: row tables exceed their buffer");
+  SPRC_REQUIRE(h_meta.size() <= (size_t)max_queries * 40 + 64, "encode_query: row tables exceed their buffer");
   // pageable source: the copy is staged before the call returns, so h_meta may be rebuilt for the next batch
   SPRC_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), h_meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   m_toff = d_meta;

@@ -14,16 +14,20 @@ torch.manual_seed(0)
 
 def run(lens):
     B = len(lens)
-    L8 = [(n + 7) // 8 * 8 for n in lens]
-    toff = [sum(L8[:b]) for b in range(B)]
-    T8 = sum(L8)
+    toff, T8 = [], 0
+    for g in range((B + 1) // 2):
+        used = 0
+        for b in range(2 * g, min(2 * g + 2, B)):
+            toff.append(T8 + used)
+            used += lens[b]
+        T8 += (used + 7) // 8 * 8
     rows = 32 * B + T8
     qkv = (torch.randn(rows, 2304, device=dev) * 0.5).bfloat16()
     out = torch.full((rows, 768), float("nan"), device=dev).bfloat16()
     pairs = []
     for g in range((B + 1) // 2):
         b0, b1 = 2 * g, 2 * g + 1
-        pairs += [toff[b0], lens[b0], toff[b1] if b1 < B else toff[b0], lens[b1] if b1 < B else 0]
+        pairs += [toff[b0], lens[b0], toff[b0] + lens[b0], lens[b1] if b1 < B else 0]
     pd = torch.tensor(pairs, dtype=torch.int32, device=dev)
     L.check(lib.sprc_op_attention_ragged(L.ptr(qkv), 2304, L.ptr(out), 768, B, rows, L.ptr(pd), 0.125, L.cur_stream()))
     torch.cuda.synchronize()
