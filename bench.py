@@ -62,6 +62,17 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures of this workload
+    (profiles/ncu_traffic.json, written by tools/summarize_ncu.py from `ncu --metrics dram__bytes_*` /
+    `ncu --set full` runs of the same query step); None when no capture has been summarised."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -365,7 +376,9 @@ def main():
     scan_gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9 if scan["ms"] > 0 else 0.0
     scan_tf = scan["flops"] / (scan["ms"] / 1e3) / 1e12 if scan["ms"] > 0 else 0.0
     roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tf,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"], "traffic": None,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
+                "traffic": ncu_traffic().get("gemm_bytes_per_launch"),
+                "traffic_source": ncu_traffic().get("gemm_source"),
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": gemm["n"] / K, "avg_launch_us": gemm["ms"] * 1e3 / max(gemm["n"], 1),
                 "share_of_step": gemm["ms"] / prof_total if prof_total else None,
@@ -394,7 +407,8 @@ def main():
     s_ms, s_bytes, s_n = prof2[3 * 4], prof2[3 * 4 + 2], prof2[3 * 4 + 3]
     hbm_gbs = s_bytes / (s_ms / 1e3) / 1e9 if s_ms > 0 else 0.0
     roofline_scan_hbm = {"kernel": "scan_topk_kernel", "bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm"],
-                         "unit": "GB/s", "frac": hbm_gbs / pk["hbm"], "traffic": None,
+                         "unit": "GB/s", "frac": hbm_gbs / pk["hbm"],
+                         "traffic": ncu_traffic().get("scan_bytes_per_launch"),
                          "avg_launch_us": s_ms * 1e3 / max(s_n, 1),
                          "note": "128 queries (one UMMA M tile) x the %d-row gallery shard, top-%d; gallery "
                                  "(%.0f MB) exceeds L2; algorithmic bytes N*32*256*2 + Q*512 per launch" % (

@@ -20,14 +20,15 @@ model.load_state_dict(sd, strict=False)
 N = 2048
 raws = torch.randn(N, 257, 1024, device=dev).bfloat16()
 ids, mask = synth.make_token_ids(Bq, seed=1)
+lens = mask.sum(dim=1).to(torch.int32).contiguous()   # host: caption lengths for the ragged passes
 ids, mask = ids.to(dev), mask.to(dev)
 rows = torch.randint(0, N, (Bq,), dtype=torch.int32).to(dev)
 fusion = torch.empty(Bq, 256, device=dev, dtype=torch.bfloat16)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(iters):
     e0.record()
-    L.check(lib.sprc_encode_query(model._h, L.ptr(raws), L.BF16, L.ptr(rows), L.ptr(ids), L.ptr(mask), Bq, None,
-                                  L.ptr(fusion), L.cur_stream()))
+    L.check(lib.sprc_encode_query_lens(model._h, L.ptr(raws), L.BF16, L.ptr(rows), L.ptr(ids), L.ptr(lens), Bq, None,
+                                       L.ptr(fusion), L.cur_stream()))
     e1.record()
     torch.cuda.synchronize()
     print(f"encode_query Bq={Bq}: {e0.elapsed_time(e1):.3f} ms = {Bq / e0.elapsed_time(e1) * 1e3:.0f} q/s")

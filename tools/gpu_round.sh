@@ -12,8 +12,11 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_be
 # launch list of the same command (short): cold-cache serialised per-launch times
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_ncu_launches.csv \
   python bench.py --steps 2 --warmup 3 --index-images 128 --no-cpu-baseline > $O/${TAG}_ncu_launches_run.log 2>&1
+# dram bytes of every GEMM launch of the query steps (roofline.traffic = mean over the launches)
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_bf16_tcgen05 --csv --log-file $O/${TAG}_ncu_gemm_traffic.csv \
+  python tests/gpu_prof_qstep.py 592 1 > $O/${TAG}_ncu_gemm_traffic_run.log 2>&1
 # full captures of the top kernels of one query step (ViT depth 1 model, query path only)
-for spec in "gemm:regex:gemm_bf16_tcgen05:30:3" "scan:regex:scan_topk:0:1" "ln:regex:layernorm:20:2" "attnqf:regex:qf_.*attention_tc:4:2"; do
+for spec in "gemm:regex:gemm_bf16_tcgen05_2cta:30:4" "scan:regex:scan_topk:0:1" "ln:regex:layernorm:20:2" "attnqf:regex:qf_.*attention_tc:4:2"; do
   IFS=: read name kind pat skip cnt <<< "$spec"
   if [ "$name" = "scan" ]; then
     timeout 300 ncu --set full --clock-control none --import-source on -k $kind:$pat -s $skip -c $cnt -f -o $O/${TAG}_full_$name \
