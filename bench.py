@@ -452,6 +452,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_scan": roofline_scan, "roofline_scan_hbm": roofline_scan_hbm,
             "step_breakdown_ms": breakdown,
+            # queries/s x the REFERENCE's FLOPs per composed query (all 64 padded rows) / sustained peak: an
+            # "effective" figure - the ragged passes execute fewer FLOPs than that; roofline.achieved counts executed ones
             "frac_of_qformer_gemm_roofline": value / world * FLOP_PER_QUERY[args.vit] / (pk["tf_sust"] * 1e12),
             "index_build": {"images_per_s_per_gpu": index_ips, "seconds": index_s,
                             "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (pk["tf_sust"] * 1e12),
