@@ -200,8 +200,8 @@ def main():
 
     import torch.distributed as dist
 
-    from oracle import synth
     from sprc_b200 import _lib as L
+    from sprc_b200 import synth
     from sprc_b200.model import Blip2QformerCirAlignPrompt
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -440,7 +440,7 @@ def main():
                        "l2": "inputs_exceed_l2 (gallery %.0f MB + weights; query batches rotate)" % (
                            n_local * 32 * 256 * 2 / 1e6),
                        "parallelism": "gallery rows sharded x%d, queries data-parallel" % world,
-                       "weights": "synthetic seed 0, full depth (oracle/synth.py)",
+                       "weights": "synthetic seed 0, full depth (sprc_b200/synth.py)",
                        "captions": "32-token rows, %.1f live tokens on average (SURVEY 8d: L~U{3..20} + [CLS],[SEP]); "
                                    "%s" % (float(lens_h.float().mean()),
                                            "query passes over live text rows only (ragged layout)" if ragged

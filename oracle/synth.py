@@ -1,136 +1,6 @@
-"""TEST INFRASTRUCTURE — seeded synthetic checkpoints and inputs shared by the oracle, the golden-vector
-generator, the parity tests and bench.py (SURVEY.md §8d "Synthetic inputs").
-
-No dataset, checkpoint or tokenizer vocabulary exists offline, so both the reference (in the build
-container) and the CUDA path (on the GPU box) are driven from the same generated state dict
-(reference key names and shapes) and the same generated images / token ids.
-Everything here is deterministic CPU torch RNG, so the GPU box regenerates bit-identical tensors.
-"""
-from __future__ import annotations
-
-import torch
-
-VIT_DIMS = {
-    # name: (width, full depth, heads, mlp)
-    "eva_clip_g": (1408, 39, 16, 6144),
-    "clip_L": (1024, 23, 16, 4096),
-}
-
-
-def state_dict_spec(vit: str, vit_depth: int | None = None, qf_layers: int = 12, with_lm_head: bool = False):
-    """[(key, shape, kind)] in checkpoint order; kind in {w, b, ln_w, ln_b, emb}."""
-    Dv, full_depth, _, mlp = VIT_DIMS[vit]
-    depth = vit_depth or full_depth
-    spec = [("query_tokens", (1, 32, 768), "emb"), ("temp", (), "temp"), ("prompt_tokens", (1, 32, 768), "emb")]
-    ve = "visual_encoder."
-    if vit == "eva_clip_g":
-        spec += [(ve + "cls_token", (1, 1, Dv), "emb"), (ve + "pos_embed", (1, 257, Dv), "emb"),
-                 (ve + "patch_embed.proj.weight", (Dv, 3, 14, 14), "w"), (ve + "patch_embed.proj.bias", (Dv,), "b")]
-        for i in range(depth):
-            p = f"{ve}blocks.{i}."
-            spec += [(p + "norm1.weight", (Dv,), "ln_w"), (p + "norm1.bias", (Dv,), "ln_b"),
-                     (p + "attn.q_bias", (Dv,), "b"), (p + "attn.v_bias", (Dv,), "b"),
-                     (p + "attn.qkv.weight", (3 * Dv, Dv), "w"),
-                     (p + "attn.proj.weight", (Dv, Dv), "w"), (p + "attn.proj.bias", (Dv,), "b"),
-                     (p + "norm2.weight", (Dv,), "ln_w"), (p + "norm2.bias", (Dv,), "ln_b"),
-                     (p + "mlp.fc1.weight", (mlp, Dv), "w"), (p + "mlp.fc1.bias", (mlp,), "b"),
-                     (p + "mlp.fc2.weight", (Dv, mlp), "w"), (p + "mlp.fc2.bias", (Dv,), "b")]
-    else:
-        spec += [(ve + "class_embedding", (Dv,), "emb"), (ve + "positional_embedding", (257, Dv), "emb"),
-                 (ve + "conv1.weight", (Dv, 3, 14, 14), "w"),
-                 (ve + "ln_pre.weight", (Dv,), "ln_w"), (ve + "ln_pre.bias", (Dv,), "ln_b")]
-        for i in range(depth):
-            p = f"{ve}transformer.resblocks.{i}."
-            spec += [(p + "attn.in_proj_weight", (3 * Dv, Dv), "w"), (p + "attn.in_proj_bias", (3 * Dv,), "b"),
-                     (p + "attn.out_proj.weight", (Dv, Dv), "w"), (p + "attn.out_proj.bias", (Dv,), "b"),
-                     (p + "ln_1.weight", (Dv,), "ln_w"), (p + "ln_1.bias", (Dv,), "ln_b"),
-                     (p + "mlp.c_fc.weight", (mlp, Dv), "w"), (p + "mlp.c_fc.bias", (mlp,), "b"),
-                     (p + "mlp.c_proj.weight", (Dv, mlp), "w"), (p + "mlp.c_proj.bias", (Dv,), "b"),
-                     (p + "ln_2.weight", (Dv,), "ln_w"), (p + "ln_2.bias", (Dv,), "ln_b")]
-    spec += [("ln_vision.weight", (Dv,), "ln_w"), ("ln_vision.bias", (Dv,), "ln_b")]
-    qb = "Qformer.bert."
-    spec += [(qb + "embeddings.word_embeddings.weight", (30523, 768), "emb"),
-             (qb + "embeddings.position_embeddings.weight", (512, 768), "emb"),
-             (qb + "embeddings.LayerNorm.weight", (768,), "ln_w"), (qb + "embeddings.LayerNorm.bias", (768,), "ln_b")]
-    for l in range(qf_layers):
-        p = f"{qb}encoder.layer.{l}."
-
-        def attn(prefix, kv_width):
-            return [(prefix + "self.query.weight", (768, 768), "w"), (prefix + "self.query.bias", (768,), "b"),
-                    (prefix + "self.key.weight", (768, kv_width), "w"), (prefix + "self.key.bias", (768,), "b"),
-                    (prefix + "self.value.weight", (768, kv_width), "w"), (prefix + "self.value.bias", (768,), "b"),
-                    (prefix + "output.dense.weight", (768, 768), "w"), (prefix + "output.dense.bias", (768,), "b"),
-                    (prefix + "output.LayerNorm.weight", (768,), "ln_w"),
-                    (prefix + "output.LayerNorm.bias", (768,), "ln_b")]
-
-        spec += attn(p + "attention.", 768)
-        if l % 2 == 0:
-            spec += attn(p + "crossattention.", Dv)
-        for nm in ("", "_query"):
-            spec += [(p + f"intermediate{nm}.dense.weight", (3072, 768), "w"),
-                     (p + f"intermediate{nm}.dense.bias", (3072,), "b"),
-                     (p + f"output{nm}.dense.weight", (768, 3072), "w"), (p + f"output{nm}.dense.bias", (768,), "b"),
-                     (p + f"output{nm}.LayerNorm.weight", (768,), "ln_w"),
-                     (p + f"output{nm}.LayerNorm.bias", (768,), "ln_b")]
-    spec += [("vision_proj.weight", (256, 768), "w"), ("vision_proj.bias", (256,), "b"),
-             ("text_proj.weight", (256, 768), "w"), ("text_proj.bias", (256,), "b"),
-             ("itm_head.weight", (2, 768), "w_itm"), ("itm_head.bias", (2,), "b")]
-    return spec
-
-
-def make_state_dict(vit: str, vit_depth: int | None = None, qf_layers: int = 12, seed: int = 0):
-    """Seeded fp32 state dict under the reference's key names.  Scales follow the reference's own
-    initialisers (std 0.02, eva_vit.py:300-315 / Qformer.py:670-680) but LayerNorm affine parameters and
-    biases are perturbed away from (1, 0) so that every parameter participates in the parity check."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    for key, shape, kind in state_dict_spec(vit, vit_depth, qf_layers):
-        if kind == "temp":
-            sd[key] = torch.tensor(0.07)
-        elif kind == "w":
-            sd[key] = torch.randn(shape, generator=g) * 0.02
-        elif kind == "w_itm":
-            sd[key] = torch.randn(shape, generator=g) * 0.2
-        elif kind == "b":
-            sd[key] = torch.randn(shape, generator=g) * 0.02
-        elif kind == "ln_w":
-            sd[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
-        elif kind == "ln_b":
-            sd[key] = 0.05 * torch.randn(shape, generator=g)
-        elif kind == "emb":
-            sd[key] = torch.randn(shape, generator=g) * 0.02
-        else:
-            raise ValueError(kind)
-    return sd
-
-
-def make_images(n: int, seed: int = 1234):
-    """randn images clamped to the post-Normalize range of data_utils.py:104."""
-    g = torch.Generator().manual_seed(seed)
-    return torch.randn(n, 3, 224, 224, generator=g).clamp_(-2.2, 2.2)
-
-
-def make_token_ids(n: int, seed: int = 4321):
-    """[CLS] w_1..w_L [SEP] pad...  with L ~ U{3..20}, w ~ U{1000..29999}; returns (ids, mask) int64 [n,32]."""
-    g = torch.Generator().manual_seed(seed)
-    ids = torch.zeros(n, 32, dtype=torch.long)
-    for i in range(n):
-        L = int(torch.randint(3, 21, (1,), generator=g))
-        ids[i, 0] = 101
-        ids[i, 1:1 + L] = torch.randint(1000, 30000, (L,), generator=g)
-        ids[i, 1 + L] = 102
-    return ids, (ids != 0).long()
-
-
-def make_gallery_features(n: int, seed: int = 99, device="cpu", dtype=torch.float32):
-    """Unit-norm randn gallery features [n,32,256] for scan-only measurements."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.randn(n, 32, 256, generator=g, device=device, dtype=torch.float32)
-    return torch.nn.functional.normalize(x, dim=-1).to(dtype)
-
-
-def make_dyadic(shape, seed: int, device="cpu"):
-    """Entries k/16 with |k| <= 4: every 256-term dot product is exact in fp32 and in bf16 storage, so
-    rankings are independent of summation order (SURVEY.md §7 "Bit-exact top-k")."""
-    g = torch.Generator().manual_seed(seed)
-    return (torch.randint(-4, 5, shape, generator=g).float() / 16.0).to(device)
+"""TEST INFRASTRUCTURE — the synthetic checkpoint / input generators live in sprc_b200/synth.py (bench.py's own arm
+needs them and may not import from oracle/); this module re-exports them for the oracle, the golden-vector generator
+and the tests."""
+from sprc_b200.synth import *  # noqa: F401,F403
+from sprc_b200.synth import VIT_DIMS, make_dyadic, make_gallery_features, make_images, make_state_dict  # noqa: F401
+from sprc_b200.synth import make_token_ids, state_dict_spec  # noqa: F401
