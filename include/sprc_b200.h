@@ -125,6 +125,10 @@ int sprc_rerank(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, 
 
 /* End-to-end query step with HOST buffers (what generate_*_val_predictions + compute_* do per batch,
  * validate_blip.py:386-408,253-255): H2D of ids/mask/ref_rows, fusion, scan, top-k, D2H of [Bq,k]. */
+/* sprc_rerank over the live text rows only (see sprc_encode_query_lens): text_len_host int32 [R] in HOST memory. */
+int sprc_rerank_lens(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
+                     const int64_t* input_ids, const int32_t* text_len_host, int R, int T, float* p, void* stream);
+
 int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
                          const int32_t* ref_rows_host, const int64_t* input_ids_host,
                          const int64_t* attention_mask_host, int Bq, int k, float* out_score_host,

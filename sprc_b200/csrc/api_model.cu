@@ -150,8 +150,20 @@ int sprc_rerank(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, 
   for (const char* nm : {"itm_head.weight", "itm_head.bias"})
     if (!h->m.slots[nm].loaded) return set_error(-61, "sprc_rerank: %s was never loaded", nm);
   if (h->m.count_missing() != 0) return set_error(-61, "sprc_rerank: weights missing");
-  return h->m.rerank(static_cast<const bf16*>(raws_bf16), ref_rows, cand_rows, input_ids, attention_mask, R, T, p,
-                     S(stream));
+  return h->m.rerank(static_cast<const bf16*>(raws_bf16), ref_rows, cand_rows, input_ids, attention_mask, nullptr, R,
+                     T, p, S(stream));
+}
+
+int sprc_rerank_lens(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
+                     const int64_t* input_ids, const int32_t* text_len_host, int R, int T, float* p, void* stream) {
+  if (!h || !raws_bf16 || !ref_rows || !cand_rows || !input_ids || !text_len_host || !p)
+    return set_error(-22, "sprc_rerank_lens: null argument");
+  for (const char* nm : {"itm_head.weight", "itm_head.bias"})
+    if (!h->m.slots[nm].loaded) return set_error(-61, "sprc_rerank_lens: %s was never loaded", nm);
+  if (h->m.count_missing() != 0) return set_error(-61, "sprc_rerank_lens: weights missing");
+  SPRC_REQUIRE(ragged_query_enabled(), "sprc_rerank_lens: the ragged passes are disabled (SPRC_RAGGED=0)");
+  return h->m.rerank(static_cast<const bf16*>(raws_bf16), ref_rows, cand_rows, input_ids, nullptr, text_len_host, R, T,
+                     p, S(stream));
 }
 
 int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,

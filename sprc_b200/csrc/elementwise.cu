@@ -210,7 +210,7 @@ int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_
 // zero.
 __global__ void __launch_bounds__(192)
 qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, const int64_t* __restrict__ ids,
-                            const int* __restrict__ slot_sample, const int* __restrict__ toff,
+                            int ids_div, const int* __restrict__ slot_sample, const int* __restrict__ toff,
                             const int* __restrict__ len, const float4* __restrict__ word,
                             const float4* __restrict__ pos, int vocab, int B, float4* __restrict__ out) {
   const int r = blockIdx.x;
@@ -223,7 +223,7 @@ qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, con
     const int b = slot_sample[slot];        // sample owning this row (slack rows: the pair's second sample)
     const int t = slot - toff[b];
     if (t < len[b]) {
-      long long id = ids[(size_t)b * 32 + t];
+      long long id = ids[(size_t)(b / ids_div) * 32 + t];   // rerank repeats each caption for its T candidates
       if (id < 0) id = 0;
       if (id >= vocab) id = vocab - 1;
       const float4 w = __ldg(word + (size_t)id * 192 + c);
@@ -236,12 +236,13 @@ qformer_embed_ragged_kernel(const float4* __restrict__ qe, int q_is_batched, con
   out[(size_t)r * 192 + c] = v;
 }
 
-int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, const int* slot_sample,
-                         const int* toff, const int* len, const float* word_emb, const float* pos_emb, int vocab, int B,
-                         int rows_total, float* out, cudaStream_t st) {
+int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, int ids_div,
+                         const int* slot_sample, const int* toff, const int* len, const float* word_emb,
+                         const float* pos_emb, int vocab, int B, int rows_total, float* out, cudaStream_t st) {
   if (B <= 0) return 0;
+  if (ids_div < 1) ids_div = 1;
   qformer_embed_ragged_kernel<<<rows_total, 192, 0, st>>>(
-      reinterpret_cast<const float4*>(query_embeds), q_is_batched, ids, slot_sample, toff, len,
+      reinterpret_cast<const float4*>(query_embeds), q_is_batched, ids, ids_div, slot_sample, toff, len,
       reinterpret_cast<const float4*>(word_emb), reinterpret_cast<const float4*>(pos_emb), vocab, B,
       reinterpret_cast<float4*>(out));
   count_launch();

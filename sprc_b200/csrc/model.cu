@@ -284,7 +284,8 @@ int Model::init(int kind, int vit_depth, int qf_layers_, int max_images_, int ma
   SPRC_TRY(alloc_t(&d_mask, nq * 32));
   SPRC_TRY(alloc_t(&d_rows, nq + 16));
   SPRC_TRY(alloc_t(&d_rows2, nq + 16));
-  SPRC_TRY(alloc_t(&d_meta, nq * 40 + 64));
+  meta_cap = nq * 40 + 64;
+  SPRC_TRY(alloc_t(&d_meta, meta_cap));
   SPRC_TRY(alloc_t(&d_fusion, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_score, nq * 256));
   SPRC_TRY(alloc_t(&d_topk_idx, nq * 256));
@@ -663,7 +664,8 @@ bool ragged_query_enabled() {
 // computes the query rows only, align_prompt.py:343).  !with_enc: text pass (text FFN on every row, Qformer.py:434-435,
 // 469-475; the last layer computes the [CLS] rows only, gathered into dense [B, 768] buffers: qt = fp32, qcq = 16-bit,
 // align_prompt.py:348).
-int Model::qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st) {
+int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
+                                 cudaStream_t st) {
   const int qrows = 32 * B, rows_all = qrows + T8;
   SPRC_REQUIRE(rows_all <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows_all, qf_rows);
   const size_t to = (size_t)qrows;   // first text row
@@ -690,17 +692,25 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st) 
         SPRC_TRY(linear(qhb, qrows, 768, 768, L.cq_w, 768, L.cq_b, ACT_NONE, nullptr, nullptr, qcq, 768, 0, 0, st));
         AttnDesc c;
         c.Q = qcq;
-        c.K = kv + (size_t)ci * 24 * kv_rows * 64;
-        c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
-        c.kv_head_stride = kv_rows * 64;
+        if (kv_idx0) {   // rerank: plain K/V rows, keys = cat(reference image, candidate image)
+          c.K = kv + (size_t)ci * 1536;
+          c.V = kv + (size_t)ci * 1536 + 768;
+          c.ldk = c.ldv = n_cross * 1536;
+          c.kv_idx0 = kv_idx0;
+          c.kv_idx1 = kv_idx1;
+        } else {         // head-major blocks (cross_kv)
+          c.K = kv + (size_t)ci * 24 * kv_rows * 64;
+          c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
+          c.kv_head_stride = kv_rows * 64;
+          c.ldk = c.ldv = 64;
+        }
         c.O = qctx;
         c.B = B;
         c.H = 12;
         c.dh = 64;
         c.Lq = 32;
-        c.Lk = 257;
+        c.Lk = Lk;
         c.ldq = 768;
-        c.ldk = c.ldv = 64;
         c.ldo = 768;
         c.q_batch_rows = 32;
         c.kv_batch_rows = 257;
@@ -728,14 +738,14 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st) 
   return 0;
 }
 
-int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
-                               const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16,
-                               cudaStream_t st) {
-  SPRC_REQUIRE(Bq > 0 && Bq <= max_queries, "encode_query: Bq=%d outside (0, %d]", Bq, max_queries);
-  SPRC_REQUIRE(ref_dtype == SPRC_F32 || ref_dtype == SPRC_BF16, "encode_query: ref dtype %d unsupported", ref_dtype);
+// Row tables of the ragged layout (attention_qfr.cu), uploaded to d_meta: toff[B] | len[B] | cls[B] | row_sample[T8] |
+// pairs int4 [ceil(B / 2)].  Text rows: the two samples of a pair are adjacent, each pair's slot is rounded up to 8.
+int Model::build_ragged_meta(const int32_t* lens_host, int repeat, int B, int* T8_out, cudaStream_t st) {
+  const int32_t* text_len_host = lens_host;
+  if (repeat < 1) repeat = 1;
   // ---- row tables: toff[B] | len[B] | cls[B] | row_sample[T8] | pairs int4 [ceil(B / 2)] ----
   // text rows: the two samples of a pair are adjacent, each pair's slot is rounded up to 8 rows
-  const int B = Bq, P = (B + 1) / 2;
+  const int P = (B + 1) / 2;
   h_meta.assign((size_t)B * 3, 0);
   int T8 = 0;
   std::vector<int32_t> rsmp;
@@ -743,7 +753,7 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
   for (int g = 0; g < P; ++g) {
     int used = 0;
     for (int b = 2 * g; b < 2 * g + 2 && b < B; ++b) {
-      int L = text_len_host[b];
+      int L = text_len_host[b / repeat];
       SPRC_REQUIRE(L >= 0 && L <= 32, "encode_query: caption %d has %d live tokens", b, L);
       if (L < 1) L = 1;   // an all-masked caption still owns its [CLS] row (the padded path reads row 32 regardless)
       h_meta[b] = T8 + used;
@@ -770,7 +780,8 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
     h_meta[off_pairs + 4 * g + 2] = h_meta[b0] + L0;   // sample 1 follows sample 0 directly
     h_meta[off_pairs + 4 * g + 3] = L1;
   }
-  SPRC_REQUIRE(h_meta.size() <= (size_t)max_queries * 40 + 64, "encode_query: row tables exceed their buffer");
+  SPRC_REQUIRE(h_meta.size() <= meta_cap, "ragged row tables (%zu ints) exceed their buffer (%zu)", h_meta.size(),
+               meta_cap);
   // pageable source: the copy is staged before the call returns, so h_meta may be rebuilt for the next batch
   SPRC_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), h_meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   m_toff = d_meta;
@@ -779,6 +790,18 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
   m_slot = d_meta + off_slot;
   m_pairs = d_meta + off_pairs;
 
+  *T8_out = T8;
+  return 0;
+}
+
+int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
+                               const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16,
+                               cudaStream_t st) {
+  SPRC_REQUIRE(Bq > 0 && Bq <= max_queries, "encode_query: Bq=%d outside (0, %d]", Bq, max_queries);
+  SPRC_REQUIRE(ref_dtype == SPRC_F32 || ref_dtype == SPRC_BF16, "encode_query: ref dtype %d unsupported", ref_dtype);
+  const int B = Bq;
+  int T8 = 0;
+  SPRC_TRY(build_ragged_meta(text_len_host, 1, B, &T8, st));
   const size_t row_elems = (size_t)257 * Dv;
   const bf16* rb;
   if (ref_rows) {
@@ -793,15 +816,15 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
   SPRC_TRY(cross_kv(rb, Bq, true, st));
   const int rows_all = 32 * B + T8;
   // pass 1: fusion = Qformer(text, query_tokens, enc = reference embeds)   (align_prompt.py:332-339)
-  SPRC_TRY(qformer_embed_ragged(query_tokens, 0, ids, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all, qt,
-                                st));
+  SPRC_TRY(qformer_embed_ragged(query_tokens, 0, ids, 1, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all,
+                                qt, st));
   SPRC_TRY(layernorm(qt, rows_all, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers_ragged(B, T8, true, st));
+  SPRC_TRY(qformer_layers_ragged(B, T8, true, 257, nullptr, nullptr, st));
   // pass 2: text = Qformer(text, query_embeds = fusion[:, :32]) with no encoder states (:341-346); the query rows of
   // pass 1's output are rows [0, 32 B) of qh
-  SPRC_TRY(qformer_embed_ragged(qh, 1, ids, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all, qt, st));
+  SPRC_TRY(qformer_embed_ragged(qh, 1, ids, 1, m_slot, m_toff, m_len, word_emb, pos_emb, vocab, B, rows_all, qt, st));
   SPRC_TRY(layernorm(qt, rows_all, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(qformer_layers_ragged(B, T8, false, st));
+  SPRC_TRY(qformer_layers_ragged(B, T8, false, 0, nullptr, nullptr, st));
   // fusion_feats = normalize(text_proj(h[:, 32]))   (:348-350): the gathered [CLS] rows (dense [B, 768] in qcq + B*768)
   SPRC_TRY(linear(qcq + (size_t)B * 768, Bq, 768, 768, tproj_w, 256, tproj_b, ACT_NONE, nullptr, qproj, nullptr, 256, 0,
                   0, st));
@@ -810,7 +833,7 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
 }
 
 int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t* cand_rows, const int64_t* ids,
-                  const int64_t* mask, int R, int T, float* p, cudaStream_t st) {
+                  const int64_t* mask, const int32_t* text_len_host, int R, int T, float* p, cudaStream_t st) {
   SPRC_REQUIRE(max_pairs > 0, "rerank: handle was created with max_pairs = 0");
   SPRC_REQUIRE(R > 0 && T > 0 && T <= max_pairs, "rerank: R=%d T=%d (max_pairs %d)", R, T, max_pairs);
   const size_t row_elems = (size_t)257 * Dv;
@@ -837,6 +860,19 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_CUDA(cudaMemcpyAsync(d_rows, idx0.data(), pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SPRC_CUDA(cudaMemcpyAsync(d_rows2, idx1.data(), pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SPRC_CUDA(cudaStreamSynchronize(st));  // idx0/idx1 host vectors are reused by the next chunk
+    if (text_len_host && ragged_enabled()) {
+      // ragged rows: every pair owns its 32 query rows + the live tokens of its caption (attention_qfr.cu)
+      int T8 = 0;
+      SPRC_TRY(build_ragged_meta(text_len_host + r0, T, pairs, &T8, st));
+      const int rows_all = 32 * pairs + T8;
+      SPRC_TRY(qformer_embed_ragged(query_tokens, 0, ids + (size_t)r0 * 32, T, m_slot, m_toff, m_len, word_emb, pos_emb,
+                                    vocab, pairs, rows_all, qt, st));
+      SPRC_TRY(layernorm(qt, rows_all, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));
+      SPRC_TRY(qformer_layers_ragged(pairs, T8, true, 514, d_rows, d_rows2, st));
+      SPRC_TRY(itm_head_prob(qh, 32, pairs, itm_w, itm_b, p + (size_t)r0 * T, st));
+      continue;
+    }
+    SPRC_REQUIRE(mask != nullptr, "rerank: attention mask or caption lengths needed");
     SPRC_TRY(qformer_key_mask(mask + (size_t)r0 * 32, T, pairs, qmask, st));
     SPRC_TRY(qformer_embed_rows(query_tokens, 0, ids + (size_t)r0 * 32, T, word_emb, pos_emb, vocab, pairs, qt, st));
     SPRC_TRY(layernorm(qt, pairs * 64, 768, emb_g, emb_b, 1e-12f, 0, 0, qh, qhb, st));

@@ -87,7 +87,8 @@ struct Model {
   int64_t* d_mask = nullptr;
   int32_t* d_rows = nullptr;
   int32_t* d_rows2 = nullptr;
-  int32_t* d_meta = nullptr;     // ragged layout tables (see encode_query_ragged)
+  int32_t* d_meta = nullptr;     // ragged layout tables (see build_ragged_meta)
+  size_t meta_cap = 0;
   std::vector<int32_t> h_meta;
   const int32_t *m_toff = nullptr, *m_len = nullptr, *m_slot = nullptr, *m_cls = nullptr;
   const void* m_pairs = nullptr;
@@ -130,9 +131,14 @@ struct Model {
   // computed.  text_len_host[b] = number of live tokens of caption b (sum of its attention mask), host memory.
   int encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
                           const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16, cudaStream_t st);
-  int qformer_layers_ragged(int B, int T8, bool with_enc, cudaStream_t st);
+  // kv_idx0 / kv_idx1 (rerank): two-segment keys cat(ref, target) through sample index tables over plain K/V rows
+  int qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
+                            cudaStream_t st);
+  // row tables of the ragged layout for B samples; sample b has lens_host[b / repeat] live text tokens
+  int build_ragged_meta(const int32_t* lens_host, int repeat, int B, int* T8_out, cudaStream_t st);
+  // text_len_host (optional, host int32 [R]): caption lengths -> ragged rows (live text tokens only)
   int rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t* cand_rows, const int64_t* ids,
-             const int64_t* mask, int R, int T, float* p, cudaStream_t st);
+             const int64_t* mask, const int32_t* text_len_host, int R, int T, float* p, cudaStream_t st);
 };
 
 }  // namespace sprc

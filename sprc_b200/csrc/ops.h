@@ -44,9 +44,9 @@ int qformer_embed_rows(const float* query_embeds, int q_batch_rows, const int64_
                        const float* word_emb, const float* pos_emb, int vocab, int B, float* out, cudaStream_t st);
 
 // Ragged Q-Former layout (attention_qfr.cu): pre-LayerNorm embedding rows and row gathers
-int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, const int* slot_sample,
-                         const int* toff, const int* len, const float* word_emb, const float* pos_emb, int vocab, int B,
-                         int rows_total, float* out, cudaStream_t st);
+int qformer_embed_ragged(const float* query_embeds, int q_is_batched, const int64_t* ids, int ids_div,
+                         const int* slot_sample, const int* toff, const int* len, const float* word_emb,
+                         const float* pos_emb, int vocab, int B, int rows_total, float* out, cudaStream_t st);
 int gather_rows768(const float* src32, const bf16* src16, const int* rows, int base, int n, float* dst32, bf16* dst16,
                    cudaStream_t st);
 int attention_qf_ragged(const bf16* qkv, int ldqkv, bf16* out, int ldo, int B, int rows_total, const int4* pairs_dev,

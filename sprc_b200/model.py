@@ -338,12 +338,22 @@ class Blip2QformerCirAlignPrompt:
     def rerank_rows(self, raws_bf16, ref_rows, cand_rows, input_ids, attention_mask, T):
         R = ref_rows.shape[0]
         ids = input_ids.to(self._device, torch.int64).contiguous()
-        am = attention_mask.to(self._device, torch.int64).contiguous()
+        lens = None
+        if attention_mask.device.type == "cpu" and self._ragged:   # caption lengths known on the host: ragged rows
+            m = attention_mask.to(torch.int64)
+            if bool((m[:, :-1] >= m[:, 1:]).all()) and bool(((m == 0) | (m == 1)).all()):
+                lens = m.sum(dim=1).to(torch.int32).contiguous()
         p = torch.empty(R * T, device=self._device)
+        rr = ref_rows.to(self._device, torch.int32).contiguous()
+        cr = cand_rows.to(self._device, torch.int32).contiguous()
         with torch.cuda.device(self._device):
-            L.check(self._lib.sprc_rerank(self._h, L.ptr(raws_bf16), L.ptr(ref_rows.to(torch.int32).contiguous()),
-                                          L.ptr(cand_rows.to(torch.int32).contiguous()), L.ptr(ids), L.ptr(am), R, T,
-                                          L.ptr(p), self._stream()))
+            if lens is not None:
+                L.check(self._lib.sprc_rerank_lens(self._h, L.ptr(raws_bf16), L.ptr(rr), L.ptr(cr), L.ptr(ids),
+                                                   L.ptr(lens), R, T, L.ptr(p), self._stream()))
+            else:
+                am = attention_mask.to(self._device, torch.int64).contiguous()
+                L.check(self._lib.sprc_rerank(self._h, L.ptr(raws_bf16), L.ptr(rr), L.ptr(cr), L.ptr(ids), L.ptr(am), R,
+                                              T, L.ptr(p), self._stream()))
         return p
 
 
