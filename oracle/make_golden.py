@@ -116,9 +116,13 @@ def run_cat(name="tiny_L_cat", base="tiny_L"):
     with torch.no_grad(), ref_loader.no_cuda_moves():
         feats, raws = model.extract_target_features(images)
         sim = ref_loader.call_inference(model, raws[ref_rows], feats, ids, mask)
+        # its own inference_rerank (:337-398): R = 2 references x T = 2 candidate FEATURE blocks [R*T,32,256]
+        rr = model.inference_rerank(raws[[0, 1]], feats[[2, 3, 1, 2]], ref_loader.TokenBatch(ids[:2], mask[:2]))
     out = dict(case=dict(cfg, name=name, seed=0, kind="cat"), feats=feats.clone(),
                sim=sim.reshape(cfg["n_queries"], -1).clone(), temp=float(sd["temp"]), ref_rows=ref_rows, input_ids=ids,
-               attention_mask=mask)
+               attention_mask=mask,
+               rerank=dict(R=2, T=2, ref_rows=torch.tensor([0, 1]), cand_rows=torch.tensor([2, 3, 1, 2]),
+                           sim=rr.clone()))
     torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
     print(f"[golden] {name}: sim {tuple(out['sim'].shape)} temp {out['temp']}", flush=True)
     return out

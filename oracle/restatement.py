@@ -209,6 +209,15 @@ def inference_rerank(sd, ref_embeds, tgt_embeds, input_ids, attention_mask):
     return logits.softmax(dim=-1)[:, -1]
 
 
+def cat_inference_rerank(sd, ref_embeds, tgt_feats, input_ids, attention_mask):
+    """blip2_qformer_cir_cat.py:337-398: the composed query of each of R references against its own T candidate
+    feature blocks `tgt_feats` [R*T,32,256]; sim = max over the 32 tokens (:392-394), no temperature."""
+    R = ref_embeds.shape[0]
+    T = tgt_feats.shape[0] // R if R > 1 else tgt_feats.shape[0]
+    f = fusion_features(sd, ref_embeds, input_ids, attention_mask).repeat_interleave(T, dim=0)   # [R*T,256]
+    return torch.einsum("ntd,nd->nt", tgt_feats, f).max(dim=-1).values
+
+
 # ------------------------------------------------------------------------------------------------
 # metrics tail of validate_blip.py on integer ids (SURVEY.md §8f N1); used to check Recall@K parity
 # ------------------------------------------------------------------------------------------------

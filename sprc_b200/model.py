@@ -396,8 +396,18 @@ class Blip2QformerCirCat(Blip2QformerCirAlignPrompt):
             return raws
         return feats.cpu(), raws.cpu()
 
+    @torch.no_grad()
     def inference_rerank(self, refereence_embeds, target_embeds, text):
-        raise NotImplementedError("blip2_cir_cat.inference_rerank (:338-398) is not wired; use blip2_cir_rerank")
+        """sim [R*T] — blip2_qformer_cir_cat.py:337-398.  `target_embeds` are candidate FEATURE blocks
+        [R*T,32,256] (the reference's docstring says raw embeds; the matmul at :392 needs 256-d rows): each reference's
+        composed query (the T repeated rows of :349-361 are identical, computed once here) is scored against its own T
+        candidates, max over the 32 tokens; no division by temp."""
+        tok = self._tokenize(text)
+        R, n = refereence_embeds.shape[0], target_embeds.shape[0]
+        T = n // R if R > 1 else n
+        fusion = self.encode_query(refereence_embeds, tok.input_ids, tok.attention_mask)
+        rows = torch.arange(R * T, device=self._device, dtype=torch.int32).view(R, T)
+        return self.gather_scores(fusion, self._gallery_bf16(target_embeds), rows).reshape(-1)
 
 
 MODEL_REGISTRY = {"blip2_cir_align_prompt": Blip2QformerCirAlignPrompt, "blip2_cir_rerank": Blip2QformerCirRerank,

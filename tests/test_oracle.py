@@ -140,3 +140,23 @@ def test_cir_cat_golden_is_align_prompt_similarity_over_temp():
     c = torch.load(os.path.join(gd, "tiny_L_cat.pt"))
     assert torch.allclose(c["feats"], a["feats"], atol=2e-6)
     assert torch.allclose(c["sim"] * c["temp"], a["sim"], atol=2e-6)
+
+
+def test_cir_cat_rerank_restatement_matches_reference_golden():
+    """blip2_cir_cat.inference_rerank (blip2_qformer_cir_cat.py:337-398) restated vs the reference's own output."""
+    import os
+
+    import torch
+
+    from oracle import restatement as R
+    from oracle import synth
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_L_cat.pt"))
+    case, rr = g["case"], g["rerank"]
+    sd = synth.make_state_dict(case["vit"], case["vit_depth"], case["qf_layers"], seed=0)
+    with torch.no_grad():
+        feats, raws = R.extract_target_features(sd, synth.make_images(case["n_images"]))
+        s = R.cat_inference_rerank(sd, raws[rr["ref_rows"]], feats[rr["cand_rows"]], g["input_ids"][:rr["R"]],
+                                   g["attention_mask"][:rr["R"]])
+    assert s.shape == rr["sim"].shape
+    assert (s - rr["sim"]).abs().max().item() < 2e-6
