@@ -128,10 +128,34 @@ def run_cat(name="tiny_L_cat", base="tiny_L"):
     return out
 
 
+def run_spread(name="spread_L"):
+    """Recall@K parity case: the reference's `inference` similarity [Q,N] on a gain-4 checkpoint (synth.make_state_dict:
+    similarities spread like a trained model's), N = 128 gallery images, Q = 64 composed queries.  The test plants the
+    labels from THIS ranking (restatement.plant_targets) and compares the recalls of the CUDA path with it."""
+    cfg = dict(vit="clip_L", vit_depth=2, qf_layers=2, n_images=128, n_queries=64, gain=4.0)
+    sd = synth.make_state_dict(cfg["vit"], cfg["vit_depth"], cfg["qf_layers"], seed=0, gain=cfg["gain"])
+    model = ref_loader.build_reference_model(cfg["vit"], seed=0, vit_depth=cfg["vit_depth"], qf_layers=cfg["qf_layers"])
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys
+    images = synth.make_images(cfg["n_images"])
+    ids, mask = synth.make_token_ids(cfg["n_queries"])
+    ref_rows = torch.randint(0, cfg["n_images"], (cfg["n_queries"],), generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        feats, raws = model.extract_target_features(images)
+        sim = torch.cat([ref_loader.call_inference(model, raws[ref_rows[i:i + 16]], feats, ids[i:i + 16], mask[i:i + 16])
+                         for i in range(0, cfg["n_queries"], 16)])
+    out = dict(case=dict(cfg, name=name, seed=0), sim=sim.clone(), ref_rows=ref_rows, input_ids=ids, attention_mask=mask)
+    torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"[golden] {name}: sim {tuple(sim.shape)} range [{sim.min():.3f}, {sim.max():.3f}]", flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tiny_L_cat"])
+    names = sys.argv[1:] or (list(CASES) + ["tiny_L_cat", "spread_L"])
     for n in names:
         if n == "tiny_L_cat":
             run_cat()
+        elif n == "spread_L":
+            run_spread()
         else:
             run_case(n, CASES[n])

@@ -241,3 +241,39 @@ def fiq_recalls(order, target_idx):
     labels = order == target_idx[:, None]
     Q = order.shape[0]
     return (labels[:, :10].sum().item() / Q) * 100.0, (labels[:, :50].sum().item() / Q) * 100.0
+
+
+def plant_targets(order, reference_idx, seed=11):
+    """Labels for a synthetic split, planted from an ORACLE ranking: after the reference image is
+    removed from each query's ranking (validate_blip.py:259-262) the target is the item at rank r, r drawn with
+    P(r<=1)=.2, P(r<=5)=.5, P(r<=10)=.7, P(r<=50)=.95, rest <=100 — so the oracle's recalls are ~20/50/70/95 %.
+    Returns (target_idx [Q], ranks [Q] 1-based, group_members [Q,6] holding the reference, the target and 4 others)."""
+    g = torch.Generator().manual_seed(seed)
+    Q, N = order.shape
+    hi = min(100, N - 1)
+    bands = [(1, 1, .2), (2, 5, .3), (6, 10, .2), (11, min(50, hi), .25), (min(51, hi), hi, .05)]
+    u = torch.rand(Q, generator=g)
+    ranks = torch.empty(Q, dtype=torch.long)
+    for j in range(Q):
+        acc = 0.0
+        for lo, up, p in bands:
+            acc += p
+            if u[j] < acc or (lo, up, p) == bands[-1]:
+                ranks[j] = int(torch.randint(lo, up + 1, (1,), generator=g))
+                break
+    keep = order != reference_idx[:, None]
+    ranked = order[keep].view(Q, N - 1)
+    target = ranked[torch.arange(Q), ranks - 1]
+    members = torch.empty(Q, 6, dtype=torch.long)
+    for j in range(Q):
+        others = [int(x) for x in torch.randperm(N, generator=g) if int(x) not in (int(reference_idx[j]), int(target[j]))][:4]
+        members[j] = torch.tensor([int(reference_idx[j]), int(target[j])] + others)
+    return target, ranks, members
+
+
+def target_ranks(sim, reference_idx, target_idx):
+    """1-based rank of each query's target in argsort(1 - sim) after the reference row is removed."""
+    order = ranking(sim)
+    Q, N = order.shape
+    ranked = order[order != reference_idx[:, None]].view(Q, N - 1)
+    return (ranked == target_idx[:, None]).float().argmax(dim=1) + 1

@@ -79,17 +79,20 @@ def state_dict_spec(vit: str, vit_depth: int | None = None, qf_layers: int = 12,
     return spec
 
 
-def make_state_dict(vit: str, vit_depth: int | None = None, qf_layers: int = 12, seed: int = 0):
+def make_state_dict(vit: str, vit_depth: int | None = None, qf_layers: int = 12, seed: int = 0, gain: float = 1.0):
     """Seeded fp32 state dict under the reference's key names.  Scales follow the reference's own
     initialisers (std 0.02, eva_vit.py:300-315 / Qformer.py:670-680) but LayerNorm affine parameters and
-    biases are perturbed away from (1, 0) so that every parameter participates in the parity check."""
+    biases are perturbed away from (1, 0) so that every parameter participates in the parity check.
+    `gain` multiplies every Linear / conv weight matrix: at the initialisers' scale (gain 1) the features of all
+    images nearly coincide (similarities within 0.157..0.173); gain 4 spreads them over [-0.13, 0.13] like a trained
+    model's, which is what a Recall@K comparison needs (tests/test_parity_gpu.py recall parity)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for key, shape, kind in state_dict_spec(vit, vit_depth, qf_layers):
         if kind == "temp":
             sd[key] = torch.tensor(0.07)
         elif kind == "w":
-            sd[key] = torch.randn(shape, generator=g) * 0.02
+            sd[key] = torch.randn(shape, generator=g) * 0.02 * gain   # gain 1.0: bit-identical to the earlier data
         elif kind == "w_itm":
             sd[key] = torch.randn(shape, generator=g) * 0.2
         elif kind == "b":

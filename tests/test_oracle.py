@@ -160,3 +160,32 @@ def test_cir_cat_rerank_restatement_matches_reference_golden():
                                    g["attention_mask"][:rr["R"]])
     assert s.shape == rr["sim"].shape
     assert (s - rr["sim"]).abs().max().item() < 2e-6
+
+
+def test_spread_golden_restatement_and_planted_recalls():
+    """Recall-parity case (tests/golden/spread_L.pt, the reference's `inference` on a gain-4 checkpoint): the
+    restatement reproduces the reference's similarity, and labels planted from that ranking give the oracle recalls
+    the planting distribution promises (every recall > 0, exactly one positive per query)."""
+    import os
+
+    import torch
+
+    from oracle import restatement as R
+    from oracle import synth
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spread_L.pt"))
+    c = g["case"]
+    sd = synth.make_state_dict(c["vit"], c["vit_depth"], c["qf_layers"], seed=0, gain=c["gain"])
+    with torch.no_grad():
+        feats, raws = R.extract_target_features(sd, synth.make_images(c["n_images"]))
+        sim = R.inference(sd, raws[g["ref_rows"]], feats, g["input_ids"], g["attention_mask"])
+    # fp32 summation-order noise (batch 64 here vs 16 in the reference run) through gain-4 weights: 2e-5 measured
+    assert (sim - g["sim"]).abs().max().item() < 5e-5
+    assert g["sim"].max() - g["sim"].min() > 0.2          # spread like a trained model's, not 0.157..0.173
+    order = R.ranking(g["sim"])
+    tgt, ranks, members = R.plant_targets(order, g["ref_rows"])
+    assert torch.equal(R.target_ranks(g["sim"], g["ref_rows"], tgt), ranks)
+    rec = R.cirr_recalls(order, g["ref_rows"], tgt, members)
+    Q = ranks.numel()
+    assert rec[3:] == tuple(100.0 * int((ranks <= k).sum()) / Q for k in (1, 5, 10, 50))
+    assert 5 < rec[3] < 40 and 30 < rec[4] < 70 and 50 < rec[5] < 90 and rec[6] > 85 and all(r > 0 for r in rec)
