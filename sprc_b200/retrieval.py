@@ -180,6 +180,97 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
     return sc, ix, sub
 
 
+# ---------------------------------------------------------------------------------------------------
+# rerank of the first T candidates  (cirr_test_submission.py:87-112, validate_blip_rerank.py:48-71,196-221)
+# ---------------------------------------------------------------------------------------------------
+def fetch_raw_rows(index: GalleryIndex, rows: torch.Tensor) -> torch.Tensor:
+    """Raw embeds [n,257,Dv] of GLOBAL gallery rows `rows` on this rank's device.  One rank: a gather from the
+    resident table.  Row-sharded index (SURVEY §8e "replicas + row fetch"): every rank tells every rank which rows
+    it needs (one small all-gather of row ids), owners send exactly those rows point to point (batched isend/irecv:
+    NVLink under NCCL, also valid under gloo).  Collective: every rank must call it the same number of times; a rank
+    with nothing to fetch passes an empty `rows`."""
+    dist, rank, world = _dist()
+    rows = rows.to(torch.int64).cpu()
+    dev = index.raws.device
+    if world == 1:
+        return index.raws[(rows - index.lo).to(dev)]
+    n = torch.tensor([rows.numel()], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c) for c in counts]
+    width = max(max(counts), 1)
+    mine = torch.full((width,), -1, dtype=torch.int64, device=dev)
+    mine[: rows.numel()] = rows.to(dev)
+    req = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(req, mine)
+    req = [r[:c].cpu() for r, c in zip(req, counts)]                      # what each rank needs
+    own = owner_of(rows, index.n_total, world)                            # who holds what I need
+    out = torch.empty((rows.numel(),) + tuple(index.raws.shape[1:]), dtype=index.raws.dtype, device=dev)
+    ops, recv_bufs, keep_alive = [], {}, []
+    for p in range(world):
+        wanted = req[p][owner_of(req[p], index.n_total, world) == rank]   # rows rank p needs from me, in p's order
+        if p == rank:
+            out[(own == rank).nonzero().flatten().to(dev)] = index.raws[(wanted - index.lo).to(dev)]
+            continue
+        if wanted.numel():
+            buf = index.raws[(wanted - index.lo).to(dev)].contiguous()
+            keep_alive.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, p))
+        n_from_p = int((own == p).sum())
+        if n_from_p:
+            recv_bufs[p] = torch.empty((n_from_p,) + tuple(index.raws.shape[1:]), dtype=index.raws.dtype, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv_bufs[p], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for p, buf in recv_bufs.items():
+        out[(own == p).nonzero().flatten().to(dev)] = buf
+    return out
+
+
+@torch.no_grad()
+def rerank_topk(backend, index: GalleryIndex, top_rows: torch.Tensor, ref_rows: torch.Tensor, input_ids: torch.Tensor,
+                attention_mask: torch.Tensor, T: int) -> torch.Tensor:
+    """Re-order the first T entries of each query's ranking `top_rows` [Q,K] (global rows, identical on all ranks) by
+    `inference_rerank` probability, descending, ties keeping the first-stage order — the reference's loop
+    (cirr_test_submission.py:87-112) on integer rows.  Queries are independent, so ranks split them contiguously
+    (SURVEY §8e); the raw embeds of each chunk's reference + candidate rows come from their owner ranks
+    (`fetch_raw_rows`), and one all-gather of the re-ordered rows makes the result identical everywhere."""
+    dist, rank, world = _dist()
+    top_rows = top_rows.cpu().to(torch.int64).clone()
+    ref_rows = ref_rows.cpu().to(torch.int64)
+    Q = top_rows.shape[0]
+    max_pairs = int(getattr(backend, "max_pairs", 0))
+    if max_pairs < T:
+        raise ValueError("rerank needs a model built with max_pairs >= top (Blip2QformerCirRerank)")
+    step = max(1, max_pairs // T)
+    qlo, qhi = shard_range(Q, rank, world)
+    longest = max(shard_range(Q, r, world)[1] - shard_range(Q, r, world)[0] for r in range(world))
+    dev = index.raws.device
+    for it in range((longest + step - 1) // step):                        # same trip count on every rank
+        s, e = min(qlo + it * step, qhi), min(qlo + (it + 1) * step, qhi)
+        cand = top_rows[s:e, :T]
+        need = torch.cat([ref_rows[s:e], cand.reshape(-1)])
+        uniq, inv = torch.unique(need, return_inverse=True)
+        table = fetch_raw_rows(index, uniq)
+        if e == s:
+            continue
+        R_ = e - s
+        p = backend.rerank_rows(table, inv[:R_].to(torch.int32).to(dev), inv[R_:].to(torch.int32).to(dev),
+                                input_ids[s:e], attention_mask[s:e], T).reshape(R_, T).cpu()
+        order = torch.argsort(1 - p, dim=-1, stable=True)
+        top_rows[s:e, :T] = torch.gather(cand, 1, order)
+    if world > 1:
+        mine = torch.full((longest, T), -1, dtype=torch.int64, device=dev)
+        mine[: qhi - qlo] = top_rows[qlo:qhi, :T].to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        for r in range(world):
+            lo_r, hi_r = shard_range(Q, r, world)
+            top_rows[lo_r:hi_r, :T] = parts[r][: hi_r - lo_r].cpu()
+    return top_rows
+
+
 def _tokenize(backend, captions):
     tok = backend.tokenizer(list(captions), padding="max_length", truncation=True, max_length=32, return_tensors="pt")
     return tok.input_ids, tok.attention_mask
@@ -266,8 +357,12 @@ def extract_index_blip_features(dataset, blip_model, save_memory=False):
 
 
 @torch.no_grad()
-def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, index_names, txt_processors):
-    """validate_blip.py:232-285 -> (gR@1, gR@2, gR@3, R@1, R@5, R@10, R@50) in percent."""
+def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, index_names, txt_processors,
+                             rerank_top: int = 0):
+    """validate_blip.py:232-285 -> (gR@1, gR@2, gR@3, R@1, R@5, R@10, R@50) in percent.
+    rerank_top = T > 0: validate_blip_rerank.py:166-239 — after the reference image is deleted from each ranking, its
+    first T entries are re-ordered by `inference_rerank` (the reference hard-codes T = 200) and the subset ranking
+    follows the re-ordered list."""
     index = index_features.index if isinstance(index_features, IndexFeatures) else as_index(index_features,
                                                                                             index_names)
     ref_names, tgt_names, caps, groups = [], [], [], []
@@ -287,16 +382,31 @@ def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, i
     B = max(1, blip_model.max_queries)
     for s in range(0, len(caps), B):
         sl = slice(s, s + B)
-        _, ix, sub = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=51, subset_rows=group_rows[sl])
+        _, ix, sub = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl],
+                                k=min(max(50, rerank_top) + 1, max(index.n_total, 51)), subset_rows=group_rows[sl])
         tops.append(ix.cpu())
         subs.append(sub.cpu())
-    return cirr_recalls_from_topk(torch.cat(tops), ref_rows, tgt_rows, group_rows, torch.cat(subs))
+    top_rows, sub_scores = torch.cat(tops).to(torch.int64), torch.cat(subs)
+    if rerank_top > 0:
+        Q, K1 = top_rows.shape
+        keep = top_rows != ref_rows[:, None]                      # :190-194 reference removed BEFORE the rerank
+        ranked = torch.stack([r[k_][: K1 - 1] for r, k_ in zip(top_rows, keep)])
+        T = min(rerank_top, ranked.shape[1], index.n_total - 1)
+        ranked = rerank_topk(blip_model, index, ranked, ref_rows, ids, mask, T)
+        # subset ranking follows the re-ordered list: members inside the first T take their new positions
+        hit = ranked[:, :T, None] == group_rows[:, None, :]       # [Q,T,6]
+        pos = torch.where(hit.any(dim=1), hit.float().argmax(dim=1), torch.full(group_rows.shape, -1))
+        sub_scores = torch.where(pos >= 0, 1e6 - pos.float(), sub_scores.float())
+        top_rows = ranked
+    return cirr_recalls_from_topk(top_rows, ref_rows, tgt_rows, group_rows, sub_scores)
 
 
 @torch.no_grad()
 def compute_fiq_val_metrics(relative_val_dataset, blip_model, index_features, index_names, txt_processors,
-                            save_memory=False):
-    """validate_blip.py:24-57 -> (R@10, R@50) in percent; captions joined as :180-183."""
+                            save_memory=False, rerank_top: int = 0):
+    """validate_blip.py:24-57 -> (R@10, R@50) in percent; captions joined as :180-183.
+    rerank_top = T > 0: validate_blip_rerank.py:24-96 — the first T entries of each ranking re-ordered by
+    `inference_rerank` before the labels are taken (the reference hard-codes T = 40)."""
     index = index_features.index if isinstance(index_features, IndexFeatures) else as_index(index_features,
                                                                                             index_names)
     ref_names, tgt_names, caps = [], [], []
@@ -315,9 +425,11 @@ def compute_fiq_val_metrics(relative_val_dataset, blip_model, index_features, in
     B = max(1, blip_model.max_queries)
     for s in range(0, len(caps), B):
         sl = slice(s, s + B)
-        _, ix, _ = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=50)
+        _, ix, _ = query_topk(blip_model, index, ref_rows[sl], ids[sl], mask[sl], k=max(50, rerank_top))
         tops.append(ix.cpu())
     top = torch.cat(tops)
+    if rerank_top > 0:
+        top = rerank_topk(blip_model, index, top, ref_rows, ids, mask, min(rerank_top, index.n_total))
     if not bool((top >= 0).all()) and index.n_total >= 50:
         raise AssertionError("top-k returned unfilled slots")
     return fiq_recalls_from_topk(top, tgt_rows)
@@ -389,20 +501,7 @@ def generate_cirr_test_dicts(relative_test_dataset, blip_model, index_features, 
         subs.append(sub.cpu())
     top_rows, sub_scores = torch.cat(tops), torch.cat(subs)
     if rerank:
-        if _dist()[2] > 1:
-            raise NotImplementedError("rerank over a sharded index: candidates' raw embeds live on their owner ranks")
-        T = min(top, top_rows.shape[1])
-        step = max(1, getattr(blip_model, "max_pairs", 0) // T)
-        if step < 1 or getattr(blip_model, "max_pairs", 0) < T:
-            raise ValueError("rerank needs a model built with max_pairs >= top (Blip2QformerCirRerank)")
-        dev = blip_model.device
-        for s in range(0, len(caps), step):
-            sl = slice(s, s + step)
-            cand = top_rows[sl, :T]
-            p = blip_model.rerank_rows(index.raws, (ref_rows[sl] - index.lo).to(dev), (cand - index.lo).reshape(-1).to(dev),
-                                       ids[sl], mask[sl], T).reshape(-1, T).cpu()
-            order = torch.argsort(1 - p, dim=-1, stable=True)
-            top_rows[sl, :T] = torch.gather(cand, 1, order)
+        top_rows = rerank_topk(blip_model, index, top_rows, ref_rows, ids, mask, min(top, top_rows.shape[1]))
     return cirr_submission_from_topk(top_rows, ref_rows, group_rows, sub_scores, index.names, pairs_id)
 
 

@@ -16,9 +16,18 @@ from sprc_b200 import retrieval as RT
 
 
 class OracleBackend:
-    """CPU stand-in with the five methods retrieval.query_topk uses."""
+    """CPU stand-in with the methods retrieval.query_topk / rerank_topk use."""
     device = torch.device("cpu")
     max_queries = 8
+    max_pairs = 8      # rerank chunk = max_pairs // T queries
+
+    def rerank_rows(self, table, ref_rows, cand_rows, input_ids, attention_mask, T):
+        """Stand-in pair score: a function of the VALUES of the reference / candidate raw embeds and the caption only
+        (never of where the rows sit in `table`), like inference_rerank."""
+        r = table[ref_rows.long()].float().mean(dim=1)                       # [R,Dv]
+        c = table[cand_rows.long()].float().mean(dim=1).view(r.shape[0], T, -1)
+        txt = (input_ids.float() * attention_mask.float()).sum(dim=1, keepdim=True) / 3e5
+        return torch.sigmoid(40 * (r[:, None] * c).sum(-1) + txt).reshape(-1)
 
     def __init__(self, proj):
         self.proj = proj  # fixed random projection playing the role of the Q-Former fusion
@@ -80,7 +89,13 @@ def _worker(rank, world, port, out_path):
         index = RT.GalleryIndex(feats=feats[lo:hi].contiguous(), raws=raws[lo:hi].contiguous(), names=names, lo=lo,
                                 hi=hi, n_total=N)
         sc, ix, sub = RT.query_topk(OracleBackend(proj), index, ref_rows, ids, mask, k=10, subset_rows=subset)
-        torch.save((sc, ix, sub), f"{out_path}.{rank}")
+        # rerank of the first 4 candidates: queries split over ranks, raw embeds fetched from their owner ranks
+        rr = RT.rerank_topk(OracleBackend(proj), index, ix.long(), ref_rows, ids, mask, 4)
+        need = torch.tensor([36, 0, 18, 19, 0, 5][: 3 + 3 * rank])           # ragged, repeated, cross-shard requests
+        got = RT.fetch_raw_rows(index, need)
+        assert torch.equal(got, raws[need]), "fetch_raw_rows must return the owners' rows in request order"
+        assert RT.fetch_raw_rows(index, torch.empty(0, dtype=torch.long)).shape[0] == 0
+        torch.save((sc, ix, sub, rr), f"{out_path}.{rank}")
     finally:
         dist.destroy_process_group()
 
@@ -98,7 +113,16 @@ def test_sharded_query_topk_equals_single_process(tmp_path):
     # single-process result == plain oracle ranking
     fusion = be.encode_query(raws, ids, mask, ref_rows=ref_rows)
     assert torch.equal(ix1.long(), R.ranking(R.similarity(fusion.float(), feats.float()), 10))
+    rr1 = RT.rerank_topk(be, index, ix1.long(), ref_rows, ids, mask, 4)
+    # brute force, the reference's loop (cirr_test_submission.py:87-112) one query at a time
+    for q in range(len(ref_rows)):
+        cand = ix1[q, :4].long()
+        table = torch.cat([raws[ref_rows[q:q + 1]], raws[cand]])
+        p = be.rerank_rows(table, torch.tensor([0]), torch.arange(1, 5), ids[q:q + 1], mask[q:q + 1], 4)
+        assert torch.equal(rr1[q, :4], cand[torch.argsort(1 - p, stable=True)]) and torch.equal(rr1[q, 4:], ix1[q, 4:].long())
+    assert not torch.equal(rr1, ix1.long())            # the stand-in scores do re-order something
     for r in range(2):
-        sc, ix, sub = torch.load(f"{out}.{r}")
+        sc, ix, sub, rr = torch.load(f"{out}.{r}")
         assert torch.equal(ix, ix1) and torch.equal(sc, sc1), f"rank {r}"
         assert torch.equal(sub, sub1)
+        assert torch.equal(rr, rr1), f"rank {r}: sharded rerank must equal the single-process rerank"

@@ -200,3 +200,78 @@ def test_cirr_submission_from_topk_matches_reference_semantics():
     sub = torch.gather(sim, 1, groups)
     got_g, got_s = R.cirr_submission_from_topk(top, ref, groups, sub, names, pairs)
     assert got_g == want_g and got_s == want_s
+
+
+def test_val_metrics_with_rerank_match_reference_semantics():
+    """compute_cirr_val_metrics / compute_fiq_val_metrics with rerank_top (validate_blip_rerank.py:24-96,166-239) on
+    integer rows against the reference's order of operations spelled out on full rankings: sort -> (CIRR: delete the
+    reference) -> re-order the first T by the pair score -> labels / subset mask -> recalls."""
+    import torch
+
+    from oracle import restatement as R
+    from sprc_b200 import retrieval as RT
+    from test_dist_cpu import OracleBackend
+
+    g = torch.Generator().manual_seed(5)
+    N, Q, Dv, T = 60, 12, 16, 7
+    feats = torch.nn.functional.normalize(torch.randn(N, 32, 256, generator=g), dim=-1).to(torch.bfloat16)
+    raws = torch.randn(N, 257, Dv, generator=g).to(torch.bfloat16)
+    be = OracleBackend(torch.randn(Dv, 256, generator=g))
+    be.max_pairs = 3 * T
+
+    class Tok:
+        def __call__(self, caps, **kw):
+            ids = torch.tensor([[101] + [1000 + (hash_(c) + j) % 20000 for j in range(30)] + [102] for c in caps])
+            return type("B", (), dict(input_ids=ids, attention_mask=torch.ones_like(ids)))()
+
+    hash_ = lambda c: sum(ord(ch) for ch in c)  # noqa: E731
+    be.tokenizer = Tok()
+    names = [f"n{i:03d}" for i in range(N)]
+    ref = torch.randint(0, N, (Q,), generator=g)
+    caps = [f"caption number {q}" for q in range(Q)]
+    ids, mask = RT._tokenize(be, caps)
+    fusion = be.encode_query(raws, ids, mask, ref_rows=ref)
+    sim = R.similarity(fusion.float(), feats.float())
+    order = R.ranking(sim)
+    tgt, _, members = R.plant_targets(order, ref, seed=3)
+    index = RT.GalleryIndex(feats=feats, raws=raws, names=names)
+    txt = {"eval": lambda c: c}
+
+    def pair_scores(q, cand):
+        table = torch.cat([raws[ref[q:q + 1]], raws[cand]])
+        return be.rerank_rows(table, torch.tensor([0]), torch.arange(1, len(cand) + 1), ids[q:q + 1], mask[q:q + 1],
+                              len(cand))
+
+    # --- CIRR: reference deleted first, then the first T re-ordered
+    full = []
+    for q in range(Q):
+        r = order[q][order[q] != ref[q]]
+        p = pair_scores(q, r[:T])
+        full.append(torch.cat([r[:T][torch.argsort(1 - p, stable=True)], r[T:]]))
+    full = torch.stack(full)
+    labels = full == tgt[:, None]
+    gm = (full[:, :, None] == members[:, None, :]).any(-1)
+    glabels = labels[gm].view(Q, -1)
+    want = tuple(100.0 * float(l[:, :k].sum()) / Q for l, k in
+                 [(glabels, 1), (glabels, 2), (glabels, 3), (labels, 1), (labels, 5), (labels, 10), (labels, 50)])
+    cirr_ds = [(names[int(ref[q])], names[int(tgt[q])], caps[q], [names[int(m)] for m in members[q]]) for q in range(Q)]
+    got = RT.compute_cirr_val_metrics(cirr_ds, be, index, names, txt, rerank_top=T)
+    assert got == pytest.approx(want)
+    plain = RT.compute_cirr_val_metrics(cirr_ds, be, index, names, txt)
+    assert plain == pytest.approx(R.cirr_recalls(order, ref, tgt, members))
+    assert plain != pytest.approx(want)                      # the rerank does change the recalls of this split
+
+    # --- FashionIQ: the reference stays in the ranking (validate_blip_rerank.py:40-71)
+    fiq_ds = [(names[int(ref[q])], names[int(tgt[q])], ("caption number", f"{q}")) for q in range(Q)]
+    # captions are joined by the driver (validate_blip.py:180-183): rebuild ids the same way for the expectation
+    caps_f = [f"{c0.strip('.?, ').capitalize()} and {c1.strip('.?, ')}" for _, _, (c0, c1) in fiq_ds]
+    ids, mask = RT._tokenize(be, caps_f)
+    fusion = be.encode_query(raws, ids, mask, ref_rows=ref)
+    order = R.ranking(R.similarity(fusion.float(), feats.float()))
+    full = []
+    for q in range(Q):
+        p = pair_scores(q, order[q][:T])
+        full.append(torch.cat([order[q][:T][torch.argsort(1 - p, stable=True)], order[q][T:]]))
+    fl = torch.stack(full) == tgt[:, None]
+    want_f = (100.0 * float(fl[:, :10].sum()) / Q, 100.0 * float(fl[:, :50].sum()) / Q)
+    assert RT.compute_fiq_val_metrics(fiq_ds, be, index, names, txt, rerank_top=T) == pytest.approx(want_f)
