@@ -84,8 +84,8 @@ def make_state_dict(vit: str, vit_depth: int | None = None, qf_layers: int = 12,
     initialisers (std 0.02, eva_vit.py:300-315 / Qformer.py:670-680) but LayerNorm affine parameters and
     biases are perturbed away from (1, 0) so that every parameter participates in the parity check.
     `gain` multiplies every Linear / conv weight matrix: at the initialisers' scale (gain 1) the features of all
-    images nearly coincide (similarities within 0.157..0.173); gain 4 spreads them over [-0.13, 0.13] like a trained
-    model's, which is what a Recall@K comparison needs (tests/test_parity_gpu.py recall parity)."""
+    images nearly coincide (similarities within 0.157..0.173); gain 2.5 spreads them over [-0.07, 0.13], closer to a
+    trained model's, which is what a Recall@K comparison needs (tests/test_parity_gpu.py recall parity)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for key, shape, kind in state_dict_spec(vit, vit_depth, qf_layers):

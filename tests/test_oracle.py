@@ -163,7 +163,7 @@ def test_cir_cat_rerank_restatement_matches_reference_golden():
 
 
 def test_spread_golden_restatement_and_planted_recalls():
-    """Recall-parity case (tests/golden/spread_L.pt, the reference's `inference` on a gain-4 checkpoint): the
+    """Recall-parity case (tests/golden/spread_L.pt, the reference's `inference` on a gain-2.5 checkpoint): the
     restatement reproduces the reference's similarity, and labels planted from that ranking give the oracle recalls
     the planting distribution promises (every recall > 0, exactly one positive per query)."""
     import os
@@ -179,9 +179,9 @@ def test_spread_golden_restatement_and_planted_recalls():
     with torch.no_grad():
         feats, raws = R.extract_target_features(sd, synth.make_images(c["n_images"]))
         sim = R.inference(sd, raws[g["ref_rows"]], feats, g["input_ids"], g["attention_mask"])
-    # fp32 summation-order noise (batch 64 here vs 16 in the reference run) through gain-4 weights: 2e-5 measured
+    # fp32 summation-order noise (batch 64 here vs 16 in the reference run) through the amplified weights
     assert (sim - g["sim"]).abs().max().item() < 5e-5
-    assert g["sim"].max() - g["sim"].min() > 0.2          # spread like a trained model's, not 0.157..0.173
+    assert g["sim"].max() - g["sim"].min() > 0.15         # spread over ~0.2, not the 0.016 of the gain-1 checkpoints
     order = R.ranking(g["sim"])
     tgt, ranks, members = R.plant_targets(order, g["ref_rows"])
     assert torch.equal(R.target_ranks(g["sim"], g["ref_rows"], tgt), ranks)
