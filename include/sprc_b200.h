@@ -165,6 +165,12 @@ int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, in
                  int ldc, int act, int impl, void* stream);
 /* out_f32 = LayerNorm(A W^T + bias + residual) * gamma + beta over rows of N = 768, out_ln16 = the same in the 16-bit
  * operand format (fused Q-Former post-LN sublayer, Qformer.py:291-295,373-381); residual may alias out_f32. */
+/* Same GEMM with TWO weight sets in one launch: rows [0, m_split) use (W, bias), rows [m_split, M) use (W2, bias2)
+ * (the fusion pass's query rows -> *_query FFN, text rows -> text FFN, Qformer.py:455-468).  Dense rows,
+ * m_split % 256 == 0. */
+int sprc_op_gemm2w(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
+                   const float* bias, const float* bias2, const float* residual, float* out_f32, void* out_bf16,
+                   int act, void* stream);
 int sprc_op_gemm_ln(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
                     int grp_stride, const float* bias, const float* residual, const float* gamma, const float* beta,
                     float eps, float* out_f32, void* out_ln16, int ldc, void* stream);

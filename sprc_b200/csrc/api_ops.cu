@@ -52,6 +52,28 @@ int sprc_op_gemm(const void* A, const void* W, int M, int N, int K, int lda, int
   return impl == 0 ? gemm_bf16_tcgen05(d, st) : gemm_bf16_simt(d, st);
 }
 
+int sprc_op_gemm2w(const void* A, const void* W, const void* W2, int M, int m_split, int N, int K, const float* bias,
+                   const float* bias2, const float* residual, float* out_f32, void* out_bf16, int act, void* stream) {
+  GemmDesc d;
+  d.A = static_cast<const bf16*>(A);
+  d.W = static_cast<const bf16*>(W);
+  d.W2 = static_cast<const bf16*>(W2);
+  d.M = M;
+  d.m_split = m_split;
+  d.N = N;
+  d.K = K;
+  d.lda = K;
+  d.ldw = K;
+  d.bias = bias;
+  d.bias2 = bias2;
+  d.residual = residual;
+  d.out_f32 = out_f32;
+  d.out_bf16 = static_cast<bf16*>(out_bf16);
+  d.ldc = N;
+  d.act = act;
+  return gemm_bf16_tcgen05(d, static_cast<cudaStream_t>(stream));
+}
+
 int sprc_op_gemm_ln(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int grp_rows, int grp_stride,
                     const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
                     float* out_f32, void* out_ln16, int ldc, void* stream) {

@@ -86,6 +86,12 @@ struct GemmDesc {
   // out + (n / 64) * (M * 64) + m * 64 + (n % 64)  (ldc ignored): every 64-column block - one attention head of a
   // packed K/V projection - becomes a contiguous [M, 64] matrix.  Dense rows only.
   int out_col_block = 0;
+  // Two weight sets in one launch: rows [0, m_split) use (W, bias), rows [m_split, M) use (W2, bias2) — the fusion
+  // pass's query rows -> *_query FFN, text rows -> text FFN (Qformer.py:455-468) as ONE grid instead of a full-size
+  // launch plus a half-empty one.  m_split must be a multiple of 256 (one pair tile); dense rows; same N, K, ldw.
+  const bf16* W2 = nullptr;
+  const float* bias2 = nullptr;
+  int m_split = 0;
 };
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)

@@ -443,6 +443,11 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
                "gemm: grp_rows=%d must divide 128 and M=%d", d.grp_rows, d.M);
   SPRC_REQUIRE(d.out_col_block == 0 || (d.out_col_block == 64 && d.out_bf16 && d.grp_rows == 0 && d.N % 64 == 0),
                "gemm: out_col_block needs 64, a 16-bit output, dense rows and N %% 64 == 0");
+  if (d.W2) {
+    SPRC_REQUIRE(d.m_split > 0 && d.m_split < d.M && d.m_split % 256 == 0 && d.grp_rows == 0 && !d.out_col_block,
+                 "gemm: two weight sets need dense rows and 0 < m_split (%d) < M (%d), m_split %% 256 == 0", d.m_split,
+                 d.M);
+  }
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
   // CTA pairs (256 x 256 tiles) whenever every pair gets work; the single-CTA kernels cover ragged N and small problems
   // (a ragged last N block - ViT-g's 1408 = 5.5 x 256, 4224 = 16.5 x 256 - runs as a half-empty 256-column tile: its
@@ -450,6 +455,22 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   // slower single-CTA kernel)
   if (gemm_2cta_enabled() && d.N >= 256 && tiles256 >= device_sm_count() && (!d.residual || d.residual == d.out_f32))
     return launch_gemm_2cta(d, st);
+  if (d.W2) {   // the single-CTA kernels take one weight set: two launches over the two row ranges
+    GemmDesc a = d, b = d;
+    a.W2 = b.W2 = nullptr;
+    a.bias2 = b.bias2 = nullptr;
+    a.m_split = b.m_split = 0;
+    a.M = d.m_split;
+    b.M = d.M - d.m_split;
+    b.A = d.A + (size_t)d.m_split * d.lda;
+    b.W = d.W2;
+    b.bias = d.bias2;
+    if (d.residual) b.residual = d.residual + (size_t)d.m_split * d.ldc;
+    if (d.out_f32) b.out_f32 = d.out_f32 + (size_t)d.m_split * d.ldc;
+    if (d.out_bf16) b.out_bf16 = d.out_bf16 + (size_t)d.m_split * d.ldc;
+    SPRC_TRY(gemm_bf16_tcgen05(a, st));
+    return gemm_bf16_tcgen05(b, st);
+  }
   if (d.N % 256 == 0 && tiles256 >= device_sm_count()) return launch_gemm<256, 4>(d, st);
   return launch_gemm<128, 6>(d, st);
 }

@@ -53,11 +53,14 @@ struct Gemm2Params {
   int accumulate;
   int rev;
   int col_block;   // 1: column-blocked 16-bit output (GemmDesc::out_col_block = 64)
+  int m_split;     // > 0: pair tiles whose first row is >= m_split read tmB2 / bias2 (GemmDesc::W2)
+  const float* bias2;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                              const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+                              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmC,
+                              const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -79,6 +82,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.m_split > 0) tma_prefetch_desc(&tmB2);
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's producer arms it; both CTAs' TMA bytes complete it
@@ -109,6 +113,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         const int tile = p.rev ? num_tiles - 1 - t : t;
         const int m0 = (tile / p.num_n_blocks) * (2 * BM) + static_cast<int>(crank) * BM;
         const int n0 = (tile % p.num_n_blocks) * BN + static_cast<int>(crank) * (BN / 2);
+        const CUtensorMap* tmW = (p.m_split > 0 && (tile / p.num_n_blocks) * (2 * BM) >= p.m_split) ? &tmB2 : &tmB;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
@@ -117,7 +122,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             tma_load_3d_2cta(&tmA, bar, sA + stage * A_BYTES, kb * BK, m0, 0, kEvictNormal);
           else
             tma_load_3d_2cta(&tmA, bar, sA + stage * A_BYTES, kb * BK, 0, m0 / p.grp_rows, kEvictNormal);
-          tma_load_2d_2cta(&tmB, bar, sB + stage * B_BYTES, kb * BK, n0, kEvictLast);
+          tma_load_2d_2cta(tmW, bar, sB + stage * B_BYTES, kb * BK, n0, kEvictLast);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -178,6 +183,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       const int tile = p.rev ? num_tiles - 1 - t : t;
       const int m0 = (tile / p.num_n_blocks) * (2 * BM) + static_cast<int>(crank) * BM + q * 32;
       const int n0 = (tile % p.num_n_blocks) * BN + cpart * (BN / 4);
+      const float* bias = (p.m_split > 0 && m0 >= p.m_split) ? p.bias2 : p.bias;
       int c1 = m0, c2 = 0;
       if (p.grp_rows > 0) {
         c2 = m0 >> p.grp_shift;
@@ -199,7 +205,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+              if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
               float v0 = __uint_as_float(o[4 * j]) + b.x, v1 = __uint_as_float(o[4 * j + 1]) + b.y;
               float v2 = __uint_as_float(o[4 * j + 2]) + b.z, v3 = __uint_as_float(o[4 * j + 3]) + b.w;
               if (p.act == ACT_GELU) {
@@ -219,7 +225,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+              if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
               float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
               float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
               if (p.act == ACT_GELU) {
@@ -286,7 +292,7 @@ bool gemm_2cta_enabled() {
 
 // Caller (gemm_bf16_tcgen05) has validated the descriptor (N % 32 == 0); the last N block may be ragged.
 int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmB2, tmC;
   {
     const bool f32 = d.out_f32 != nullptr;
     const void* out = f32 ? static_cast<const void*>(d.out_f32) : static_cast<const void*>(d.out_bf16);
@@ -310,6 +316,7 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
     SPRC_TRY(make_tmap_any(&tmA, d.A, 2, d.K, d.M, 1, d.lda, (uint64_t)d.M * d.lda, BK, BM, 1, 3, 128));
   }
   SPRC_TRY(make_tmap_any(&tmB, d.W, 2, d.K, d.N, 1, d.ldw, 0, BK, BN / 2, 1, 2, 128));
+  SPRC_TRY(make_tmap_any(&tmB2, d.W2 ? d.W2 : d.W, 2, d.K, d.N, 1, d.ldw, 0, BK, BN / 2, 1, 2, 128));
 
   Gemm2Params p;
   p.M = d.M;
@@ -329,6 +336,8 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   p.accumulate = d.residual ? 1 : 0;
   p.rev = next_sweep_reverse();
   p.col_block = d.out_col_block ? 1 : 0;
+  p.m_split = d.W2 ? d.m_split : 0;
+  p.bias2 = d.bias2;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -354,11 +363,11 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   prof_begin(st);
-  SPRC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel, tmA, tmB, tmC, p));
+  SPRC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel, tmA, tmB, tmB2, tmC, p));
   if (prof_enabled()) {
     char tag[56];
-    snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d 2cta", d.M, d.N, d.K, d.grp_rows, d.act, d.residual ? 1 : 0,
-             d.out_f32 ? 1 : 0);
+    snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d 2cta%s", d.M, d.N, d.K, d.grp_rows, d.act,
+             d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.W2 ? " w2" : "");
     prof_end(PROF_GEMM, 2.0 * d.M * (double)d.N * d.K,
              2.0 * ((double)d.M * d.K + (double)d.N * d.K) + (double)d.M * d.N * (d.out_f32 ? 4.0 : 2.0), st, tag);
   }

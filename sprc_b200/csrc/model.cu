@@ -418,6 +418,13 @@ static bool fused_ln_enabled() {
   }();
   return on;
 }
+static bool dual_ffn_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPRC_DUAL_FFN");   // SPRC_DUAL_FFN=0: separate launches for query-row and text-row FFNs
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 static int linear_ln(const bf16* A, int M, int K, int lda, const bf16* W, const float* bias, const float* gamma,
                      const float* beta, float eps, float* x, bf16* xb, int grp_rows, int grp_stride, cudaStream_t st) {
   if (!fused_ln_enabled()) {
@@ -719,13 +726,41 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
         SPRC_TRY(attention(c, st));
         SPRC_TRY(linear_ln(qctx, qrows, 768, 768, L.co_w, L.co_b, L.co_g, L.co_beta, 1e-12f, qh, qhb, 0, 0, st));
       }
-      SPRC_TRY(linear(qhb, qrows, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
-      SPRC_TRY(linear_ln(qffn, qrows, 3072, 3072, L.qo_w, L.qo_b, L.qo_g, L.qo_beta, 1e-12f, qh, qhb, 0, 0, st));
-      if (!last) {
-        SPRC_TRY(linear(qhb + to * 768, T8, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
-                        qffn + to * 3072, 3072, 0, 0, st));
-        SPRC_TRY(linear_ln(qffn + to * 3072, T8, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f,
-                           qh + to * 768, qhb + to * 768, 0, 0, st));
+      if (!last && T8 > 0 && qrows % 256 == 0 && dual_ffn_enabled() && !fused_ln_enabled()) {
+        // both FFNs as ONE grid per GEMM: query rows read the *_query weights, text rows the text weights
+        // (GemmDesc::W2) - a 27.9k-row launch instead of an 18.9k-row one plus a half-empty 9k-row one
+        GemmDesc d;
+        d.A = qhb;
+        d.M = rows_all;
+        d.m_split = qrows;
+        d.K = d.lda = d.ldw = 768;
+        d.N = d.ldc = 3072;
+        d.W = L.qi_w, d.bias = L.qi_b;
+        d.W2 = L.ti_w, d.bias2 = L.ti_b;
+        d.act = ACT_GELU;
+        d.out_bf16 = qffn;
+        SPRC_TRY(gemm_bf16_tcgen05(d, st));
+        GemmDesc e;
+        e.A = qffn;
+        e.M = rows_all;
+        e.m_split = qrows;
+        e.K = e.lda = e.ldw = 3072;
+        e.N = e.ldc = 768;
+        e.W = L.qo_w, e.bias = L.qo_b;
+        e.W2 = L.to_w, e.bias2 = L.to_b;
+        e.residual = e.out_f32 = qh;
+        SPRC_TRY(gemm_bf16_tcgen05(e, st));
+        SPRC_TRY(layernorm(qh, qrows, 768, L.qo_g, L.qo_beta, 1e-12f, 0, 0, qh, qhb, st));
+        SPRC_TRY(layernorm(qh + to * 768, T8, 768, L.to_g, L.to_beta, 1e-12f, 0, 0, qh + to * 768, qhb + to * 768, st));
+      } else {
+        SPRC_TRY(linear(qhb, qrows, 768, 768, L.qi_w, 3072, L.qi_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));
+        SPRC_TRY(linear_ln(qffn, qrows, 3072, 3072, L.qo_w, L.qo_b, L.qo_g, L.qo_beta, 1e-12f, qh, qhb, 0, 0, st));
+        if (!last) {
+          SPRC_TRY(linear(qhb + to * 768, T8, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr,
+                          qffn + to * 3072, 3072, 0, 0, st));
+          SPRC_TRY(linear_ln(qffn + to * 3072, T8, 3072, 3072, L.to_w, L.to_b, L.to_g, L.to_beta, 1e-12f,
+                             qh + to * 768, qhb + to * 768, 0, 0, st));
+        }
       }
     } else if (!last) {
       SPRC_TRY(linear(qhb, rows_all, 768, 768, L.ti_w, 3072, L.ti_b, ACT_GELU, nullptr, nullptr, qffn, 3072, 0, 0, st));

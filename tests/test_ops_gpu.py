@@ -173,3 +173,30 @@ def test_gemm_cta_pair_kernel_matches_torch(lib, M, N, K, act, res, f32, grp):
         mask = torch.ones(rows, dtype=torch.bool, device=dev)
         mask[pr] = False
         assert torch.equal(out[mask], out0[mask])
+
+
+@pytest.mark.parametrize("M,split,N,K,act,res", [(27912, 18944, 3072, 768, 1, False), (27912, 18944, 768, 3072, 0, True),
+                                                 (1000, 512, 768, 768, 0, True)])
+def test_gemm_two_weight_sets_match_torch(lib, M, split, N, K, act, res):
+    """GemmDesc::W2 (`sprc_op_gemm2w`): rows [0, split) use (W, bias), rows [split, M) use (W2, bias2) in ONE launch of
+    the CTA-pair kernel — the fusion pass's query-row / text-row FFNs (Qformer.py:455-468).  The last case is too
+    small for the pair kernel and takes the two-launch fallback: same result."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    W1 = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    W2 = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b1, b2 = torch.randn(N, device=dev, generator=g), torch.randn(N, device=dev, generator=g)
+    out = torch.randn(M, N, device=dev, generator=g) if res else torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    ref = torch.cat([A[:split].float() @ W1.float().T + b1, A[split:].float() @ W2.float().T + b2])
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if res:
+        ref = ref + out
+    L.check(so.sprc_op_gemm2w(L.ptr(A), L.ptr(W1), L.ptr(W2), M, split, N, K, L.ptr(b1), L.ptr(b2),
+                              L.ptr(out) if res else None, L.ptr(out) if res else None, None if res else L.ptr(out),
+                              act, L.cur_stream()))
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err < (1e-3 if res else 6e-2), err
