@@ -123,16 +123,27 @@ int sprc_gather_scores(sprc_handle* h, const void* queries_bf16, int Q, const vo
 int sprc_rerank(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
                 const int64_t* input_ids, const int64_t* attention_mask, int R, int T, float* p, void* stream);
 
-/* End-to-end query step with HOST buffers (what generate_*_val_predictions + compute_* do per batch,
- * validate_blip.py:386-408,253-255): H2D of ids/mask/ref_rows, fusion, scan, top-k, D2H of [Bq,k]. */
 /* sprc_rerank over the live text rows only (see sprc_encode_query_lens): text_len_host int32 [R] in HOST memory. */
 int sprc_rerank_lens(sprc_handle* h, const void* raws_bf16, const int32_t* ref_rows, const int32_t* cand_rows,
                      const int64_t* input_ids, const int32_t* text_len_host, int R, int T, float* p, void* stream);
 
+/* End-to-end query step with HOST buffers (what generate_*_val_predictions + compute_* do per batch,
+ * validate_blip.py:386-408,253-255): H2D of ids/mask/ref_rows, fusion, scan, top-k, D2H of [Bq,k]; returns when the
+ * results are in out_*_host (= sprc_query_topk_host_submit + sprc_query_topk_host_wait). */
 int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
                          const int32_t* ref_rows_host, const int64_t* input_ids_host,
                          const int64_t* attention_mask_host, int Bq, int k, float* out_score_host,
                          int32_t* out_idx_host, void* stream);
+/* The same step split in two so that a query loop can keep the GPU busy while the host prepares the next batch
+ * (the reference's loop, validate_blip.py:386-408, is strictly serial): _submit enqueues the H2D copies, the kernels
+ * and the D2H copies of ONE batch on `stream` and returns; _wait blocks until the OLDEST submitted, not yet awaited
+ * batch has its results in the out_*_host buffers it was submitted with.  Up to 4 batches may be in flight; the host
+ * buffers of a batch (pinned memory) must stay untouched until its _wait returns.  Same stream for every call. */
+int sprc_query_topk_host_submit(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
+                                const int32_t* ref_rows_host, const int64_t* input_ids_host,
+                                const int64_t* attention_mask_host, int Bq, int k, float* out_score_host,
+                                int32_t* out_idx_host, void* stream);
+int sprc_query_topk_host_wait(sprc_handle* h);
 
 /* Number of kernels this library has launched on behalf of the calling process (bench `gpu_launches`). */
 int64_t sprc_launch_count(void);

@@ -84,6 +84,12 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
          c_void_p],
     ),
+    "sprc_query_topk_host_submit": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+         c_void_p],
+    ),
+    "sprc_query_topk_host_wait": (c_int, [c_void_p]),
     "sprc_launch_count": (c_int64, []),
     "sprc_set_act_dtype": (c_int, [c_int]),
     "sprc_profile": (c_int, [c_int]),

@@ -12,6 +12,10 @@ using namespace sprc;
 
 struct sprc_handle {
   Model m;
+  // sprc_query_topk_host_submit / _wait: one event per batch in flight (ring, oldest first)
+  static constexpr int kInflight = 4;
+  cudaEvent_t done[kInflight] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned submitted = 0, awaited = 0;
 };
 
 namespace {
@@ -56,7 +60,12 @@ int sprc_create(const sprc_config* cfg, sprc_handle** out) {
   return 0;
 }
 
-void sprc_destroy(sprc_handle* h) { delete h; }
+void sprc_destroy(sprc_handle* h) {
+  if (!h) return;
+  for (cudaEvent_t ev : h->done)
+    if (ev) cudaEventDestroy(ev);
+  delete h;
+}
 
 int sprc_load_weights(sprc_handle* h, const sprc_tensor_desc* t, int n, int* n_missing) {
   if (!h || (!t && n > 0)) return set_error(-22, "sprc_load_weights: null argument");
@@ -166,12 +175,15 @@ int sprc_rerank_lens(sprc_handle* h, const void* raws_bf16, const int32_t* ref_r
                      p, S(stream));
 }
 
-int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
-                         const int32_t* ref_rows_host, const int64_t* ids_host, const int64_t* mask_host, int Bq,
-                         int k, float* out_score_host, int32_t* out_idx_host, void* stream) {
+int sprc_query_topk_host_submit(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
+                                const int32_t* ref_rows_host, const int64_t* ids_host, const int64_t* mask_host, int Bq,
+                                int k, float* out_score_host, int32_t* out_idx_host, void* stream) {
   if (!h || !raws_bf16 || !gallery_bf16 || !ref_rows_host || !ids_host || !mask_host || !out_score_host ||
       !out_idx_host)
     return set_error(-22, "sprc_query_topk_host: null argument");
+  if (h->submitted - h->awaited >= (unsigned)sprc_handle::kInflight)
+    return set_error(-11, "sprc_query_topk_host_submit: %d batches already in flight, call _wait first",
+                     sprc_handle::kInflight);
   Model& m = h->m;
   SPRC_REQUIRE(Bq > 0 && Bq <= m.max_queries, "sprc_query_topk_host: Bq=%d outside (0, %d]", Bq, m.max_queries);
   SPRC_REQUIRE(k > 0 && k <= 256, "sprc_query_topk_host: k=%d outside [1, 256]", k);
@@ -197,8 +209,29 @@ int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gall
   SPRC_TRY(sprc_sim_topk(h, m.d_fusion, Bq, gallery_bf16, N, 0, k, m.d_topk_score, m.d_topk_idx, nullptr, stream));
   SPRC_CUDA(cudaMemcpyAsync(out_score_host, m.d_topk_score, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
   SPRC_CUDA(cudaMemcpyAsync(out_idx_host, m.d_topk_idx, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
-  SPRC_CUDA(cudaStreamSynchronize(st));
+  cudaEvent_t& ev = h->done[h->submitted % sprc_handle::kInflight];
+  if (!ev) SPRC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  SPRC_CUDA(cudaEventRecord(ev, st));
+  ++h->submitted;
   return 0;
+}
+
+int sprc_query_topk_host_wait(sprc_handle* h) {
+  if (!h) return set_error(-22, "sprc_query_topk_host_wait: null handle");
+  if (h->awaited == h->submitted) return set_error(-22, "sprc_query_topk_host_wait: nothing in flight");
+  SPRC_CUDA(cudaEventSynchronize(h->done[h->awaited % sprc_handle::kInflight]));
+  ++h->awaited;
+  return 0;
+}
+
+int sprc_query_topk_host(sprc_handle* h, const void* raws_bf16, const void* gallery_bf16, int64_t N,
+                         const int32_t* ref_rows_host, const int64_t* ids_host, const int64_t* mask_host, int Bq,
+                         int k, float* out_score_host, int32_t* out_idx_host, void* stream) {
+  if (h && h->submitted != h->awaited)
+    return set_error(-11, "sprc_query_topk_host: %u submitted batches are still in flight", h->submitted - h->awaited);
+  SPRC_TRY(sprc_query_topk_host_submit(h, raws_bf16, gallery_bf16, N, ref_rows_host, ids_host, mask_host, Bq, k,
+                                       out_score_host, out_idx_host, stream));
+  return sprc_query_topk_host_wait(h);
 }
 
 }  // extern "C"

@@ -21,6 +21,10 @@ Model::~Model() {
   for (void* p : allocs) cudaFree(p);
   if (staging) cudaFree(staging);
   if (scan_ws) cudaFree(scan_ws);
+  for (int i = 0; i < kMetaRing; ++i) {
+    if (h_meta_pin[i]) cudaFreeHost(h_meta_pin[i]);
+    if (meta_ev[i]) cudaEventDestroy(meta_ev[i]);
+  }
 }
 
 int Model::alloc(void** p, size_t bytes) {
@@ -817,8 +821,17 @@ int Model::build_ragged_meta(const int32_t* lens_host, int repeat, int B, int* T
   }
   SPRC_REQUIRE(h_meta.size() <= meta_cap, "ragged row tables (%zu ints) exceed their buffer (%zu)", h_meta.size(),
                meta_cap);
-  // pageable source: the copy is staged before the call returns, so h_meta may be rebuilt for the next batch
-  SPRC_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), h_meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  // pinned ring slot -> d_meta, fully asynchronous: the host may prepare and enqueue up to kMetaRing batches ahead
+  const int slot = static_cast<int>(meta_seq++ % kMetaRing);
+  if (!h_meta_pin[slot]) {
+    SPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_meta_pin[slot]), meta_cap * sizeof(int32_t)));
+    SPRC_CUDA(cudaEventCreateWithFlags(&meta_ev[slot], cudaEventDisableTiming));
+  } else {
+    SPRC_CUDA(cudaEventSynchronize(meta_ev[slot]));   // the copy that last used this slot has executed
+  }
+  memcpy(h_meta_pin[slot], h_meta.data(), h_meta.size() * sizeof(int32_t));
+  SPRC_CUDA(cudaMemcpyAsync(d_meta, h_meta_pin[slot], h_meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  SPRC_CUDA(cudaEventRecord(meta_ev[slot], st));
   m_toff = d_meta;
   m_len = d_meta + B;
   m_cls = d_meta + 2 * B;

@@ -90,6 +90,12 @@ struct Model {
   int32_t* d_meta = nullptr;     // ragged layout tables (see build_ragged_meta)
   size_t meta_cap = 0;
   std::vector<int32_t> h_meta;
+  // pinned staging ring for the row tables: a pageable source would make cudaMemcpyAsync synchronise the stream
+  // first (the host could never run ahead of the GPU); a slot is reused only after its own copy has executed
+  static constexpr int kMetaRing = 8;
+  int32_t* h_meta_pin[kMetaRing] = {};
+  cudaEvent_t meta_ev[kMetaRing] = {};
+  unsigned meta_seq = 0;
   const int32_t *m_toff = nullptr, *m_len = nullptr, *m_slot = nullptr, *m_cls = nullptr;
   const void* m_pairs = nullptr;
   bf16* d_fusion = nullptr;

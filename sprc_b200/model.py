@@ -291,6 +291,19 @@ class Blip2QformerCirAlignPrompt:
                                                    L.ptr(mask_host), Bq, k, L.ptr(out_score_host),
                                                    L.ptr(out_idx_host), self._stream()))
 
+    def query_topk_host_submit(self, raws_bf16, gallery_bf16, ref_rows_host, ids_host, mask_host, k, out_score_host,
+                               out_idx_host):
+        """Enqueue one end-to-end step (H2D, fusion, scan, top-k, D2H) and return; `query_topk_host_wait` blocks until
+        the oldest submitted step has its results in the host buffers it was given (pinned, untouched until then)."""
+        with torch.cuda.device(self._device):
+            L.check(self._lib.sprc_query_topk_host_submit(self._h, L.ptr(raws_bf16), L.ptr(gallery_bf16),
+                                                          gallery_bf16.shape[0], L.ptr(ref_rows_host), L.ptr(ids_host),
+                                                          L.ptr(mask_host), ids_host.shape[0], k,
+                                                          L.ptr(out_score_host), L.ptr(out_idx_host), self._stream()))
+
+    def query_topk_host_wait(self):
+        L.check(self._lib.sprc_query_topk_host_wait(self._h))
+
     # ------------------------------------------------------------------ the reference's method surface
     def _tokenize(self, text):
         if isinstance(text, TokenBatch):
