@@ -880,6 +880,14 @@ int Model::encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_
   return 0;
 }
 
+static __global__ void rerank_pair_images_kernel(int32_t* ref_img, int32_t* cand_img, int pairs, int T, int r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pairs) {
+    ref_img[i] = i / T;    // reference image of the pair: KV rows [0, 257)
+    cand_img[i] = r + i;   // candidate image: KV rows [257, 514)
+  }
+}
+
 int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t* cand_rows, const int64_t* ids,
                   const int64_t* mask, const int32_t* text_len_host, int R, int T, float* p, cudaStream_t st) {
   SPRC_REQUIRE(max_pairs > 0, "rerank: handle was created with max_pairs = 0");
@@ -887,7 +895,6 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
   const size_t row_elems = (size_t)257 * Dv;
   int rc = max_pairs / T;  // queries per chunk
   if (rc < 1) rc = 1;
-  std::vector<int32_t> idx0, idx1;
   for (int r0 = 0; r0 < R; r0 += rc) {
     const int r = (R - r0) < rc ? (R - r0) : rc;
     const int pairs = r * T;
@@ -899,15 +906,11 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_TRY(gather_rows_bf16(raws_table, SPRC_BF16, cand_rows + (size_t)r0 * T, pairs, row_elems,
                               raws + (size_t)r * row_elems, st));
     SPRC_TRY(cross_kv(raws, n_img, false, st));
-    idx0.resize(pairs);
-    idx1.resize(pairs);
-    for (int i = 0; i < pairs; ++i) {
-      idx0[i] = i / T;   // reference image of the pair: KV rows [0, 257)
-      idx1[i] = r + i;   // candidate image: KV rows [257, 514)
-    }
-    SPRC_CUDA(cudaMemcpyAsync(d_rows, idx0.data(), pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    SPRC_CUDA(cudaMemcpyAsync(d_rows2, idx1.data(), pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    SPRC_CUDA(cudaStreamSynchronize(st));  // idx0/idx1 host vectors are reused by the next chunk
+    // pair i reads the K/V rows of image i / T (its reference) and of image r + i (its candidate): written on the
+    // device, so the call enqueues only (no host staging, no synchronisation)
+    rerank_pair_images_kernel<<<(pairs + 255) / 256, 256, 0, st>>>(d_rows, d_rows2, pairs, T, r);
+    count_launch();
+    SPRC_CUDA(cudaGetLastError());
     if (text_len_host && ragged_enabled()) {
       // ragged rows: every pair owns its 32 query rows + the live tokens of its caption (attention_qfr.cu)
       int T8 = 0;
