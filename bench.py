@@ -404,8 +404,8 @@ def main():
     gemm_tf = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
     scan_gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9 if scan["ms"] > 0 else 0.0
     scan_tf = scan["flops"] / (scan["ms"] / 1e3) / 1e12 if scan["ms"] > 0 else 0.0
-    roofline = {"kernel": "gemm_bf16_tcgen05_2cta_kernel (128 of 132 launches/step; gemm_bf16_tcgen05_kernel for the "
-                          "four 592-row tail GEMMs)", "bound": "tensor", "achieved": gemm_tf,
+    roofline = {"kernel": "gemm_bf16_tcgen05_2cta_kernel (every GEMM of the step but the four 592-row tail GEMMs, which "
+                          "run the single-CTA gemm_bf16_tcgen05_kernel)", "bound": "tensor", "achieved": gemm_tf,
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
                 "traffic": ncu_traffic().get("gemm_bytes_per_launch"),
                 "traffic_source": ncu_traffic().get("gemm_source"),
