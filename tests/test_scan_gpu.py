@@ -155,7 +155,8 @@ def test_full_size_properties_gallery_50k():
 @pytest.mark.parametrize("cfg,Q,N,k,P", [("C2 ViT-L CIRR shape", 2200, 21000, 51, 1),
                                          ("C3 ViT-g FashionIQ shape", 6000, 75000, 50, 1),
                                          ("C4 gallery 200k over 8 row shards", 1184, 200000, 50, 8),
-                                         ("bench.py --gpus 8 shape: 8 x 592 queries, 50k rows in 8 shards", 4736, 50000, 50, 8)])
+                                         ("bench.py --gpus 8 shape: 8 x 592 queries, 50k rows in 8 shards", 4736, 50000, 50, 8),
+                                         ("bench.py --gpus 8 default: 8 x 2368 queries, 50k rows in 8 shards", 18944, 50000, 50, 8)])
 def test_baseline_config_shapes_bit_exact(cfg, Q, N, k, P):
     """BASELINE.json configs[1..3] at their FULL sizes: dyadic-grid features make every dot product exact in fp32,
     so the whole top-k (scores and rows, ties -> lower row) must equal the oracle's `similarity` + stable argsort
