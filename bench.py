@@ -421,6 +421,9 @@ def main():
                      "share_of_step": scan["ms"] / prof_total if prof_total else None,
                      "note": "gallery bytes N*32*256*2 per launch; queries/launch = %d" % (world * Bq)}
     # ---- scan in its HBM-bound regime (one 128-query tile per gallery pass: every gallery byte is read once) ----
+    # a kernel timed ALONE (MEASURED_PEAKS' burst regime): let the power state of the long loops above settle first
+    torch.cuda.synchronize()
+    time.sleep(1.0)
     q128 = torch.nn.functional.normalize(torch.randn(128, 256, device=dev), dim=-1).to(adt)
     sc128 = torch.empty(128, k, device=dev)
     ix128 = torch.empty(128, k, device=dev, dtype=torch.int32)
