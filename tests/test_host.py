@@ -275,3 +275,33 @@ def test_val_metrics_with_rerank_match_reference_semantics():
     fl = torch.stack(full) == tgt[:, None]
     want_f = (100.0 * float(fl[:, :10].sum()) / Q, 100.0 * float(fl[:, :50].sum()) / Q)
     assert RT.compute_fiq_val_metrics(fiq_ds, be, index, names, txt, rerank_top=T) == pytest.approx(want_f)
+
+
+def test_c_abi_argument_validation_without_a_gpu():
+    """Error contract of include/sprc_b200.h: a null handle / pointer is refused with a negative
+    errno-style code (-22) and a message through sprc_last_error() BEFORE any CUDA call, so this runs without a GPU;
+    nothing computes here."""
+    lib = L.load()
+    z = ctypes.c_void_p(0)
+
+    def refused(rc, word):
+        msg = lib.sprc_last_error().decode()
+        assert rc == -22 and word in msg, (rc, msg)
+
+    refused(lib.sprc_create(None, None), "null")
+    refused(lib.sprc_load_weights(z, None, 1, None), "null")
+    refused(lib.sprc_encode_gallery(z, z, 1, z, z, z, z, z), "null")
+    refused(lib.sprc_encode_query(z, z, 0, z, z, z, 1, z, z, z), "null")
+    refused(lib.sprc_encode_query_lens(z, z, 0, z, z, z, 1, z, z, z), "null")
+    refused(lib.sprc_sim_topk(z, z, 1, z, 1, 0, 1, z, z, z, z), "null")
+    refused(lib.sprc_topk_merge(z, z, z, 1, 1, 1, z, z, z), "null")
+    refused(lib.sprc_gather_scores(z, z, 1, z, 1, z, 1, z, z), "null")
+    refused(lib.sprc_rerank(z, z, z, z, z, z, 1, 1, z, z), "null")
+    refused(lib.sprc_rerank_lens(z, z, z, z, z, z, 1, 1, z, z), "null")
+    refused(lib.sprc_query_topk_host(z, z, z, 1, z, z, z, 1, 1, z, z, z), "null")
+    refused(lib.sprc_query_topk_host_submit(z, z, z, 1, z, z, z, 1, 1, z, z, z), "null")
+    refused(lib.sprc_query_topk_host_wait(z), "null")
+    refused(lib.sprc_profile_dump(None), "null")
+    refused(lib.sprc_set_act_dtype(7), "0 (bf16) or 1 (fp16)")
+    lib.sprc_destroy(z)        # destroying a null handle is a no-op, like free(NULL)
+    assert lib.sprc_launch_count() >= 0
