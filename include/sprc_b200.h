@@ -195,6 +195,36 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
                       int Lk, int ldq, int ldk, int ldv, int ldo, int q_batch_rows, int kv_batch_rows,
                       const float* key_mask, float scale, void* stream);
 
+/* LayerNorm folded into the neighbouring GEMMs (opt-in schedule SPRC_LN_FOLD=1, csrc/ln_fold.cu, csrc/common.h
+ * GemmFold; Qformer.py:291-295,373-381 post-LN sublayers).  Row statistics: 12 (mean, M2) float pairs per row of 768.
+ * sprc_op_fold_weight: Wf = round16(W diag(gamma)), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n].
+ * sprc_op_gemm_fold, consumer (fold->st_in set): out_bf16 = act(rstd (A Wf^T - mean c) + d), bias = d;
+ * producer (fold->st_out set, N = 768): out_f32 = A W^T + bias + LN(resid) (resid as is when st_res is null),
+ * fold->out16 = its raw 16-bit copy, fold->st_out = its row statistics.  Rows >= split take the *2 members. */
+typedef struct sprc_gemm_fold {
+  int32_t split;
+  float eps;
+  const void* st_in;
+  const void* st_in2;
+  const float* c;
+  const float* c2;
+  const float* resid;
+  const void* st_res;
+  const void* st_res2;
+  const float* res_g;
+  const float* res_b;
+  const float* res_g2;
+  const float* res_b2;
+  void* st_out;
+  void* st_out2;
+  void* out16;
+} sprc_gemm_fold;
+int sprc_op_fold_weight(const void* W_bf16, const float* gamma, const float* beta, const float* bias, int N, int K,
+                        void* Wf_bf16, float* c, float* d, void* stream);
+int sprc_op_gemm_fold(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
+                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
+                      const sprc_gemm_fold* fold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,242 @@
+// LayerNorm folded into the neighbouring GEMMs of the Q-Former's post-LN sublayers (opt-in: SPRC_LN_FOLD=1).
+//
+// Reference arithmetic (lavis/models/blip2_models/Qformer.py:291-295 BertSelfOutput, :373-381 BertOutput):
+//     y = LayerNorm(dense(a) + x) ;  the next sublayer reads y twice: as the A operand of its GEMMs and as its residual.
+// Default schedule: GEMM (TMA reduce-add into the fp32 stream) + a LayerNorm kernel = 18 B of HBM traffic per element
+// and sublayer, 12 % of the 2368-query step (DESIGN.md §3, §8 "Next" item 1).  Folded schedule (GemmFold, common.h):
+//     producer GEMM   s' = acc + b + LN(s)        writes s' fp32 + raw 16-bit copy + 12 (mean, M2) partials per row
+//     consumer GEMM   act(rstd (s16 (W diag(g))^T - mean c) + d),  c = rowsum(W diag(g)),  d = W beta + b
+// i.e. LN(s) W^T + b with the per-row scalars pulled out of the contraction: 10 B per element, no LayerNorm launch.
+// The folded weights W diag(g) are derived here from the loaded state dict; c is summed over the ROUNDED 16-bit folded
+// weight, so `acc - mean c` is exactly sum_k (s16_k - mean) Wf_nk in the tensor core's own operands.
+//
+// Scope: the ragged composed-query passes (Model::qformer_layers_ragged) for layers 0 .. L-2; the last layer runs the
+// default schedule on a materialised stream (its row-restricted outputs and the [CLS] gather stay as they are).
+// Status: compiled and algebra-checked on CPU (oracle/ln_fold.py, tests/test_ln_fold.py); NOT yet validated on a GPU
+// (tests/test_ln_fold_gpu.py is gated behind SPRC_TEST_LN_FOLD=1) - off by default for that reason.
+#include <stdlib.h>
+
+#include "model.h"
+#include "ptx.cuh"
+
+namespace sprc {
+
+bool ln_fold_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPRC_LN_FOLD");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+// One warp per output row n:  Wf[n,k] = round16(W[n,k] * gamma[k]);  c[n] = sum_k Wf[n,k];
+// d[n] = sum_k W[n,k] * beta[k] + bias[n].
+__global__ void __launch_bounds__(256)
+fold_weight_kernel(const unsigned short* __restrict__ W, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                   unsigned short* __restrict__ Wf, float* __restrict__ c, float* __restrict__ d, int fp16) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float cs = 0.f, ds = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = from_act(W[(size_t)n * K + k], fp16);
+    const unsigned short wf = to_act(w * gamma[k], fp16);
+    Wf[(size_t)n * K + k] = wf;
+    cs += from_act(wf, fp16);
+    ds += w * beta[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+  }
+  if (lane == 0) {
+    c[n] = cs;
+    d[n] = ds + (bias ? bias[n] : 0.f);
+  }
+}
+
+int fold_weight(const bf16* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf,
+                float* c, float* d, cudaStream_t st) {
+  SPRC_REQUIRE(W && gamma && beta && Wf && c && d && N > 0 && K > 0, "fold_weight: bad arguments");
+  fold_weight_kernel<<<(N + 7) / 8, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(W), gamma, beta, bias, N, K,
+                                                  reinterpret_cast<unsigned short*>(Wf), c, d, act_fp16());
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int plain_linear(const bf16* A, int M, int K, const bf16* W, int N, const float* bias, int act, bf16* out,
+                        cudaStream_t st) {
+  GemmDesc d;
+  d.A = A;
+  d.W = W;
+  d.M = M;
+  d.N = d.ldc = N;
+  d.K = d.lda = d.ldw = K;
+  d.bias = bias;
+  d.act = act;
+  d.out_bf16 = out;
+  return gemm_bf16_tcgen05(d, st);
+}
+
+int Model::fold_one(FoldedLinear* f, const bf16* W, const float* bias, const float* gamma, const float* beta, int N,
+                    cudaStream_t st) {
+  if (!f->w) {
+    SPRC_TRY(alloc_t(&f->w, (size_t)N * 768));
+    SPRC_TRY(alloc_t(&f->c, N));
+    SPRC_TRY(alloc_t(&f->d, N));
+  }
+  return fold_weight(W, gamma, beta, bias, N, 768, f->w, f->c, f->d, st);
+}
+
+// Folded weights of every GEMM that reads a LayerNorm output in layers 0 .. L-2 of the ragged passes (re-derived after
+// every sprc_load_weights), plus the two statistics buffers.
+int Model::prepare_fold(cudaStream_t st) {
+  if (fold_ready) return 0;
+  if (!fold_st[0]) {
+    SPRC_TRY(alloc_t(&fold_st[0], (size_t)qf_rows * kFoldParts));
+    SPRC_TRY(alloc_t(&fold_st[1], (size_t)qf_rows * kFoldParts));
+  }
+  folds.resize(qf_layers);
+  for (int l = 0; l < qf_layers; ++l) {
+    const QfLayer& L = layers[l];
+    QfFold& F = folds[l];
+    if (l > 0) {   // self-attention Q/K/V read the previous layer's FFN LayerNorms (output_query / output)
+      const QfLayer& P = layers[l - 1];
+      SPRC_TRY(fold_one(&F.qkv_q, L.qkv_w, L.qkv_b, P.qo_g, P.qo_beta, 2304, st));
+      SPRC_TRY(fold_one(&F.qkv_t, L.qkv_w, L.qkv_b, P.to_g, P.to_beta, 2304, st));
+    }
+    if (L.has_cross) {
+      SPRC_TRY(fold_one(&F.cq, L.cq_w, L.cq_b, L.so_g, L.so_beta, 768, st));
+      SPRC_TRY(fold_one(&F.qi, L.qi_w, L.qi_b, L.co_g, L.co_beta, 3072, st));
+    } else {
+      SPRC_TRY(fold_one(&F.qi, L.qi_w, L.qi_b, L.so_g, L.so_beta, 3072, st));
+    }
+    SPRC_TRY(fold_one(&F.ti, L.ti_w, L.ti_b, L.so_g, L.so_beta, 3072, st));
+  }
+  fold_ready = true;
+  return 0;
+}
+
+bool Model::fold_usable(int B, int T8, const int32_t* kv_idx0) const {
+  return ln_fold_enabled() && !kv_idx0 && qf_layers >= 2 && T8 > 0 && (32 * B) % 256 == 0;
+}
+
+// Layers 0 .. L-2 of one ragged Q-Former pass in the folded schedule, then the materialising LayerNorms; the caller
+// (qformer_layers_ragged) runs the last layer in the default schedule.  Row ranges: query rows [0, 32 B) and text rows
+// [32 B, 32 B + T8) owe DIFFERENT LayerNorms after the fusion pass's FFNs and may sit in different statistics buffers
+// (the cross-attention sublayer touches the query rows only), hence the per-range state (cur*, g*, b*).
+int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cudaStream_t st) {
+  SPRC_TRY(prepare_fold(st));
+  const int qrows = 32 * B, rows_all = qrows + T8;
+  SPRC_REQUIRE(rows_all <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows_all, qf_rows);
+  const size_t to = (size_t)qrows;
+  bool raw = false;        // the stream (qh fp32, qhb 16-bit) holds pre-LN sums that still owe a LayerNorm
+  int curQ = 0, curT = 0;  // statistics buffer of the query rows / text rows
+  const float *gQ = nullptr, *bQ = nullptr, *gT = nullptr, *bT = nullptr;
+
+  auto producer = [&](const bf16* A, int M, int K, const bf16* W, const float* b, const bf16* W2,
+                      const float* b2) -> int {
+    GemmFold f;
+    f.split = M > qrows ? qrows : 0;
+    f.resid = qh;
+    f.out16 = qhb;
+    if (raw) {
+      f.st_res = fold_st[curQ], f.res_g = gQ, f.res_b = bQ;
+      f.st_res2 = fold_st[curT], f.res_g2 = gT, f.res_b2 = bT;
+    }
+    f.st_out = fold_st[curQ ^ 1];
+    f.st_out2 = fold_st[curT ^ 1];
+    GemmDesc d;
+    d.A = A;
+    d.M = M;
+    d.K = d.lda = d.ldw = K;
+    d.N = d.ldc = 768;
+    d.W = W, d.bias = b;
+    if (W2) d.W2 = W2, d.bias2 = b2, d.m_split = qrows;
+    d.out_f32 = qh;
+    d.fold = &f;
+    SPRC_TRY(gemm_bf16_tcgen05(d, st));
+    curQ ^= 1;
+    if (M > qrows) curT ^= 1;
+    raw = true;
+    return 0;
+  };
+  auto consumer = [&](int M, const FoldedLinear& w, const FoldedLinear* w2, int N, int act, bf16* out) -> int {
+    GemmFold f;
+    f.split = M > qrows ? qrows : 0;
+    f.st_in = fold_st[curQ];
+    f.st_in2 = fold_st[curT];
+    f.c = w.c;
+    GemmDesc d;
+    d.A = qhb;
+    d.M = M;
+    d.K = d.lda = d.ldw = 768;
+    d.N = d.ldc = N;
+    d.W = w.w, d.bias = w.d;
+    if (w2) d.W2 = w2->w, d.bias2 = w2->d, d.m_split = qrows, f.c2 = w2->c;
+    d.act = act;
+    d.out_bf16 = out;
+    d.fold = &f;
+    return gemm_bf16_tcgen05(d, st);
+  };
+
+  for (int l = 0; l < qf_layers - 1; ++l) {
+    const QfLayer& L = layers[l];
+    const QfFold& F = folds[l];
+    // ---- self-attention over all rows (Qformer.py:175-281) ----
+    if (!raw)
+      SPRC_TRY(plain_linear(qhb, rows_all, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, qqkv, st));
+    else if (with_enc)
+      SPRC_TRY(consumer(rows_all, F.qkv_q, &F.qkv_t, 2304, ACT_NONE, qqkv));
+    else
+      SPRC_TRY(consumer(rows_all, F.qkv_t, nullptr, 2304, ACT_NONE, qqkv));
+    SPRC_TRY(attention_qf_ragged(qqkv, 2304, qctx, 768, B, rows_all, static_cast<const int4*>(m_pairs), 0.125f, st));
+    SPRC_TRY(producer(qctx, rows_all, 768, L.so_w, L.so_b, nullptr, nullptr));
+    gQ = gT = L.so_g, bQ = bT = L.so_beta;
+    if (with_enc) {
+      if (L.has_cross) {   // query rows only (Qformer.py:436-452)
+        const int ci = l / 2;
+        const long long kv_rows = (long long)B * 257;
+        SPRC_TRY(consumer(qrows, F.cq, nullptr, 768, ACT_NONE, qcq));
+        AttnDesc c;
+        c.Q = qcq;
+        c.K = kv + (size_t)ci * 24 * kv_rows * 64;
+        c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
+        c.kv_head_stride = kv_rows * 64;
+        c.ldk = c.ldv = 64;
+        c.O = qctx;
+        c.B = B;
+        c.H = 12;
+        c.dh = 64;
+        c.Lq = 32;
+        c.Lk = Lk;
+        c.ldq = 768;
+        c.ldo = 768;
+        c.q_batch_rows = 32;
+        c.kv_batch_rows = 257;
+        c.scale = 0.125f;
+        c.Lk1 = 257;
+        SPRC_TRY(attention(c, st));
+        SPRC_TRY(producer(qctx, qrows, 768, L.co_w, L.co_b, nullptr, nullptr));
+        gQ = L.co_g, bQ = L.co_beta;
+      }
+      // query rows -> *_query FFN, text rows -> text FFN (Qformer.py:455-468), one launch per GEMM
+      SPRC_TRY(consumer(rows_all, F.qi, &F.ti, 3072, ACT_GELU, qffn));
+      SPRC_TRY(producer(qffn, rows_all, 3072, L.qo_w, L.qo_b, L.to_w, L.to_b));
+      gQ = L.qo_g, bQ = L.qo_beta, gT = L.to_g, bT = L.to_beta;
+    } else {   // no encoder states: every row takes the text FFN (Qformer.py:434-435, 469-475)
+      SPRC_TRY(consumer(rows_all, F.ti, nullptr, 3072, ACT_GELU, qffn));
+      SPRC_TRY(producer(qffn, rows_all, 3072, L.to_w, L.to_b, nullptr, nullptr));
+      gQ = gT = L.to_g, bQ = bT = L.to_beta;
+    }
+  }
+  // materialise LN(s) for the last layer (fp32 stream + 16-bit operand copy)
+  SPRC_TRY(layernorm(qh, qrows, 768, gQ, bQ, 1e-12f, 0, 0, qh, qhb, st));
+  SPRC_TRY(layernorm(qh + to * 768, T8, 768, gT, bT, 1e-12f, 0, 0, qh + to * 768, qhb + to * 768, st));
+  return 0;
+}
+
+}  // namespace sprc

@@ -374,6 +374,7 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
   SPRC_CUDA(cudaGetLastError());
   SPRC_CUDA(cudaDeviceSynchronize());
   s.loaded = true;
+  fold_ready = false;   // folded weights (ln_fold.cu) are derived from the loaded ones
   return 0;
 }
 
@@ -683,7 +684,12 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
   float* x_cls = qt;
   bf16* ctx_cls = qcq;
   bf16* x_cls_b = qcq + (size_t)B * 768;
-  for (int l = 0; l < qf_layers; ++l) {
+  int first_layer = 0;
+  if (fold_usable(B, T8, kv_idx0)) {   // SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu)
+    SPRC_TRY(qformer_layers_ragged_fold(B, T8, with_enc, Lk, st));
+    first_layer = qf_layers - 1;
+  }
+  for (int l = first_layer; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     const bool last = l == qf_layers - 1;
     SPRC_TRY(linear(qhb, rows_all, 768, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, nullptr, nullptr, qqkv, 2304, 0, 0, st));

@@ -1,0 +1,188 @@
+"""GPU checks of the LayerNorm-folded schedule (csrc/ln_fold.cu, csrc/gemm2.cu FOLD = 1; opt-in SPRC_LN_FOLD=1).
+
+GATED: the fold was written after the round's GPU budget was spent, so these tests have not run on a B200 yet; they
+run only with SPRC_TEST_LN_FOLD=1 and are the first thing to run in the next round (the default path and the default
+`pytest -m gpu` run do not touch the fold).  Reference semantics: Qformer.py:291-295, 373-381 (post-LN sublayers),
+emulated on the CPU in oracle/ln_fold.py and checked against the fp32 restatement in tests/test_ln_fold.py.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SPRC_TEST_LN_FOLD") != "1",
+                                 reason="LayerNorm fold not validated on a GPU yet: set SPRC_TEST_LN_FOLD=1")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sprc_b200 import _lib as L
+
+    return L, L.load()
+
+
+def _fold_struct(L, **kw):
+    f = L.SprcGemmFold()
+    f.split, f.eps = kw.pop("split", 0), kw.pop("eps", 1e-12)
+    keep = []
+    for k, t in kw.items():
+        if t is not None:
+            setattr(f, k, t.data_ptr())
+            keep.append(t)
+    return f, keep
+
+
+def test_fold_weight_kernel(lib):
+    from oracle import ln_fold as LF
+
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    W = (torch.randn(3072, 768, device=dev, generator=g) * 0.03).bfloat16()
+    bias = torch.randn(3072, device=dev, generator=g)
+    gamma, beta = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
+    Wf = torch.empty_like(W)
+    c, d = torch.empty(3072, device=dev), torch.empty(3072, device=dev)
+    L.check(so.sprc_op_fold_weight(L.ptr(W), L.ptr(gamma), L.ptr(beta), L.ptr(bias), 3072, 768, L.ptr(Wf), L.ptr(c),
+                                   L.ptr(d), L.cur_stream()))
+    torch.cuda.synchronize()
+    wf, cc, dd = LF.fold_weight(W.float().cpu(), bias.cpu(), gamma.cpu(), beta.cpu(), rnd=True)
+    assert torch.equal(Wf.float().cpu(), wf)
+    assert (c.cpu() - cc).abs().max() < 1e-4 and (d.cpu() - dd).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("M,split,K,dual,normed", [(512, 0, 768, False, False), (1000, 0, 768, False, True),
+                                                  (27912, 18944, 768, False, True), (27912, 18944, 3072, True, True)])
+def test_producer_gemm(lib, M, split, K, dual, normed):
+    """s' = A W^T + b + LN(resid) in place, raw 16-bit copy, 12 row-statistics partials."""
+    from oracle import ln_fold as LF
+
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    W1 = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    W2 = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b1, b2 = torch.randn(768, device=dev, generator=g), torch.randn(768, device=dev, generator=g)
+    x = torch.randn(M, 768, device=dev, generator=g) * 1.7 + torch.randn(M, 1, device=dev, generator=g)
+    g1, be1 = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
+    g2, be2 = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
+    st_res = LF.row_stats_partials(x.cpu()).to(dev).contiguous()
+    hi = torch.arange(M, device=dev) >= split if split else torch.zeros(M, dtype=torch.bool, device=dev)
+    r = x
+    if normed:
+        n1 = torch.nn.functional.layer_norm(x, (768,), g1, be1, 1e-12)
+        n2 = torch.nn.functional.layer_norm(x, (768,), g2, be2, 1e-12)
+        r = torch.where(hi[:, None], n2, n1)
+    y1 = A.float() @ W1.float().T + b1
+    y2 = A.float() @ W2.float().T + b2 if dual else y1
+    ref = torch.where(hi[:, None], y2, y1) + r
+    out16 = torch.zeros(M, 768, device=dev, dtype=torch.bfloat16)
+    st_a = torch.full((M, 12, 2), float("nan"), device=dev)
+    st_b = torch.full((M, 12, 2), float("nan"), device=dev)
+    f, keep = _fold_struct(L, split=split, resid=x, out16=out16, st_out=st_a, st_out2=st_b if split else None,
+                           st_res=st_res if normed else None, st_res2=st_res if (normed and split) else None,
+                           res_g=g1 if normed else None, res_b=be1 if normed else None,
+                           res_g2=g2 if (normed and split) else None, res_b2=be2 if (normed and split) else None)
+    L.check(so.sprc_op_gemm_fold(L.ptr(A), L.ptr(W1), L.ptr(W2) if dual else None, M, split if dual else 0, 768, K,
+                                 L.ptr(b1), L.ptr(b2) if dual else None, 0, L.ptr(x), None, f, L.cur_stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    assert (x - ref).abs().max().item() < 2e-3
+    assert (out16.float() - ref).abs().max().item() < 6e-2
+    st = torch.where(hi[:, None, None], st_b, st_a) if split else st_a
+    m, rs = LF.merge_stats(st.cpu(), 1e-12)
+    assert (m - ref.mean(-1).cpu()).abs().max() < 1e-4
+    assert ((rs - torch.rsqrt(ref.var(-1, unbiased=False) + 1e-12).cpu()) / rs).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("M,split,N,act,dual", [(512, 0, 768, 0, False), (1000, 0, 2304, 0, False),
+                                                (27912, 18944, 3072, 1, True), (27912, 18944, 2304, 0, True)])
+def test_consumer_gemm(lib, M, split, N, act, dual):
+    """act(LN(s) W^T + b) from the raw 16-bit rows, the folded weight and the row statistics."""
+    from oracle import ln_fold as LF
+
+    L, so = lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    s = torch.randn(M, 768, device=dev, generator=g) * 1.7 + 0.4 * torch.randn(M, 1, device=dev, generator=g)
+    s16 = s.bfloat16()
+    st = LF.row_stats_partials(s.cpu()).to(dev).contiguous()
+    outs, refs, keepw = [], [], []
+    for i in range(2 if dual else 1):
+        W = (torch.randn(N, 768, device=dev, generator=g) * 768 ** -0.5).bfloat16()
+        b = torch.randn(N, device=dev, generator=g)
+        ga, be = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
+        Wf, c, d = torch.empty_like(W), torch.empty(N, device=dev), torch.empty(N, device=dev)
+        L.check(so.sprc_op_fold_weight(L.ptr(W), L.ptr(ga), L.ptr(be), L.ptr(b), N, 768, L.ptr(Wf), L.ptr(c), L.ptr(d),
+                                       L.cur_stream()))
+        keepw.append((Wf, c, d))
+        y = torch.nn.functional.layer_norm(s, (768,), ga, be, 1e-12) @ W.float().T + b
+        refs.append(torch.nn.functional.gelu(y) if act == 1 else y)
+    hi = torch.arange(M, device=dev) >= split if split else torch.zeros(M, dtype=torch.bool, device=dev)
+    ref = torch.where(hi[:, None], refs[-1], refs[0])
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    f, keep = _fold_struct(L, split=split, st_in=st, st_in2=st if split else None, c=keepw[0][1],
+                           c2=keepw[-1][1] if dual else None)
+    L.check(so.sprc_op_gemm_fold(L.ptr(s16), L.ptr(keepw[0][0]), L.ptr(keepw[-1][0]) if dual else None, M,
+                                 split if dual else 0, N, 768, L.ptr(keepw[0][2]),
+                                 L.ptr(keepw[-1][2]) if dual else None, act, None, L.ptr(out), f, L.cur_stream()))
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err < 8e-2, err   # bf16 operands of |values| <~ 6, one output rounding
+
+
+_E2E = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from sprc_b200 import synth
+from sprc_b200.model import Blip2QformerCirAlignPrompt
+dev = torch.device("cuda:0")
+m = Blip2QformerCirAlignPrompt(vit_model="clip_L", device=dev, max_images=8, max_queries=64, vit_depth=1, qf_layers=4)
+sd = synth.make_state_dict("clip_L", 1, 4, seed=0, gain=2.5)
+g = torch.Generator().manual_seed(3)
+for k in sd:
+    if "LayerNorm.weight" in k: sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+    elif "LayerNorm.bias" in k: sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+m.load_state_dict(sd)
+B = 64
+ids, mask = synth.make_token_ids(B)
+raws = torch.randn(B, 257, 1024, generator=g).to(dev).bfloat16()
+f = m.encode_query(raws, ids, mask, out_dtype=torch.float32)
+torch.cuda.synchronize()
+torch.save(f.cpu(), sys.argv[1])
+"""
+
+
+def test_fused_query_passes_equal_default_schedule(tmp_path):
+    """Whole composed-query fusion (64 queries, 4 Q-Former layers, non-trivial LayerNorm parameters) with and without
+    the fold, each in its own process (the switch is read once per process), both against the fp32 restatement."""
+    from oracle import restatement as R
+    from oracle import synth
+
+    outs = {}
+    for tag, val in (("default", "0"), ("fold", "1")):
+        path = str(tmp_path / f"{tag}.pt")
+        env = dict(os.environ, SPRC_LN_FOLD=val)
+        subprocess.run([sys.executable, "-c", _E2E % ROOT, path], check=True, env=env, timeout=600)
+        outs[tag] = torch.load(path)
+    sd = synth.make_state_dict("clip_L", 1, 4, seed=0, gain=2.5)
+    g = torch.Generator().manual_seed(3)
+    for k in sd:
+        if "LayerNorm.weight" in k:
+            sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif "LayerNorm.bias" in k:
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+    ids, mask = synth.make_token_ids(64)
+    raws = torch.randn(64, 257, 1024, generator=g).bfloat16().float()
+    want = R.fusion_features(sd, raws, ids, mask)
+    e_def = ((outs["default"] - want).norm() / want.norm()).item()
+    e_fold = ((outs["fold"] - want).norm() / want.norm()).item()
+    print(f"\n[ln fold] rel-Frobenius vs fp32 restatement: default {e_def:.3e}, folded {e_fold:.3e}")
+    assert torch.isfinite(outs["fold"]).all()
+    assert e_fold < 1.5 * e_def + 1e-3
