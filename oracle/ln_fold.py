@@ -187,3 +187,87 @@ def fusion_features_device(sd, reference_embeds, input_ids, attention_mask, fold
     text = qformer_device(sd, fusion[:, :32], input_ids, attention_mask, None, fold, rnd)
     w, b = _lin_params(sd, "text_proj")
     return F.normalize(_r16(text[:, 32], rnd) @ _r16(w, rnd).t() + b, dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# ViT blocks (pre-LN) in the device schedules: csrc/model.cu Model::vit_forward / csrc/ln_fold.cu vit_blocks_fold
+# ------------------------------------------------------------------------------------------------
+def _stats_any(s):
+    """Row statistics partials for rows of any width that is a multiple of 64 (16 for ViT-L, 22 for ViT-g)."""
+    parts = s.shape[-1] // 64
+    rows = s.reshape(-1, parts, 4, 16)
+    cm = rows.mean(-1)
+    cm2 = ((rows - cm[..., None]) ** 2).sum(-1)
+    mean, m2 = cm[..., 0], cm2[..., 0]
+    for cc in range(1, 4):
+        na, nt = 16.0 * cc, 16.0 * cc + 16.0
+        dl = cm[..., cc] - mean
+        mean = mean + dl * (16.0 / nt)
+        m2 = m2 + cm2[..., cc] + dl * dl * (na * 16.0 / nt)
+    return torch.stack([mean, m2], dim=-1).reshape(*s.shape[:-1], parts, 2)
+
+
+def _merge_any(st, eps):
+    parts = st.shape[-2]
+    m = st[..., 0].mean(-1)
+    m2 = (st[..., 1] + 64.0 * (st[..., 0] - m[..., None]) ** 2).sum(-1)
+    return m, torch.rsqrt(m2 / (64.0 * parts) + eps)
+
+
+def image_embeds_device(sd, images, fold, rnd=True):
+    """restatement.image_embeds (eva_vit.py:324-340 / clip_vit.py:171-185 + ln_vision) in the device schedule.
+    fold=True: norm1 of blocks >= 1 and every norm2 are folded into qkv / fc1 (raw residual stream, statistics written
+    by the proj / fc2 producers); block 0's norm1 and ln_vision stay LayerNorm kernels."""
+    vit, depth, _ = R._infer_dims(sd)
+    p = "visual_encoder."
+    eva = vit == "eva_clip_g"
+    if eva:
+        Dv = sd[p + "cls_token"].shape[-1]
+        x = _r16(R.patchify(images), rnd) @ _r16(sd[p + "patch_embed.proj.weight"].float().view(Dv, 588), rnd).t() \
+            + sd[p + "patch_embed.proj.bias"].float()
+        x = torch.cat([sd[p + "cls_token"].float().expand(x.shape[0], -1, -1), x], 1) + sd[p + "pos_embed"].float()
+        eps, act = 1e-6, F.gelu
+    else:
+        Dv = sd[p + "class_embedding"].shape[0]
+        x = _r16(R.patchify(images), rnd) @ _r16(sd[p + "conv1.weight"].float().view(Dv, 588), rnd).t()
+        cls = sd[p + "class_embedding"].float().view(1, 1, Dv).expand(x.shape[0], -1, -1)
+        x = torch.cat([cls, x], 1) + sd[p + "positional_embedding"].float()
+        x = R._ln(x, sd[p + "ln_pre.weight"], sd[p + "ln_pre.bias"], 1e-5)
+        eps, act = 1e-5, (lambda h: h * torch.sigmoid(1.702 * h))
+    scale = (Dv // 16) ** -0.5
+    st = None   # statistics of the raw stream (fold only)
+
+    def names(i):
+        if eva:
+            b = f"{p}blocks.{i}."
+            bias = torch.cat([sd[b + "attn.q_bias"], torch.zeros_like(sd[b + "attn.v_bias"]), sd[b + "attn.v_bias"]])
+            return (b + "norm1", b + "norm2", sd[b + "attn.qkv.weight"].float(), bias.float(), b + "attn.proj",
+                    b + "mlp.fc1", b + "mlp.fc2")
+        b = f"{p}transformer.resblocks.{i}."
+        return (b + "ln_1", b + "ln_2", sd[b + "attn.in_proj_weight"].float(), sd[b + "attn.in_proj_bias"].float(),
+                b + "attn.out_proj", b + "mlp.c_fc", b + "mlp.c_proj")
+
+    def read_ln(x, st, ln, w, b, a=None):
+        g, be = sd[ln + ".weight"].float(), sd[ln + ".bias"].float()
+        if st is None:
+            y = _r16(R._ln(x, g, be, eps), rnd) @ _r16(w, rnd).t() + b
+        else:
+            wf, c, d = fold_weight(w, b, g, be, rnd)
+            m, rs = _merge_any(st, eps)
+            y = rs[..., None] * (_r16(x, rnd) @ wf.t() - m[..., None] * c) + d
+        return _r16(a(y) if a is not None else y, rnd)
+
+    for i in range(depth):
+        n1, n2, wqkv, bqkv, proj, fc1, fc2 = names(i)
+        qkv = read_ln(x, st if fold else None, n1, wqkv, bqkv)
+        q, k, v = qkv.split(Dv, dim=-1)
+        a = _r16(R._mha(q, k, v, 16, scale), rnd)
+        wp, bp = _lin_params(sd, proj)
+        x = x + a @ _r16(wp, rnd).t() + bp
+        st = _stats_any(x) if fold else None
+        w1, b1 = _lin_params(sd, fc1)
+        h = read_ln(x, st, n2, w1, b1, act)
+        w2, b2 = _lin_params(sd, fc2)
+        x = x + h @ _r16(w2, rnd).t() + b2
+        st = _stats_any(x) if fold else None
+    return R._ln(x, sd["ln_vision.weight"], sd["ln_vision.bias"], 1e-5)

@@ -100,11 +100,12 @@ struct GemmDesc {
 
 // Post-LN sublayer  y = LN(s), s = dense(a) + x  (Qformer.py:291-295, 373-381) without a LayerNorm kernel: the
 // residual stream holds the PRE-LN sums s (fp32 + a raw 16-bit copy) and per-row statistics; LN is applied where
-// its output is consumed.  Row statistics are 12 partials (mean, M2) per row of 768 = one per 64-column slice an
-// epilogue thread owns, merged (Chan) by whoever reads them - deterministic, no atomics.
+// its output is consumed.  Row statistics are width / 64 partials (mean, M2) per row (12 for the Q-Former's 768) = one
+// per 64-column slice an epilogue thread owns, merged (Chan) by whoever reads them - deterministic, no atomics.
+// The ViT's pre-LN blocks (eva_vit.py:173-176, clip_vit.py:132-139) use the same two forms with a raw residual.
 //   CONSUMER GEMM (st_in != null): A = raw 16-bit s, W = W * diag(gamma) (16-bit), GemmDesc::bias = d = W beta + b,
 //     c = row sums of the rounded folded weight:  out = act(rstd * (acc - mean * c) + d).
-//   PRODUCER GEMM (st_out != null; N = 768, fp32 out, GemmDesc::residual must be null): s' = acc + bias + r with
+//   PRODUCER GEMM (st_out != null; ldc == N, fp32 out, GemmDesc::residual must be null): s' = acc + bias + r with
 //     r = resid (already normalised, st_res == null) or (resid - mean) * rstd * res_g + res_b; writes s' (fp32,
 //     may alias resid), its raw 16-bit copy out16 and the statistics of s'.
 // Rows >= split (a multiple of 32; 0 = one range) take the *2 members: the fusion pass's query rows and text rows
@@ -127,7 +128,7 @@ struct GemmFold {
   bf16* out16 = nullptr;
   float eps = 1e-12f;
 };
-constexpr int kFoldParts = 12;   // statistics partials per row of 768 (64 columns each)
+constexpr int kFoldParts = 12;   // statistics partials per Q-Former row of 768 (64 columns each)
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)
 int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st);     // CUDA-core checker used by tests only

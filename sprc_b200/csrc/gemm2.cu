@@ -66,24 +66,23 @@ struct FoldArg<1> {
   GemmFold f;
 };
 
-// Chan merge of the kFoldParts (mean, M2) partials of one row of 768 (64 elements each) -> mean, rstd
-__device__ __forceinline__ void fold_row_stats(const float2* __restrict__ st, float eps, float& mean, float& rstd) {
-  float2 part[kFoldParts];
+// Chan merge of the `parts` (mean, M2) partials of one row (64 elements each) -> mean, rstd.  Two passes over the
+// partials (the second one hits L1): `parts` is 12 for the Q-Former's 768-wide rows, 16 / 22 for ViT-L / ViT-g.
+__device__ __forceinline__ void fold_row_stats(const float2* __restrict__ st, int parts, float eps, float& mean,
+                                               float& rstd) {
   float m = 0.f;
-#pragma unroll
-  for (int i = 0; i < kFoldParts; ++i) {
-    part[i] = __ldg(st + i);
-    m += part[i].x;
-  }
-  m *= (1.0f / kFoldParts);
+#pragma unroll 4
+  for (int i = 0; i < parts; ++i) m += __ldg(st + i).x;
+  m /= static_cast<float>(parts);
   float m2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < kFoldParts; ++i) {
-    const float dlt = part[i].x - m;
-    m2 += part[i].y + 64.0f * dlt * dlt;
+#pragma unroll 4
+  for (int i = 0; i < parts; ++i) {
+    const float2 pt = __ldg(st + i);
+    const float dlt = pt.x - m;
+    m2 += pt.y + 64.0f * dlt * dlt;
   }
   mean = m;
-  rstd = rsqrtf(m2 * (1.0f / (64.0f * kFoldParts)) + eps);
+  rstd = rsqrtf(m2 / (64.0f * static_cast<float>(parts)) + eps);
 }
 
 template <int FOLD>
@@ -229,7 +228,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         const bool hi = f.split > 0 && m0 >= f.split;
         if (f.st_in) {
           f_c = (p.m_split > 0 && m0 >= p.m_split) ? f.c2 : f.c;
-          if (f_rowok) fold_row_stats((hi ? f.st_in2 : f.st_in) + (size_t)row * kFoldParts, f.eps, f_mu, f_rs);
+          const int parts = p.K >> 6;   // statistics of the A rows: one partial per 64 of their K columns
+          if (f_rowok) fold_row_stats((hi ? f.st_in2 : f.st_in) + (size_t)row * parts, parts, f.eps, f_mu, f_rs);
         }
         if (f.st_out) {
           f_prod = true;
@@ -237,7 +237,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           f_norm = sr != nullptr;
           f_rg = hi ? f.res_g2 : f.res_g;
           f_rb = hi ? f.res_b2 : f.res_b;
-          if (f_norm && f_rowok) fold_row_stats(sr + (size_t)row * kFoldParts, f.eps, f_rmu, f_rrs);
+          const int parts = p.N >> 6;   // residual / output rows are N wide
+          if (f_norm && f_rowok) fold_row_stats(sr + (size_t)row * parts, parts, f.eps, f_rmu, f_rrs);
         }
       }
       int c1 = m0, c2 = 0;
@@ -263,7 +264,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               // s' = acc + bias + LN(residual row) for 16 columns; raw 16-bit copy; running (mean, M2) of the thread's
               // 64 columns.  The residual may alias the output: this warp reads its 32 x 16 block before its TMA store.
               const GemmFold& f = fa.f;
-              const size_t off = (size_t)(m0 + lane) * 768 + n;
+              const size_t off = (size_t)(m0 + lane) * p.N + n;   // rows of exactly N (ldc == N)
               float v[16];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -311,8 +312,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                                     pack_act(v[12], v[13], p.fp16), pack_act(v[14], v[15], p.fp16));
                 if (cc == nchunks - 1) {
                   float2* so = (f.split > 0 && m0 >= f.split) ? f.st_out2 : f.st_out;
-                  so[(size_t)(m0 + lane) * kFoldParts + (tile % p.num_n_blocks) * 4 + cpart] =
-                      make_float2(f_mean, f_m2);
+                  so[(size_t)(m0 + lane) * (p.N >> 6) + (n0 >> 6)] = make_float2(f_mean, f_m2);
                 }
               }
 #pragma unroll
@@ -486,19 +486,19 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   static bool attr_set[2] = {false, false};
   if (d.fold) {
-    // LayerNorm fold (GemmFold): dense rows, whole 256-column blocks; the producer form writes rows of exactly 768
+    // LayerNorm fold (GemmFold): dense rows; the producer form writes whole rows (ldc == N, N a multiple of 64)
     const GemmFold& f = *d.fold;
     const bool prod = f.st_out != nullptr, cons = f.st_in != nullptr;
     SPRC_REQUIRE(prod || cons, "gemm fold: neither st_in nor st_out is set");
-    SPRC_REQUIRE(d.grp_rows == 0 && !d.out_col_block && d.N % BN == 0 && f.split % 32 == 0,
-                 "gemm fold: dense rows, N %% 256 == 0 and split %% 32 == 0 needed (N=%d split=%d)", d.N, f.split);
-    SPRC_REQUIRE(!cons || (f.c && d.bias && d.K == 768 && d.out_bf16 && (!d.W2 || (f.c2 && d.bias2)) &&
+    SPRC_REQUIRE(d.grp_rows == 0 && !d.out_col_block && d.N % 64 == 0 && f.split % 32 == 0,
+                 "gemm fold: dense rows, N %% 64 == 0 and split %% 32 == 0 needed (N=%d split=%d)", d.N, f.split);
+    SPRC_REQUIRE(!cons || (f.c && d.bias && d.K % 64 == 0 && d.out_bf16 && (!d.W2 || (f.c2 && d.bias2)) &&
                            (f.split == 0 || f.st_in2)),
-                 "gemm fold consumer: K = 768, 16-bit output, c/d vectors for every weight set, st_in2 with a split");
-    SPRC_REQUIRE(!prod || (d.N == 768 && d.ldc == 768 && d.out_f32 && !d.residual && f.resid && f.out16 &&
+                 "gemm fold consumer: K %% 64 == 0, 16-bit output, c/d vectors for every weight set, st_in2 with a split");
+    SPRC_REQUIRE(!prod || (d.ldc == d.N && d.out_f32 && !d.residual && f.resid && f.out16 &&
                            d.act == ACT_NONE && (f.split == 0 || f.st_out2) &&
                            (!f.st_res || (f.res_g && f.res_b)) && (!f.st_res2 || (f.res_g2 && f.res_b2))),
-                 "gemm fold producer: N = ldc = 768, fp32 output, no TMA residual, resid/out16/statistics set");
+                 "gemm fold producer: ldc = N, fp32 output, no TMA residual, resid/out16/statistics set");
     if (!attr_set[1]) {
       SPRC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      SMEM_TOTAL));

@@ -11,9 +11,11 @@
 // weight, so `acc - mean c` is exactly sum_k (s16_k - mean) Wf_nk in the tensor core's own operands.
 //
 // Scope: the ragged composed-query passes (Model::qformer_layers_ragged) for layers 0 .. L-2; the last layer runs the
-// default schedule on a materialised stream (its row-restricted outputs and the [CLS] gather stay as they are).
+// default schedule on a materialised stream (its row-restricted outputs and the [CLS] gather stay as they are).  The
+// ViT's pre-LN blocks use the same two epilogues with a raw residual (Model::vit_blocks_fold, index build).
 // Status: compiled and algebra-checked on CPU (oracle/ln_fold.py, tests/test_ln_fold.py); NOT yet validated on a GPU
 // (tests/test_ln_fold_gpu.py is gated behind SPRC_TEST_LN_FOLD=1) - off by default for that reason.
+#include <math.h>
 #include <stdlib.h>
 
 #include "model.h"
@@ -82,13 +84,13 @@ static int plain_linear(const bf16* A, int M, int K, const bf16* W, int N, const
 }
 
 int Model::fold_one(FoldedLinear* f, const bf16* W, const float* bias, const float* gamma, const float* beta, int N,
-                    cudaStream_t st) {
+                    cudaStream_t st, int K) {
   if (!f->w) {
-    SPRC_TRY(alloc_t(&f->w, (size_t)N * 768));
+    SPRC_TRY(alloc_t(&f->w, (size_t)N * K));
     SPRC_TRY(alloc_t(&f->c, N));
     SPRC_TRY(alloc_t(&f->d, N));
   }
-  return fold_weight(W, gamma, beta, bias, N, 768, f->w, f->c, f->d, st);
+  return fold_weight(W, gamma, beta, bias, N, K, f->w, f->c, f->d, st);
 }
 
 // Folded weights of every GEMM that reads a LayerNorm output in layers 0 .. L-2 of the ragged passes (re-derived after
@@ -117,6 +119,98 @@ int Model::prepare_fold(cudaStream_t st) {
     SPRC_TRY(fold_one(&F.ti, L.ti_w, L.ti_b, L.so_g, L.so_beta, 3072, st));
   }
   fold_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT (pre-LN blocks, eva_vit.py:173-176 / clip_vit.py:132-139):  x += proj(attn(LN1(x)));  x += fc2(act(fc1(LN2(x))))
+// The residual stream is never normalised, so the producers (proj, fc2) add the RAW residual and the consumers (qkv of
+// the next block, fc1) fold norm1 / norm2.  Block 0's norm1 runs as a kernel (its input has no statistics yet) and so
+// does ln_vision (its output is the product).  Statistics: Dv / 64 partials per token (16 ViT-L, 22 ViT-g).
+// ------------------------------------------------------------------------------------------------
+int Model::prepare_vit_fold(cudaStream_t st) {
+  if (vit_fold_ready) return 0;
+  if (!vit_st[0]) {
+    SPRC_TRY(alloc_t(&vit_st[0], (size_t)vit_cap * 257 * (Dv / 64)));
+    SPRC_TRY(alloc_t(&vit_st[1], (size_t)vit_cap * 257 * (Dv / 64)));
+  }
+  vit_folds.resize(depth);
+  for (int i = 0; i < depth; ++i) {
+    const VitBlock& b = blocks[i];
+    if (i > 0) SPRC_TRY(fold_one(&vit_folds[i].qkv, b.qkv_w, b.qkv_b, b.ln1_g, b.ln1_b, 3 * Dv, st, Dv));
+    SPRC_TRY(fold_one(&vit_folds[i].fc1, b.fc1_w, b.fc1_b, b.ln2_g, b.ln2_b, mlp, st, Dv));
+  }
+  vit_fold_ready = true;
+  return 0;
+}
+
+bool Model::vit_fold_usable() const { return ln_fold_enabled() && Dv % 64 == 0; }
+
+int Model::vit_blocks_fold(int B, cudaStream_t st) {
+  SPRC_TRY(prepare_vit_fold(st));
+  const int T = B * 257;
+  const float scale = 1.0f / sqrtf((float)dh);
+  int cur = 0;
+  auto producer = [&](const bf16* A, int K, const bf16* W, const float* bias) -> int {
+    GemmFold f;
+    f.resid = x;     // raw residual stream (st_res stays null: nothing to normalise)
+    f.out16 = xn;    // raw 16-bit copy = A operand of the next consumer
+    f.st_out = vit_st[cur ^ 1];
+    f.eps = vit_eps;
+    GemmDesc d;
+    d.A = A;
+    d.M = T;
+    d.K = d.lda = d.ldw = K;
+    d.N = d.ldc = Dv;
+    d.W = W, d.bias = bias;
+    d.out_f32 = x;
+    d.fold = &f;
+    SPRC_TRY(gemm_bf16_tcgen05(d, st));
+    cur ^= 1;
+    return 0;
+  };
+  auto consumer = [&](const FoldedLinear& w, int N, int act, bf16* out) -> int {
+    GemmFold f;
+    f.st_in = vit_st[cur];
+    f.c = w.c;
+    f.eps = vit_eps;
+    GemmDesc d;
+    d.A = xn;
+    d.M = T;
+    d.K = d.lda = d.ldw = Dv;
+    d.N = d.ldc = N;
+    d.W = w.w, d.bias = w.d;
+    d.act = act;
+    d.out_bf16 = out;
+    d.fold = &f;
+    return gemm_bf16_tcgen05(d, st);
+  };
+  for (int i = 0; i < depth; ++i) {
+    const VitBlock& b = blocks[i];
+    if (i == 0) {
+      SPRC_TRY(layernorm(x, T, Dv, b.ln1_g, b.ln1_b, vit_eps, 0, 0, nullptr, xn, st));
+      SPRC_TRY(plain_linear(xn, T, Dv, b.qkv_w, 3 * Dv, b.qkv_b, ACT_NONE, qkv, st));
+    } else {
+      SPRC_TRY(consumer(vit_folds[i].qkv, 3 * Dv, ACT_NONE, qkv));
+    }
+    AttnDesc a;
+    a.Q = qkv;
+    a.K = qkv + Dv;
+    a.V = qkv + 2 * Dv;
+    a.O = att;
+    a.B = B;
+    a.H = heads;
+    a.dh = dh;
+    a.Lq = a.Lk = 257;
+    a.ldq = a.ldk = a.ldv = 3 * Dv;
+    a.ldo = Dv;
+    a.q_batch_rows = a.kv_batch_rows = 257;
+    a.scale = scale;
+    SPRC_TRY(attention(a, st));
+    SPRC_TRY(producer(att, Dv, b.proj_w, b.proj_b));
+    SPRC_TRY(consumer(vit_folds[i].fc1, mlp, vit_act, h1));
+    SPRC_TRY(producer(h1, mlp, b.fc2_w, b.fc2_b));
+  }
   return 0;
 }
 

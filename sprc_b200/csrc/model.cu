@@ -374,7 +374,7 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
   SPRC_CUDA(cudaGetLastError());
   SPRC_CUDA(cudaDeviceSynchronize());
   s.loaded = true;
-  fold_ready = false;   // folded weights (ln_fold.cu) are derived from the loaded ones
+  fold_ready = vit_fold_ready = false;   // folded weights (ln_fold.cu) are derived from the loaded ones
   return 0;
 }
 
@@ -462,7 +462,9 @@ int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_b
   SPRC_TRY(vit_assemble_tokens(patch_out, cls, pos, B, Dv, x, st));
   if (vit_kind == SPRC_VIT_CLIP_L) SPRC_TRY(layernorm(x, T, Dv, ln_pre_g, ln_pre_b, 1e-5f, 0, 0, x, nullptr, st));
   const float scale = 1.0f / sqrtf((float)dh);
-  for (int i = 0; i < depth; ++i) {
+  const bool fold = vit_fold_usable();   // SPRC_LN_FOLD=1: norm1 / norm2 folded into the GEMMs (ln_fold.cu)
+  if (fold) SPRC_TRY(vit_blocks_fold(B, st));
+  for (int i = fold ? depth : 0; i < depth; ++i) {
     const VitBlock& b = blocks[i];
     SPRC_TRY(layernorm(x, T, Dv, b.ln1_g, b.ln1_b, vit_eps, 0, 0, nullptr, xn, st));
     SPRC_TRY(linear(xn, T, Dv, Dv, b.qkv_w, 3 * Dv, b.qkv_b, ACT_NONE, nullptr, nullptr, qkv, 3 * Dv, 0, 0, st));

@@ -58,6 +58,10 @@ struct QfFold {
   FoldedLinear ti;            // intermediate after attention.output.LayerNorm
 };
 
+struct VitFold {
+  FoldedLinear qkv, fc1;
+};
+
 struct Model {
   // ---- dimensions ----
   int vit_kind = 0, Dv = 0, depth = 0, heads = 16, dh = 0, mlp = 0;
@@ -90,6 +94,9 @@ struct Model {
   std::vector<QfFold> folds;
   bool fold_ready = false;
   float2* fold_st[2] = {nullptr, nullptr};
+  std::vector<VitFold> vit_folds;   // ViT blocks: qkv after norm1 (blocks >= 1), fc1 after norm2
+  bool vit_fold_ready = false;
+  float2* vit_st[2] = {nullptr, nullptr};   // [vit_cap * 257][Dv / 64] (mean, M2)
 
   // ---- workspace ----
   int vit_cap = 0;   // images
@@ -160,7 +167,10 @@ struct Model {
                             cudaStream_t st);
   // LayerNorm fold (ln_fold.cu): layers 0 .. L-2 of a ragged pass without LayerNorm kernels
   int fold_one(FoldedLinear* f, const bf16* W, const float* bias, const float* gamma, const float* beta, int N,
-               cudaStream_t st);
+               cudaStream_t st, int K = 768);
+  int prepare_vit_fold(cudaStream_t st);
+  bool vit_fold_usable() const;
+  int vit_blocks_fold(int B, cudaStream_t st);   // all ViT blocks without norm1 / norm2 kernels (block 0's norm1 kept)
   int prepare_fold(cudaStream_t st);
   bool fold_usable(int B, int T8, const int32_t* kv_idx0) const;
   int qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cudaStream_t st);

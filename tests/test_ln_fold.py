@@ -74,3 +74,26 @@ def test_folded_schedule_costs_no_accuracy_in_bf16():
     print(f"rel-Frobenius vs fp32: default schedule {e_def:.3e}, folded {e_fold:.3e}")
     assert e_def < 2e-2
     assert e_fold < 1.5 * e_def + 1e-3
+
+
+@pytest.mark.parametrize("vit", ["clip_L", "eva_clip_g"])
+def test_vit_folded_schedule(vit):
+    """ViT blocks with norm1 / norm2 folded into qkv / fc1 (csrc/ln_fold.cu vit_blocks_fold): algebra against the fp32
+    restatement (eva_vit.py:173-176, clip_vit.py:132-139) with non-trivial LayerNorm parameters, 16 (ViT-L) and 22
+    (ViT-g) statistics partials per token, and the bf16 cost against the default schedule."""
+    sd = synth.make_state_dict(vit, vit_depth=3, qf_layers=1, seed=0, gain=2.5)
+    g = torch.Generator().manual_seed(9)
+    for k in sd:
+        if k.startswith("visual_encoder.") and ("norm" in k or "ln_" in k):
+            if k.endswith("weight"):
+                sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+            elif k.endswith("bias"):
+                sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+    images = synth.make_images(2)
+    want = R.image_embeds(sd, images)
+    got = LF.image_embeds_device(sd, images, fold=True, rnd=False)
+    assert (got - want).abs().max() < 1e-3, (got - want).abs().max()
+    e_def = (LF.image_embeds_device(sd, images, fold=False) - want).norm() / want.norm()
+    e_fold = (LF.image_embeds_device(sd, images, fold=True) - want).norm() / want.norm()
+    print(f"[{vit}] rel-Frobenius vs fp32: default schedule {e_def:.3e}, folded {e_fold:.3e}")
+    assert e_fold < 1.5 * e_def + 1e-3

@@ -56,9 +56,12 @@ def test_fold_weight_kernel(lib):
     assert (c.cpu() - cc).abs().max() < 1e-4 and (d.cpu() - dd).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("M,split,K,dual,normed", [(512, 0, 768, False, False), (1000, 0, 768, False, True),
-                                                  (27912, 18944, 768, False, True), (27912, 18944, 3072, True, True)])
-def test_producer_gemm(lib, M, split, K, dual, normed):
+@pytest.mark.parametrize("M,split,K,dual,normed,N", [(512, 0, 768, False, False, 768), (1000, 0, 768, False, True, 768),
+                                                    (27912, 18944, 768, False, True, 768),
+                                                    (27912, 18944, 3072, True, True, 768),
+                                                    (2570, 0, 4096, False, False, 1024),     # ViT-L fc2, raw residual
+                                                    (2570, 0, 1408, False, False, 1408)])    # ViT-g proj, ragged N block
+def test_producer_gemm(lib, M, split, K, dual, normed, N):
     """s' = A W^T + b + LN(resid) in place, raw 16-bit copy, 12 row-statistics partials."""
     from oracle import ln_fold as LF
 
@@ -66,71 +69,74 @@ def test_producer_gemm(lib, M, split, K, dual, normed):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(M + K)
     A = torch.randn(M, K, device=dev, generator=g).bfloat16()
-    W1 = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
-    W2 = (torch.randn(768, K, device=dev, generator=g) * K ** -0.5).bfloat16()
-    b1, b2 = torch.randn(768, device=dev, generator=g), torch.randn(768, device=dev, generator=g)
-    x = torch.randn(M, 768, device=dev, generator=g) * 1.7 + torch.randn(M, 1, device=dev, generator=g)
-    g1, be1 = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
-    g2, be2 = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
-    st_res = LF.row_stats_partials(x.cpu()).to(dev).contiguous()
+    W1 = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    W2 = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b1, b2 = torch.randn(N, device=dev, generator=g), torch.randn(N, device=dev, generator=g)
+    x = torch.randn(M, N, device=dev, generator=g) * 1.7 + torch.randn(M, 1, device=dev, generator=g)
+    g1, be1 = 1 + 0.3 * torch.randn(N, device=dev, generator=g), 0.2 * torch.randn(N, device=dev, generator=g)
+    g2, be2 = 1 + 0.3 * torch.randn(N, device=dev, generator=g), 0.2 * torch.randn(N, device=dev, generator=g)
+    st_res = LF._stats_any(x.cpu()).to(dev).contiguous()
     hi = torch.arange(M, device=dev) >= split if split else torch.zeros(M, dtype=torch.bool, device=dev)
     r = x
     if normed:
-        n1 = torch.nn.functional.layer_norm(x, (768,), g1, be1, 1e-12)
-        n2 = torch.nn.functional.layer_norm(x, (768,), g2, be2, 1e-12)
+        n1 = torch.nn.functional.layer_norm(x, (N,), g1, be1, 1e-12)
+        n2 = torch.nn.functional.layer_norm(x, (N,), g2, be2, 1e-12)
         r = torch.where(hi[:, None], n2, n1)
     y1 = A.float() @ W1.float().T + b1
     y2 = A.float() @ W2.float().T + b2 if dual else y1
     ref = torch.where(hi[:, None], y2, y1) + r
-    out16 = torch.zeros(M, 768, device=dev, dtype=torch.bfloat16)
-    st_a = torch.full((M, 12, 2), float("nan"), device=dev)
-    st_b = torch.full((M, 12, 2), float("nan"), device=dev)
+    out16 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    st_a = torch.full((M, N // 64, 2), float("nan"), device=dev)
+    st_b = torch.full((M, N // 64, 2), float("nan"), device=dev)
     f, keep = _fold_struct(L, split=split, resid=x, out16=out16, st_out=st_a, st_out2=st_b if split else None,
                            st_res=st_res if normed else None, st_res2=st_res if (normed and split) else None,
                            res_g=g1 if normed else None, res_b=be1 if normed else None,
                            res_g2=g2 if (normed and split) else None, res_b2=be2 if (normed and split) else None)
-    L.check(so.sprc_op_gemm_fold(L.ptr(A), L.ptr(W1), L.ptr(W2) if dual else None, M, split if dual else 0, 768, K,
+    L.check(so.sprc_op_gemm_fold(L.ptr(A), L.ptr(W1), L.ptr(W2) if dual else None, M, split if dual else 0, N, K,
                                  L.ptr(b1), L.ptr(b2) if dual else None, 0, L.ptr(x), None, f, L.cur_stream()))
     torch.cuda.synchronize()
     assert torch.isfinite(x).all()
     assert (x - ref).abs().max().item() < 2e-3
     assert (out16.float() - ref).abs().max().item() < 6e-2
     st = torch.where(hi[:, None, None], st_b, st_a) if split else st_a
-    m, rs = LF.merge_stats(st.cpu(), 1e-12)
+    m, rs = LF._merge_any(st.cpu(), 1e-12)
     assert (m - ref.mean(-1).cpu()).abs().max() < 1e-4
     assert ((rs - torch.rsqrt(ref.var(-1, unbiased=False) + 1e-12).cpu()) / rs).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("M,split,N,act,dual", [(512, 0, 768, 0, False), (1000, 0, 2304, 0, False),
-                                                (27912, 18944, 3072, 1, True), (27912, 18944, 2304, 0, True)])
-def test_consumer_gemm(lib, M, split, N, act, dual):
+@pytest.mark.parametrize("M,split,N,act,dual,K", [(512, 0, 768, 0, False, 768), (1000, 0, 2304, 0, False, 768),
+                                                  (27912, 18944, 3072, 1, True, 768),
+                                                  (27912, 18944, 2304, 0, True, 768),
+                                                  (2570, 0, 4224, 0, False, 1408),    # ViT-g qkv after norm1
+                                                  (2570, 0, 4096, 2, False, 1024)])   # ViT-L fc1 + QuickGELU after ln_2
+def test_consumer_gemm(lib, M, split, N, act, dual, K):
     """act(LN(s) W^T + b) from the raw 16-bit rows, the folded weight and the row statistics."""
     from oracle import ln_fold as LF
 
     L, so = lib
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(M + N)
-    s = torch.randn(M, 768, device=dev, generator=g) * 1.7 + 0.4 * torch.randn(M, 1, device=dev, generator=g)
+    s = torch.randn(M, K, device=dev, generator=g) * 1.7 + 0.4 * torch.randn(M, 1, device=dev, generator=g)
     s16 = s.bfloat16()
-    st = LF.row_stats_partials(s.cpu()).to(dev).contiguous()
+    st = LF._stats_any(s.cpu()).to(dev).contiguous()
     outs, refs, keepw = [], [], []
     for i in range(2 if dual else 1):
-        W = (torch.randn(N, 768, device=dev, generator=g) * 768 ** -0.5).bfloat16()
+        W = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
         b = torch.randn(N, device=dev, generator=g)
-        ga, be = 1 + 0.3 * torch.randn(768, device=dev, generator=g), 0.2 * torch.randn(768, device=dev, generator=g)
+        ga, be = 1 + 0.3 * torch.randn(K, device=dev, generator=g), 0.2 * torch.randn(K, device=dev, generator=g)
         Wf, c, d = torch.empty_like(W), torch.empty(N, device=dev), torch.empty(N, device=dev)
-        L.check(so.sprc_op_fold_weight(L.ptr(W), L.ptr(ga), L.ptr(be), L.ptr(b), N, 768, L.ptr(Wf), L.ptr(c), L.ptr(d),
+        L.check(so.sprc_op_fold_weight(L.ptr(W), L.ptr(ga), L.ptr(be), L.ptr(b), N, K, L.ptr(Wf), L.ptr(c), L.ptr(d),
                                        L.cur_stream()))
         keepw.append((Wf, c, d))
-        y = torch.nn.functional.layer_norm(s, (768,), ga, be, 1e-12) @ W.float().T + b
-        refs.append(torch.nn.functional.gelu(y) if act == 1 else y)
+        y = torch.nn.functional.layer_norm(s, (K,), ga, be, 1e-12) @ W.float().T + b
+        refs.append(torch.nn.functional.gelu(y) if act == 1 else (y * torch.sigmoid(1.702 * y) if act == 2 else y))
     hi = torch.arange(M, device=dev) >= split if split else torch.zeros(M, dtype=torch.bool, device=dev)
     ref = torch.where(hi[:, None], refs[-1], refs[0])
     out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
     f, keep = _fold_struct(L, split=split, st_in=st, st_in2=st if split else None, c=keepw[0][1],
                            c2=keepw[-1][1] if dual else None)
     L.check(so.sprc_op_gemm_fold(L.ptr(s16), L.ptr(keepw[0][0]), L.ptr(keepw[-1][0]) if dual else None, M,
-                                 split if dual else 0, N, 768, L.ptr(keepw[0][2]),
+                                 split if dual else 0, N, K, L.ptr(keepw[0][2]),
                                  L.ptr(keepw[-1][2]) if dual else None, act, None, L.ptr(out), f, L.cur_stream()))
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
@@ -184,5 +190,55 @@ def test_fused_query_passes_equal_default_schedule(tmp_path):
     e_def = ((outs["default"] - want).norm() / want.norm()).item()
     e_fold = ((outs["fold"] - want).norm() / want.norm()).item()
     print(f"\n[ln fold] rel-Frobenius vs fp32 restatement: default {e_def:.3e}, folded {e_fold:.3e}")
+    assert torch.isfinite(outs["fold"]).all()
+    assert e_fold < 1.5 * e_def + 1e-3
+
+
+_E2E_VIT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from sprc_b200 import synth
+from sprc_b200.model import Blip2QformerCirAlignPrompt
+vit = sys.argv[2]
+dev = torch.device("cuda:0")
+m = Blip2QformerCirAlignPrompt(vit_model=vit, device=dev, max_images=8, max_queries=8, vit_depth=3, qf_layers=1)
+sd = synth.make_state_dict(vit, 3, 1, seed=0, gain=2.5)
+g = torch.Generator().manual_seed(9)
+for k in sd:
+    if k.startswith("visual_encoder.") and ("norm" in k or "ln_" in k):
+        if k.endswith("weight"): sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("bias"): sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+m.load_state_dict(sd)
+feats, raws = m.extract_target_features(synth.make_images(4).to(dev))
+torch.cuda.synchronize()
+torch.save(raws.float().cpu(), sys.argv[1])
+"""
+
+
+@pytest.mark.parametrize("vit", ["clip_L", "eva_clip_g"])
+def test_vit_fold_equals_default_schedule(tmp_path, vit):
+    """ln_vision(ViT(images)) with norm1 / norm2 folded into qkv / fc1 (Model::vit_blocks_fold) against the default
+    schedule and the fp32 restatement (3 blocks, non-trivial LayerNorm parameters)."""
+    from oracle import restatement as R
+    from oracle import synth
+
+    outs = {}
+    for tag, val in (("default", "0"), ("fold", "1")):
+        path = str(tmp_path / f"{tag}.pt")
+        subprocess.run([sys.executable, "-c", _E2E_VIT % ROOT, path, vit], check=True,
+                       env=dict(os.environ, SPRC_LN_FOLD=val), timeout=600)
+        outs[tag] = torch.load(path)
+    sd = synth.make_state_dict(vit, 3, 1, seed=0, gain=2.5)
+    g = torch.Generator().manual_seed(9)
+    for k in sd:
+        if k.startswith("visual_encoder.") and ("norm" in k or "ln_" in k):
+            if k.endswith("weight"):
+                sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+            elif k.endswith("bias"):
+                sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+    want = R.image_embeds(sd, synth.make_images(4))
+    e_def = ((outs["default"] - want).norm() / want.norm()).item()
+    e_fold = ((outs["fold"] - want).norm() / want.norm()).item()
+    print(f"\n[vit ln fold {vit}] rel-Frobenius vs fp32 restatement: default {e_def:.3e}, folded {e_fold:.3e}")
     assert torch.isfinite(outs["fold"]).all()
     assert e_fold < 1.5 * e_def + 1e-3
