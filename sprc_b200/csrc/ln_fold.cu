@@ -215,7 +215,7 @@ int Model::vit_blocks_fold(int B, cudaStream_t st) {
 }
 
 bool Model::fold_usable(int B, int T8, const int32_t* kv_idx0) const {
-  return ln_fold_enabled() && !kv_idx0 && qf_layers >= 2 && T8 > 0 && (32 * B) % 256 == 0;
+  return ln_fold_enabled() && !kv_idx0 && qf_layers >= 2 && T8 > 0 && B > 0;
 }
 
 // Layers 0 .. L-2 of one ragged Q-Former pass in the folded schedule, then the materialising LayerNorms; the caller
@@ -231,18 +231,28 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cuda
   int curQ = 0, curT = 0;  // statistics buffer of the query rows / text rows
   const float *gQ = nullptr, *bQ = nullptr, *gT = nullptr, *bT = nullptr;
 
-  auto producer = [&](const bf16* A, int M, int K, const bf16* W, const float* b, const bf16* W2,
+  // Two weight sets in one launch need the row split on a pair-tile boundary (GemmDesc::m_split % 256 == 0); other
+  // batch sizes run the query-row and text-row halves of those GEMMs as two launches, so the arithmetic of a row never
+  // depends on the batch it sits in (tests/test_parity_gpu.py::test_composed_query_is_batch_invariant).
+  const bool one_launch = qrows % 256 == 0;
+
+  // Producer over rows [row0, row0 + M): s' = A W^T + b + LN(s) in place (qh, qhb), statistics into the other buffer
+  // of each row range.  A is given for row0.  The caller flips cur* once the whole sublayer has been issued.
+  auto producer = [&](int row0, int M, const bf16* A, int K, const bf16* W, const float* b, const bf16* W2,
                       const float* b2) -> int {
+    const bool text_only = row0 >= qrows;
+    const int c0 = text_only ? curT : curQ;
     GemmFold f;
-    f.split = M > qrows ? qrows : 0;
-    f.resid = qh;
-    f.out16 = qhb;
+    f.split = (!text_only && row0 + M > qrows) ? qrows - row0 : 0;
+    f.resid = qh + (size_t)row0 * 768;
+    f.out16 = qhb + (size_t)row0 * 768;
     if (raw) {
-      f.st_res = fold_st[curQ], f.res_g = gQ, f.res_b = bQ;
-      f.st_res2 = fold_st[curT], f.res_g2 = gT, f.res_b2 = bT;
+      f.st_res = fold_st[c0] + (size_t)row0 * kFoldParts;
+      f.res_g = text_only ? gT : gQ, f.res_b = text_only ? bT : bQ;
+      f.st_res2 = fold_st[curT] + (size_t)row0 * kFoldParts, f.res_g2 = gT, f.res_b2 = bT;
     }
-    f.st_out = fold_st[curQ ^ 1];
-    f.st_out2 = fold_st[curT ^ 1];
+    f.st_out = fold_st[c0 ^ 1] + (size_t)row0 * kFoldParts;
+    f.st_out2 = fold_st[curT ^ 1] + (size_t)row0 * kFoldParts;
     GemmDesc d;
     d.A = A;
     d.M = M;
@@ -250,31 +260,42 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cuda
     d.N = d.ldc = 768;
     d.W = W, d.bias = b;
     if (W2) d.W2 = W2, d.bias2 = b2, d.m_split = qrows;
-    d.out_f32 = qh;
+    d.out_f32 = qh + (size_t)row0 * 768;
     d.fold = &f;
-    SPRC_TRY(gemm_bf16_tcgen05(d, st));
-    curQ ^= 1;
-    if (M > qrows) curT ^= 1;
-    raw = true;
-    return 0;
+    return gemm_bf16_tcgen05(d, st);
   };
-  auto consumer = [&](int M, const FoldedLinear& w, const FoldedLinear* w2, int N, int act, bf16* out) -> int {
+  // Consumer over rows [row0, row0 + M) of the raw stream: out rows [row0, ...) = act(LN(s) W^T + b), N wide
+  auto consumer = [&](int row0, int M, const FoldedLinear& w, const FoldedLinear* w2, int N, int act,
+                      bf16* out) -> int {
+    const bool text_only = row0 >= qrows;
     GemmFold f;
-    f.split = M > qrows ? qrows : 0;
-    f.st_in = fold_st[curQ];
-    f.st_in2 = fold_st[curT];
+    f.split = (!text_only && row0 + M > qrows) ? qrows - row0 : 0;
+    f.st_in = fold_st[text_only ? curT : curQ] + (size_t)row0 * kFoldParts;
+    f.st_in2 = fold_st[curT] + (size_t)row0 * kFoldParts;
     f.c = w.c;
     GemmDesc d;
-    d.A = qhb;
+    d.A = qhb + (size_t)row0 * 768;
     d.M = M;
     d.K = d.lda = d.ldw = 768;
     d.N = d.ldc = N;
     d.W = w.w, d.bias = w.d;
     if (w2) d.W2 = w2->w, d.bias2 = w2->d, d.m_split = qrows, f.c2 = w2->c;
     d.act = act;
-    d.out_bf16 = out;
+    d.out_bf16 = out + (size_t)row0 * N;
     d.fold = &f;
     return gemm_bf16_tcgen05(d, st);
+  };
+  // GEMMs whose query rows and text rows use different weights: one launch (GemmDesc::W2) or one per row range
+  auto consumer2 = [&](const FoldedLinear& wq, const FoldedLinear& wt, int N, int act, bf16* out) -> int {
+    if (one_launch) return consumer(0, rows_all, wq, &wt, N, act, out);
+    SPRC_TRY(consumer(0, qrows, wq, nullptr, N, act, out));
+    return consumer(qrows, T8, wt, nullptr, N, act, out);
+  };
+  auto producer2 = [&](const bf16* A, int K, const bf16* Wq, const float* bq, const bf16* Wt,
+                       const float* bt) -> int {
+    if (one_launch) return producer(0, rows_all, A, K, Wq, bq, Wt, bt);
+    SPRC_TRY(producer(0, qrows, A, K, Wq, bq, nullptr, nullptr));
+    return producer(qrows, T8, A + (size_t)qrows * K, K, Wt, bt, nullptr, nullptr);
   };
 
   for (int l = 0; l < qf_layers - 1; ++l) {
@@ -284,17 +305,18 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cuda
     if (!raw)
       SPRC_TRY(plain_linear(qhb, rows_all, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, qqkv, st));
     else if (with_enc)
-      SPRC_TRY(consumer(rows_all, F.qkv_q, &F.qkv_t, 2304, ACT_NONE, qqkv));
+      SPRC_TRY(consumer2(F.qkv_q, F.qkv_t, 2304, ACT_NONE, qqkv));
     else
-      SPRC_TRY(consumer(rows_all, F.qkv_t, nullptr, 2304, ACT_NONE, qqkv));
+      SPRC_TRY(consumer(0, rows_all, F.qkv_t, nullptr, 2304, ACT_NONE, qqkv));
     SPRC_TRY(attention_qf_ragged(qqkv, 2304, qctx, 768, B, rows_all, static_cast<const int4*>(m_pairs), 0.125f, st));
-    SPRC_TRY(producer(qctx, rows_all, 768, L.so_w, L.so_b, nullptr, nullptr));
+    SPRC_TRY(producer(0, rows_all, qctx, 768, L.so_w, L.so_b, nullptr, nullptr));
+    curQ ^= 1, curT ^= 1, raw = true;
     gQ = gT = L.so_g, bQ = bT = L.so_beta;
     if (with_enc) {
       if (L.has_cross) {   // query rows only (Qformer.py:436-452)
         const int ci = l / 2;
         const long long kv_rows = (long long)B * 257;
-        SPRC_TRY(consumer(qrows, F.cq, nullptr, 768, ACT_NONE, qcq));
+        SPRC_TRY(consumer(0, qrows, F.cq, nullptr, 768, ACT_NONE, qcq));
         AttnDesc c;
         c.Q = qcq;
         c.K = kv + (size_t)ci * 24 * kv_rows * 64;
@@ -314,16 +336,19 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cuda
         c.scale = 0.125f;
         c.Lk1 = 257;
         SPRC_TRY(attention(c, st));
-        SPRC_TRY(producer(qctx, qrows, 768, L.co_w, L.co_b, nullptr, nullptr));
+        SPRC_TRY(producer(0, qrows, qctx, 768, L.co_w, L.co_b, nullptr, nullptr));
+        curQ ^= 1;
         gQ = L.co_g, bQ = L.co_beta;
       }
-      // query rows -> *_query FFN, text rows -> text FFN (Qformer.py:455-468), one launch per GEMM
-      SPRC_TRY(consumer(rows_all, F.qi, &F.ti, 3072, ACT_GELU, qffn));
-      SPRC_TRY(producer(qffn, rows_all, 3072, L.qo_w, L.qo_b, L.to_w, L.to_b));
+      // query rows -> *_query FFN, text rows -> text FFN (Qformer.py:455-468)
+      SPRC_TRY(consumer2(F.qi, F.ti, 3072, ACT_GELU, qffn));
+      SPRC_TRY(producer2(qffn, 3072, L.qo_w, L.qo_b, L.to_w, L.to_b));
+      curQ ^= 1, curT ^= 1;
       gQ = L.qo_g, bQ = L.qo_beta, gT = L.to_g, bT = L.to_beta;
     } else {   // no encoder states: every row takes the text FFN (Qformer.py:434-435, 469-475)
-      SPRC_TRY(consumer(rows_all, F.ti, nullptr, 3072, ACT_GELU, qffn));
-      SPRC_TRY(producer(qffn, rows_all, 3072, L.to_w, L.to_b, nullptr, nullptr));
+      SPRC_TRY(consumer(0, rows_all, F.ti, nullptr, 3072, ACT_GELU, qffn));
+      SPRC_TRY(producer(0, rows_all, qffn, 3072, L.to_w, L.to_b, nullptr, nullptr));
+      curQ ^= 1, curT ^= 1;
       gQ = gT = L.to_g, bQ = bT = L.to_beta;
     }
   }
