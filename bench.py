@@ -490,7 +490,9 @@ def main():
                        "captions": "32-token rows, %.1f live tokens on average (SURVEY 8d: L~U{3..20} + [CLS],[SEP]); "
                                    "%s" % (float(lens_h.float().mean()),
                                            "query passes over live text rows only (ragged layout)" if ragged
-                                           else "all 64 padded rows per query computed")},
+                                           else "all 64 padded rows per query computed"),
+                       "layernorm": ("folded into the neighbouring GEMMs (SPRC_LN_FOLD=1, csrc/ln_fold.cu)"
+                                     if os.environ.get("SPRC_LN_FOLD") == "1" else "kernel per sublayer (default)")},
             "clocks": clk,
             "value_repeat_after_e2e": value_repeat,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
