@@ -214,15 +214,14 @@ int Model::vit_blocks_fold(int B, cudaStream_t st) {
   return 0;
 }
 
-bool Model::fold_usable(int B, int T8, const int32_t* kv_idx0) const {
-  return ln_fold_enabled() && !kv_idx0 && qf_layers >= 2 && T8 > 0 && B > 0;
-}
+bool Model::fold_usable(int B, int T8) const { return ln_fold_enabled() && qf_layers >= 2 && T8 > 0 && B > 0; }
 
 // Layers 0 .. L-2 of one ragged Q-Former pass in the folded schedule, then the materialising LayerNorms; the caller
 // (qformer_layers_ragged) runs the last layer in the default schedule.  Row ranges: query rows [0, 32 B) and text rows
 // [32 B, 32 B + T8) owe DIFFERENT LayerNorms after the fusion pass's FFNs and may sit in different statistics buffers
 // (the cross-attention sublayer touches the query rows only), hence the per-range state (cur*, g*, b*).
-int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cudaStream_t st) {
+int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0,
+                                      const int32_t* kv_idx1, cudaStream_t st) {
   SPRC_TRY(prepare_fold(st));
   const int qrows = 32 * B, rows_all = qrows + T8;
   SPRC_REQUIRE(rows_all <= qf_rows, "qformer: %d rows exceed workspace (%d)", rows_all, qf_rows);
@@ -319,10 +318,18 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cuda
         SPRC_TRY(consumer(0, qrows, F.cq, nullptr, 768, ACT_NONE, qcq));
         AttnDesc c;
         c.Q = qcq;
-        c.K = kv + (size_t)ci * 24 * kv_rows * 64;
-        c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
-        c.kv_head_stride = kv_rows * 64;
-        c.ldk = c.ldv = 64;
+        if (kv_idx0) {   // rerank: plain K/V rows, keys = cat(reference image, candidate image)
+          c.K = kv + (size_t)ci * 1536;
+          c.V = kv + (size_t)ci * 1536 + 768;
+          c.ldk = c.ldv = n_cross * 1536;
+          c.kv_idx0 = kv_idx0;
+          c.kv_idx1 = kv_idx1;
+        } else {         // head-major blocks (cross_kv)
+          c.K = kv + (size_t)ci * 24 * kv_rows * 64;
+          c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
+          c.kv_head_stride = kv_rows * 64;
+          c.ldk = c.ldv = 64;
+        }
         c.O = qctx;
         c.B = B;
         c.H = 12;

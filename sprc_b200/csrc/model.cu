@@ -687,8 +687,8 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
   bf16* ctx_cls = qcq;
   bf16* x_cls_b = qcq + (size_t)B * 768;
   int first_layer = 0;
-  if (fold_usable(B, T8, kv_idx0)) {   // SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu)
-    SPRC_TRY(qformer_layers_ragged_fold(B, T8, with_enc, Lk, st));
+  if (fold_usable(B, T8)) {   // SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu)
+    SPRC_TRY(qformer_layers_ragged_fold(B, T8, with_enc, Lk, kv_idx0, kv_idx1, st));
     first_layer = qf_layers - 1;
   }
   for (int l = first_layer; l < qf_layers; ++l) {

@@ -172,8 +172,9 @@ struct Model {
   bool vit_fold_usable() const;
   int vit_blocks_fold(int B, cudaStream_t st);   // all ViT blocks without norm1 / norm2 kernels (block 0's norm1 kept)
   int prepare_fold(cudaStream_t st);
-  bool fold_usable(int B, int T8, const int32_t* kv_idx0) const;
-  int qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cudaStream_t st);
+  bool fold_usable(int B, int T8) const;
+  int qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
+                                 cudaStream_t st);
   // row tables of the ragged layout for B samples; sample b has lens_host[b / repeat] live text tokens
   int build_ragged_meta(const int32_t* lens_host, int repeat, int B, int* T8_out, cudaStream_t st);
   // text_len_host (optional, host int32 [R]): caption lengths -> ragged rows (live text tokens only)
