@@ -214,7 +214,8 @@ int Model::vit_blocks_fold(int B, cudaStream_t st) {
   return 0;
 }
 
-bool Model::fold_usable(int B, int T8) const { return ln_fold_enabled() && qf_layers >= 2 && T8 > 0 && B > 0; }
+// T8 == 0: the gallery pass (32 query rows per image, dense rows, no text rows; Model::qformer_layers with S = 32)
+bool Model::fold_usable(int B, int T8) const { return ln_fold_enabled() && qf_layers >= 2 && T8 >= 0 && B > 0; }
 
 // Layers 0 .. L-2 of one ragged Q-Former pass in the folded schedule, then the materialising LayerNorms; the caller
 // (qformer_layers_ragged) runs the last layer in the default schedule.  Row ranges: query rows [0, 32 B) and text rows
@@ -303,11 +304,28 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cons
     // ---- self-attention over all rows (Qformer.py:175-281) ----
     if (!raw)
       SPRC_TRY(plain_linear(qhb, rows_all, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, qqkv, st));
-    else if (with_enc)
+    else if (with_enc && T8 > 0)
       SPRC_TRY(consumer2(F.qkv_q, F.qkv_t, 2304, ACT_NONE, qqkv));
     else
-      SPRC_TRY(consumer(0, rows_all, F.qkv_t, nullptr, 2304, ACT_NONE, qqkv));
-    SPRC_TRY(attention_qf_ragged(qqkv, 2304, qctx, 768, B, rows_all, static_cast<const int4*>(m_pairs), 0.125f, st));
+      SPRC_TRY(consumer(0, rows_all, with_enc ? F.qkv_q : F.qkv_t, nullptr, 2304, ACT_NONE, qqkv));
+    if (T8 > 0) {
+      SPRC_TRY(attention_qf_ragged(qqkv, 2304, qctx, 768, B, rows_all, static_cast<const int4*>(m_pairs), 0.125f, st));
+    } else {   // gallery pass: 32 query rows per image, no mask (Model::qformer_layers, S = 32)
+      AttnDesc a;
+      a.Q = qqkv;
+      a.K = qqkv + 768;
+      a.V = qqkv + 1536;
+      a.O = qctx;
+      a.B = B;
+      a.H = 12;
+      a.dh = 64;
+      a.Lq = a.Lk = 32;
+      a.ldq = a.ldk = a.ldv = 2304;
+      a.ldo = 768;
+      a.q_batch_rows = a.kv_batch_rows = 32;
+      a.scale = 0.125f;
+      SPRC_TRY(attention(a, st));
+    }
     SPRC_TRY(producer(0, rows_all, qctx, 768, L.so_w, L.so_b, nullptr, nullptr));
     curQ ^= 1, curT ^= 1, raw = true;
     gQ = gT = L.so_g, bQ = bT = L.so_beta;
@@ -348,8 +366,13 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cons
         gQ = L.co_g, bQ = L.co_beta;
       }
       // query rows -> *_query FFN, text rows -> text FFN (Qformer.py:455-468)
-      SPRC_TRY(consumer2(F.qi, F.ti, 3072, ACT_GELU, qffn));
-      SPRC_TRY(producer2(qffn, 3072, L.qo_w, L.qo_b, L.to_w, L.to_b));
+      if (T8 > 0) {
+        SPRC_TRY(consumer2(F.qi, F.ti, 3072, ACT_GELU, qffn));
+        SPRC_TRY(producer2(qffn, 3072, L.qo_w, L.qo_b, L.to_w, L.to_b));
+      } else {
+        SPRC_TRY(consumer(0, qrows, F.qi, nullptr, 3072, ACT_GELU, qffn));
+        SPRC_TRY(producer(0, qrows, qffn, 3072, L.qo_w, L.qo_b, nullptr, nullptr));
+      }
       curQ ^= 1, curT ^= 1;
       gQ = L.qo_g, bQ = L.qo_beta, gT = L.to_g, bT = L.to_beta;
     } else {   // no encoder states: every row takes the text FFN (Qformer.py:434-435, 469-475)
@@ -361,7 +384,7 @@ int Model::qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, cons
   }
   // materialise LN(s) for the last layer (fp32 stream + 16-bit operand copy)
   SPRC_TRY(layernorm(qh, qrows, 768, gQ, bQ, 1e-12f, 0, 0, qh, qhb, st));
-  SPRC_TRY(layernorm(qh + to * 768, T8, 768, gT, bT, 1e-12f, 0, 0, qh + to * 768, qhb + to * 768, st));
+  if (T8 > 0) SPRC_TRY(layernorm(qh + to * 768, T8, 768, gT, bT, 1e-12f, 0, 0, qh + to * 768, qhb + to * 768, st));
   return 0;
 }
 

@@ -520,7 +520,13 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
   const int g = (S == 64) ? 32 : 0;  // row grouping for "first/last 32 rows of each 64-row sample"
   const int gs = (S == 64) ? 64 : 0;
   const int ldkv = n_cross * 1536;
-  for (int l = 0; l < qf_layers; ++l) {
+  int first_layer = 0;
+  if (S == 32 && with_enc && !kv_idx0 && !key_mask && kv_rows > 0 && fold_usable(B, 0)) {
+    // gallery pass with SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu), then the last layer here
+    SPRC_TRY(qformer_layers_ragged_fold(B, 0, true, Lk, nullptr, nullptr, st));
+    first_layer = qf_layers - 1;
+  }
+  for (int l = first_layer; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     // Rows whose output nobody reads are not computed in the LAST layer (their keys/values still are): the
     // fusion pass is consumed through its 32 query rows only (align_prompt.py:343 `fusion_output[:, :32]`,

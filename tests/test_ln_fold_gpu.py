@@ -212,6 +212,18 @@ m.load_state_dict(sd)
 feats, raws = m.extract_target_features(synth.make_images(4).to(dev))
 torch.cuda.synchronize()
 torch.save(raws.float().cpu(), sys.argv[1])
+if len(sys.argv) > 3:   # gallery Q-Former pass (4 layers) on fixed raw embeds
+    import ctypes
+    from sprc_b200 import _lib as L
+    m2 = Blip2QformerCirAlignPrompt(vit_model=vit, device=dev, max_images=8, max_queries=8, vit_depth=1, qf_layers=4)
+    sd2 = synth.make_state_dict(vit, 1, 4, seed=0, gain=2.5)
+    for k in sd2:
+        if "LayerNorm.weight" in k: sd2[k] = 1.0 + 0.3 * torch.randn(sd2[k].shape, generator=g)
+        elif "LayerNorm.bias" in k: sd2[k] = 0.2 * torch.randn(sd2[k].shape, generator=g)
+    m2.load_state_dict(sd2)
+    f2, _ = m2.extract_target_features(synth.make_images(4).to(dev))
+    torch.cuda.synchronize()
+    torch.save(f2.float().cpu(), sys.argv[3])
 """
 
 
@@ -240,5 +252,38 @@ def test_vit_fold_equals_default_schedule(tmp_path, vit):
     e_def = ((outs["default"] - want).norm() / want.norm()).item()
     e_fold = ((outs["fold"] - want).norm() / want.norm()).item()
     print(f"\n[vit ln fold {vit}] rel-Frobenius vs fp32 restatement: default {e_def:.3e}, folded {e_fold:.3e}")
+    assert torch.isfinite(outs["fold"]).all()
+    assert e_fold < 1.5 * e_def + 1e-3
+
+
+def test_gallery_pass_fold_equals_default_schedule(tmp_path):
+    """extract_target_features (ViT 1 block + 4 Q-Former layers, gallery pass over 32 query rows per image) with and
+    without the fold against the fp32 restatement."""
+    from oracle import restatement as R
+    from oracle import synth
+
+    outs = {}
+    for tag, val in (("default", "0"), ("fold", "1")):
+        path, path2 = str(tmp_path / f"{tag}.pt"), str(tmp_path / f"{tag}_feats.pt")
+        subprocess.run([sys.executable, "-c", _E2E_VIT % ROOT, path, "clip_L", path2], check=True,
+                       env=dict(os.environ, SPRC_LN_FOLD=val), timeout=600)
+        outs[tag] = torch.load(path2)
+    # same generator stream as the worker: 3-block ViT LayerNorm draws first, then the Q-Former's
+    g = torch.Generator().manual_seed(9)
+    sd = synth.make_state_dict("clip_L", 3, 1, seed=0, gain=2.5)
+    for k in sd:
+        if k.startswith("visual_encoder.") and ("norm" in k or "ln_" in k):
+            if k.endswith("weight") or k.endswith("bias"):
+                torch.randn(sd[k].shape, generator=g)
+    sd2 = synth.make_state_dict("clip_L", 1, 4, seed=0, gain=2.5)
+    for k in sd2:
+        if "LayerNorm.weight" in k:
+            sd2[k] = 1.0 + 0.3 * torch.randn(sd2[k].shape, generator=g)
+        elif "LayerNorm.bias" in k:
+            sd2[k] = 0.2 * torch.randn(sd2[k].shape, generator=g)
+    want, _ = R.extract_target_features(sd2, synth.make_images(4))
+    e_def = ((outs["default"] - want).norm() / want.norm()).item()
+    e_fold = ((outs["fold"] - want).norm() / want.norm()).item()
+    print(f"\n[gallery ln fold] rel-Frobenius vs fp32 restatement: default {e_def:.3e}, folded {e_fold:.3e}")
     assert torch.isfinite(outs["fold"]).all()
     assert e_fold < 1.5 * e_def + 1e-3
