@@ -61,6 +61,20 @@ def _is_punct(ch: str) -> bool:
     return unicodedata.category(ch).startswith("P")
 
 
+def _is_cjk(ch: str) -> bool:
+    """BasicTokenizer._is_chinese_char (transformers 4.36 tokenization_bert.py): CJK ideographs become single tokens."""
+    cp = ord(ch)
+    return (0x4E00 <= cp <= 0x9FFF or 0x3400 <= cp <= 0x4DBF or 0x20000 <= cp <= 0x2A6DF or 0x2A700 <= cp <= 0x2B73F
+            or 0x2B740 <= cp <= 0x2B81F or 0x2B820 <= cp <= 0x2CEAF or 0xF900 <= cp <= 0xFAFF
+            or 0x2F800 <= cp <= 0x2FA1F)
+
+
+# tokens the tokenizer never splits or lower-cases when they appear verbatim in the text (PreTrainedTokenizer.tokenize
+# splits on all_special_tokens first); [DEC] is the bos token blip2.py:33 adds, id = vocabulary size
+_SPECIAL = {"[PAD]": PAD, "[UNK]": UNK, "[CLS]": CLS, "[SEP]": SEP, "[MASK]": MASK, "[DEC]": VOCAB_SIZE}
+_SPECIAL_RE = re.compile("(" + "|".join(re.escape(t) for t in _SPECIAL) + ")")
+
+
 def _fnv1a(s: str) -> int:
     h = 0x811C9DC5
     for b in s.encode("utf-8"):
@@ -89,6 +103,8 @@ class OfflineBertTokenizer:
                 cleaned.append(" ")
             elif ord(ch) in (0, 0xFFFD) or unicodedata.category(ch) in ("Cc", "Cf"):
                 continue
+            elif _is_cjk(ch):
+                cleaned.append(" " + ch + " ")
             else:
                 cleaned.append(ch)
         text = "".join(cleaned)
@@ -135,8 +151,12 @@ class OfflineBertTokenizer:
 
     def encode(self, text: str, max_length: int = 32):
         ids = [CLS]
-        for w in self._basic(text):
-            ids.extend(self._wordpiece(w))
+        for seg in _SPECIAL_RE.split(text):
+            if seg in _SPECIAL:
+                ids.append(_SPECIAL[seg] if (self.vocab is None or seg == "[DEC]") else self.vocab.get(seg, UNK))
+                continue
+            for w in self._basic(seg):
+                ids.extend(self._wordpiece(w))
         ids = ids[: max_length - 1] + [SEP]  # truncation keeps [CLS] ... [SEP]
         return ids
 
@@ -147,7 +167,9 @@ class OfflineBertTokenizer:
             text = [text]
         n = len(text)
         ids = torch.zeros(n, max_length, dtype=torch.long)
+        mask = torch.zeros(n, max_length, dtype=torch.long)
         for i, t in enumerate(text):
             e = self.encode(t, max_length)
             ids[i, : len(e)] = torch.tensor(e, dtype=torch.long)
-        return TokenBatch(ids, (ids != PAD).long())
+            mask[i, : len(e)] = 1   # by length, not by id: a literal "[PAD]" in the text is a live token
+        return TokenBatch(ids, mask)

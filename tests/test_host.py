@@ -305,3 +305,47 @@ def test_c_abi_argument_validation_without_a_gpu():
     refused(lib.sprc_set_act_dtype(7), "0 (bf16) or 1 (fp16)")
     lib.sprc_destroy(z)        # destroying a null handle is a no-op, like free(NULL)
     assert lib.sprc_launch_count() >= 0
+
+
+def test_tokenizer_matches_transformers_bert_tokenizer(tmp_path):
+    """The third-party algorithm behind blip2.py:30-34 / align_prompt.py:323-329 is transformers' BertTokenizer
+    (BasicTokenizer + WordPiece).  Its bert-base-uncased vocabulary is not available offline, but the ALGORITHM is:
+    on a generated vocabulary `OfflineBertTokenizer` must produce the same ids and masks as the library's own
+    BertTokenizer for random captions with punctuation, accents, CJK, control / zero-width characters, over-long words,
+    literal special tokens and truncation at 32."""
+    import random
+
+    tr = pytest.importorskip("transformers")
+    rnd = random.Random(0)
+    alpha = "abcdefgh"
+    pieces = {"".join(rnd.choice(alpha) for _ in range(rnd.randint(1, 4))) for _ in range(400)}
+    pieces |= {"##" + "".join(rnd.choice(alpha) for _ in range(rnd.randint(1, 3))) for _ in range(300)}
+    toks = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"] + sorted(pieces)
+    toks += list(",.!?;:'\"()-") + ["长", "é", "1", "2", "##1", "e", "u", "ss", "i"]
+    ref = tr.BertTokenizer(vocab={t: i for i, t in enumerate(toks)})
+    ref.add_special_tokens({"bos_token": "[DEC]"})
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(toks) + "\n", encoding="utf-8")
+    ours = OfflineBertTokenizer(str(vf))
+    extras = [" ", "  ", "\t", "\n", ",", ".", "!", "-", "'", "(", ")", "长", "é", "É", "ü", " ", "​", "\x00",
+              "�", "1", "12", "ß", "İ", "$", "^", "`", "~", "　", "x" * 120, "长a", "a长b", "́", "é",
+              "\x7f", " ", "[", "]", "[pad]", "[SEP]", "[UNK]", "[MASK]", "[CLS]", "[PAD]", "a[SEP]b", "[DEC]"]
+    texts = []
+    for _ in range(1500):
+        parts = []
+        for _ in range(rnd.randint(0, 14)):
+            if rnd.random() < 0.6:
+                w = "".join(rnd.choice(alpha) for _ in range(rnd.randint(1, 9)))
+                parts.append(w.capitalize() if rnd.random() < 0.3 else w)
+            else:
+                parts.append(rnd.choice(extras))
+            if rnd.random() < 0.7:
+                parts.append(" ")
+        texts.append("".join(parts))
+    a = ref(texts, padding="max_length", truncation=True, max_length=32, return_tensors="pt")
+    b = ours(texts, max_length=32)
+    ids = b.input_ids.clone()
+    ids[ids == 30522] = ref.bos_token_id     # [DEC] = vocabulary size: 30522 with the real vocabulary
+    bad = [(t, x.tolist(), y.tolist()) for t, x, y in zip(texts, a.input_ids, ids) if not torch.equal(x, y)]
+    assert not bad, bad[:3]
+    assert torch.equal(a.attention_mask, b.attention_mask)
