@@ -8,7 +8,9 @@
   (blip2_qformer_cir_align_prompt.py:323-329): pad to 32, truncate, return int64 ids + mask.
   The third-party algorithm is WordPiece from transformers==4.36.2 (requirements.txt:9): BERT basic
   tokenisation (lower-case, NFD accent stripping, punctuation splitting) then greedy longest-match-first
-  sub-word lookup with the ``##`` continuation prefix, ``[UNK]`` for unmatched words (>100 chars too).
+  sub-word lookup with the ``##`` continuation prefix, ``[UNK]`` for unmatched words (>100 chars too); CJK
+  ideographs are split into single tokens and literal special tokens (``[SEP]`` ...) are kept whole, as the library
+  does.  tests/test_host.py checks ids and masks against the library's own BertTokenizer on a generated vocabulary.
   The bert-base-uncased vocabulary is not available offline: pass ``vocab_file`` (or set
   ``SPRC_BERT_VOCAB``) to get real ids; without it a deterministic synthetic vocabulary maps every
   word to one id in [1000, 29999] by FNV-1a hash so that string-driven synthetic runs are reproducible.
