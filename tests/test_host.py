@@ -68,10 +68,18 @@ def test_caption_processor_known_answers():
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
 def test_caption_processor_matches_reference():
+    import random
+
     ref = ref_loader.load_caption_processor()()
     ours = BlipCaptionProcessor()
     for c in CAPTIONS:
         assert ours(c) == ref(c)
+    rnd = random.Random(1)
+    atoms = ["red", "Dress", "LONGER", "a", "is", ".", "!", "\"", "(", ")", "*", "#", ":", ";", "~", ",", "-", "?", " ",
+             "  ", "   ", "\n", "\t", "\n\n", "é", "'s"]
+    for _ in range(2000):
+        c = "".join(rnd.choice(atoms) + (" " if rnd.random() < 0.5 else "") for _ in range(rnd.randint(0, 80)))
+        assert ours(c) == ref(c), repr(c)
 
 
 def test_tokenizer_layout_and_determinism():
