@@ -564,7 +564,13 @@ def load_index(path: str, device, rank: int = 0, world: int = 1, with_raws: bool
         if hi == lo:
             return torch.empty((0,) + shape_tail, dtype=dt, device=device)
         m = np.memmap(path, dtype=np.int16, mode="r", offset=offset + lo * row_elems * 2, shape=((hi - lo) * row_elems,))
-        return torch.from_numpy(np.ascontiguousarray(m)).view(dt).reshape((hi - lo,) + shape_tail).to(device)
+        import warnings
+
+        with warnings.catch_warnings():   # the mapping is read-only on purpose: it is only the source of the copy
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(np.ascontiguousarray(m)).view(dt).reshape((hi - lo,) + shape_tail)
+        out = t.to(device)
+        return out.clone() if out.device.type == "cpu" else out   # never hand out a tensor aliasing the read-only map
 
     feats = block(off_feats, row_f, (hdr["tokens"], hdr["dim"]))
     raws = None
