@@ -11,7 +11,6 @@ without the library or without a CUDA device raises.
 from __future__ import annotations
 
 import os
-
 from collections import namedtuple
 from typing import List, Optional, Sequence
 
@@ -66,8 +65,6 @@ class Blip2QformerCirAlignPrompt:
         self.training = False
         # 16-bit operand format of every kernel: bf16 (default) or fp16 (the reference's autocast precision);
         # SPRC_ACT_DTYPE overrides the default for unchanged reference scripts
-        import os
-
         act_dtype = act_dtype or os.environ.get("SPRC_ACT_DTYPE", "bf16")
         if act_dtype not in ("bf16", "fp16"):
             raise ValueError("act_dtype must be 'bf16' or 'fp16'")
