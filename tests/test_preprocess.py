@@ -85,6 +85,21 @@ def test_host_tables_reproduce_pil_pipeline_bit_exact():
         assert torch.equal(got, want), (w, h, (got - want).abs().max().item())
 
 
+def test_host_tables_bit_exact_on_random_sizes():
+    """120 random image sizes (1 x 1 up to 900 x 900, every aspect ratio on both sides of the TargetPad threshold):
+    same bit-exact bar as above, so Pillow's support-window / coefficient rounding is pinned beyond the fixed list."""
+    rng = np.random.default_rng(123)
+    pre, ref = _HostOnly(), reference_transform()
+    for i in range(120):
+        w, h = int(rng.integers(20, 900)), int(rng.integers(20, 900))
+        if i % 10 == 0:
+            w, h = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        a = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        got_u8 = _apply_tables_numpy(a, pre.plan(w, h), 224)
+        got = F.normalize(torch.from_numpy(got_u8).permute(2, 0, 1).float().div(255), P.CLIP_MEAN, P.CLIP_STD)
+        assert torch.equal(got, ref(PIL.Image.fromarray(a))), (w, h)
+
+
 def test_geometry_matches_torchvision():
     for w, h in SIZES + [(1, 1), (2000, 31), (31, 2000)]:
         im = PIL.Image.new("RGB", (w, h))
