@@ -166,27 +166,110 @@ def cpu_query_sample(vit, n_queries, gallery_cpu_f32, sd, steps=1, warmup=0, min
     return n_queries * len(times) / sum(times), sum(times) / len(times)
 
 
+def staged_reference_src():
+    """Where the UNMODIFIED reference model sources are: /root/reference in the build container, the byte-identical
+    staged copies under baseline/_ref/src (tools/stage_reference_scripts.py, written by build()) on the GPU box."""
+    for p in ("/root/reference/src", os.path.join(ROOT, "baseline", "_ref", "src")):
+        if os.path.isdir(os.path.join(p, "lavis", "models", "blip2_models")):
+            return p
+    return None
+
+
+def reference_model(vit, sd, device="cpu"):
+    """The reference's own Blip2QformerCirAlignPrompt (lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py),
+    loaded through oracle/ref_loader.py (import shims only, no arithmetic replaced), with the synthetic checkpoint and
+    transformers' BertTokenizer over the synthetic vocabulary (blip2.py:30-34 adds [DEC])."""
+    src = staged_reference_src()
+    if src is None:
+        return None
+    os.environ["SPRC_REFERENCE_SRC"] = src
+    import transformers as tr
+
+    from oracle import ref_loader as RL
+    from sprc_b200 import synth
+
+    RL.REFERENCE_SRC = src
+    model = RL.build_reference_model(vit=vit, seed=0)
+    missing = [k for k in model.load_state_dict(sd, strict=False).missing_keys if not k.startswith("Qformer.cls")
+               and "position_ids" not in k]
+    assert not missing, missing[:5]
+    tok = tr.BertTokenizer(vocab={t: i for i, t in enumerate(synth.make_vocab())})
+    tok.add_special_tokens({"bos_token": "[DEC]"})
+    model.tokenizer = tok
+    return model.to(device).eval()
+
+
+def reference_query_sample(model, vit, n_queries, gallery_f32, steps=1, warmup=0, min_seconds=0.0, device="cpu",
+                           autocast=False):
+    """One step = what the reference does for one query batch: `model.inference(reference_embeds, target_feats,
+    captions)` (tokenisation, two Q-Former passes, its own broadcast matmul + max, align_prompt.py:312-361), then
+    `torch.argsort(1 - sim).cpu()` (validate_blip.py:253-254).  Caption strings and reference embeds are synthetic."""
+    from sprc_b200 import synth
+
+    Dv = synth.VIT_DIMS[vit][0]
+    g = torch.Generator().manual_seed(77)
+    vocab = synth.make_vocab()
+    times, it = [], 0
+    while it < warmup + steps or sum(times) < min_seconds:
+        ref = torch.randn(n_queries, 257, Dv, generator=g).to(device)
+        caps = synth.make_captions(n_queries, seed=1000 + it, vocab=vocab)
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            sim = model.inference(ref, gallery_f32, caps)
+            order = torch.argsort(1 - sim.reshape(n_queries, -1).float(), dim=-1).cpu()  # noqa: F841
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        it += 1
+    return n_queries * len(times) / sum(times), sum(times) / len(times)
+
+
+def reference_batch_for_memory(n_gallery, want, avail_bytes):
+    """The reference's broadcast matmul materialises Bq copies of the gallery (Bq*N*32*256*4 bytes):
+    pick the largest query batch <= `want` whose expansion stays under 30 % of the available memory."""
+    per_query = n_gallery * 32 * 256 * 4 * 1.1
+    return int(max(1, min(want, (0.30 * avail_bytes) // per_query)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import synth
+    import psutil
+
+    from sprc_b200 import synth
 
     cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     sd = synth.make_state_dict(args.vit, None, 12, seed=0)
     gal = synth.make_gallery_features(args.gallery, seed=99)
-    nq = args.cpu_sample
-    qps, sec = cpu_query_sample(args.vit, nq, gal, sd, steps=args.steps, warmup=args.warmup)
-    sample = (f"{nq} composed queries/step in reference-sized batches of 16, resident reference embeds, fp32 torch "
-              f"restatement of the reference (oracle port; the Python reference cannot travel to this box), "
-              f"gallery {args.gallery} unit-norm synthetic features, similarity as ONE matmul (the reference's "
-              f"broadcast matmul is slower), full argsort ranking, {cores} threads")
+    model = reference_model(args.vit, sd)
+    if model is not None:
+        nq = reference_batch_for_memory(args.gallery, min(args.cpu_sample, 16), psutil.virtual_memory().available)
+        qps, sec = reference_query_sample(model, args.vit, nq, gal, steps=args.steps, warmup=args.warmup)
+        kind = "reference"
+        sample = (f"each step = ONE query batch of {nq} composed queries (caption strings + resident reference "
+                  f"embeds) through the UNMODIFIED reference Blip2QformerCirAlignPrompt.inference (its tokeniser call, "
+                  f"two fp32 Q-Former passes, its own broadcast matmul + max over the {args.gallery}-row fp32 "
+                  f"gallery) and torch.argsort(1 - sim).cpu(), torch CPU eager on {cores} threads; sources: "
+                  f"{staged_reference_src()} (byte-identical staged copies, oracle/ref_loader.py shims); the "
+                  f"reference's loops use batches of 16 (FashionIQ) / 32 (CIRR): the batch is capped so that the "
+                  f"Bq-fold gallery expansion of its matmul fits host memory")
+    else:
+        nq = args.cpu_sample
+        qps, sec = cpu_query_sample(args.vit, nq, gal, sd, steps=args.steps, warmup=args.warmup)
+        kind = "port"
+        sample = (f"{nq} composed queries/step in reference-sized batches of 16, fp32 torch restatement of the "
+                  f"reference (oracle port: the staged reference sources were not found), gallery {args.gallery}, "
+                  f"similarity as ONE matmul, full argsort ranking, {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.vit}_blip2_cirr_shape_gallery{args.gallery}", "gallery": args.gallery,
                        "queries_per_step": nq, "k": args.k},
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

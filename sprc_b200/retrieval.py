@@ -44,6 +44,7 @@ class GalleryIndex:
     hi: int = 0
     n_total: int = 0
     name_to_row: Dict[str, int] = field(default_factory=dict)
+    bounds: Optional[List[int]] = None   # world+1 row boundaries of ALL ranks' shards (None: `shard_range` split)
 
     def __post_init__(self):
         if not self.n_total:
@@ -52,6 +53,14 @@ class GalleryIndex:
             self.hi = self.lo + self.feats.shape[0]
         if not self.name_to_row:
             self.name_to_row = {n: i for i, n in enumerate(self.names)}
+
+    def owner(self, rows: torch.Tensor, world: int) -> torch.Tensor:
+        """Rank holding each global row: by the recorded shard boundaries when the index was built from a dataset
+        that dropped unreadable images (shards then differ from `shard_range`), else by `shard_range`."""
+        if self.bounds is None:
+            return owner_of(rows, self.n_total, world)
+        his = torch.tensor(self.bounds[1:], dtype=torch.int64)
+        return torch.bucketize(rows.to(torch.int64), his, right=True).clamp_(0, world - 1)
 
     def rows_of(self, names: Sequence[str]) -> torch.Tensor:
         return torch.tensor([self.name_to_row[n] for n in names], dtype=torch.int64)
@@ -125,11 +134,13 @@ def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, co
         all_names = names
     # the reference drops unreadable images silently (data_utils.py:191-192 + collate_fn); keep that:
     # rows are numbered by position among the images that were actually encoded
+    bounds = None
     if world > 1:
         counts = [len(p) for p in gathered]
         lo = sum(counts[:rank])
+        bounds = [sum(counts[:i]) for i in range(world + 1)]   # real [lo, hi) of every rank (rows were dropped)
     return GalleryIndex(feats=f.contiguous(), raws=None if r is None else r.contiguous(), names=all_names, lo=lo,
-                        hi=lo + f.shape[0], n_total=len(all_names))
+                        hi=lo + f.shape[0], n_total=len(all_names), bounds=bounds)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -158,9 +169,16 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
             fusion32[sel.to(dev)] = f.float()
         dist.all_reduce(fusion32)  # exactly one rank contributes each row: x + 0 + ... is exact
         fusion = fusion32.to(index.feats.dtype)
-    sc, ix, _ = backend.sim_topk(fusion, index.feats, k=k, row_offset=index.lo)
+    if index.feats.shape[0] == 0:
+        # empty shard (fewer images than ranks): no candidates from this rank
+        sc = torch.full((Q, k), float("-inf"), dtype=torch.float32, device=dev)
+        ix = torch.full((Q, k), -1, dtype=torch.int32, device=dev)
+    else:
+        sc, ix, _ = backend.sim_topk(fusion, index.feats, k=k, row_offset=index.lo)
     sub = None
-    if subset_rows is not None:
+    if subset_rows is not None and index.feats.shape[0] == 0:
+        sub = torch.full(tuple(subset_rows.shape), float("-inf"), dtype=torch.float32, device=dev)
+    elif subset_rows is not None:
         local = subset_rows.to(torch.int64) - index.lo
         local = torch.where((subset_rows >= index.lo) & (subset_rows < index.hi), local, torch.full_like(local, -1))
         sub = backend.gather_scores(fusion, index.feats, local.to(torch.int32))
@@ -204,11 +222,11 @@ def fetch_raw_rows(index: GalleryIndex, rows: torch.Tensor) -> torch.Tensor:
     req = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(req, mine)
     req = [r[:c].cpu() for r, c in zip(req, counts)]                      # what each rank needs
-    own = owner_of(rows, index.n_total, world)                            # who holds what I need
+    own = index.owner(rows, world)                                        # who holds what I need
     out = torch.empty((rows.numel(),) + tuple(index.raws.shape[1:]), dtype=index.raws.dtype, device=dev)
     ops, recv_bufs, keep_alive = [], {}, []
     for p in range(world):
-        wanted = req[p][owner_of(req[p], index.n_total, world) == rank]   # rows rank p needs from me, in p's order
+        wanted = req[p][index.owner(req[p], world) == rank]               # rows rank p needs from me, in p's order
         if p == rank:
             out[(own == rank).nonzero().flatten().to(dev)] = index.raws[(wanted - index.lo).to(dev)]
             continue
@@ -271,6 +289,17 @@ def rerank_topk(backend, index: GalleryIndex, top_rows: torch.Tensor, ref_rows: 
     return top_rows
 
 
+def _subset_scores_after_rerank(ranked: torch.Tensor, group_rows: torch.Tensor, sub_scores: torch.Tensor,
+                                T: int) -> torch.Tensor:
+    """Subset scores that reproduce "the re-ordered global list restricted to the group members"
+    (cirr_test_submission.py:121-123, validate_blip_rerank.py:222-228): a member found at position p < T of the
+    re-ordered list scores 1e6 - p (above any similarity), the others keep their first-stage similarity."""
+    ranked, group_rows = ranked.cpu().to(torch.int64), group_rows.cpu().to(torch.int64)
+    hit = (ranked[:, :T, None] == group_rows[:, None, :]) & (group_rows[:, None, :] >= 0)     # [Q,T,m]
+    pos = torch.where(hit.any(dim=1), hit.float().argmax(dim=1), torch.full(group_rows.shape, -1))
+    return torch.where(pos >= 0, 1e6 - pos.float(), sub_scores.cpu().float())
+
+
 def _tokenize(backend, captions):
     tok = backend.tokenizer(list(captions), padding="max_length", truncation=True, max_length=32, return_tensors="pt")
     return tok.input_ids, tok.attention_mask
@@ -294,8 +323,9 @@ def cirr_recalls_from_topk(top_rows: torch.Tensor, ref_rows: torch.Tensor, tgt_r
     ranked = torch.full((Q, K1), -1, dtype=torch.int64)
     qi = torch.arange(Q)[:, None].expand(Q, K1)
     ranked[qi[keep], pos[keep]] = top_rows[keep]
-    ranked = ranked[:, : K1 - 1]
-    labels = ranked == tgt_rows[:, None]
+    # no truncation: a row that held its reference ends in one -1 slot (never a label); a row that did not (the
+    # reference ranked below K1, or the caller removed it already, as the rerank path does) keeps all K1 entries
+    labels = (ranked == tgt_rows[:, None]) & (ranked >= 0)
     rec = lambda kk: (labels[:, :kk].any(dim=1).sum().item() / Q) * 100.0  # noqa: E731
     # subset ranking: group members without the reference, by (score desc, row asc) like the global order
     g_rows = group_rows.cpu().to(torch.int64)
@@ -393,10 +423,7 @@ def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, i
         ranked = torch.stack([r[k_][: K1 - 1] for r, k_ in zip(top_rows, keep)])
         T = min(rerank_top, ranked.shape[1], index.n_total - 1)
         ranked = rerank_topk(blip_model, index, ranked, ref_rows, ids, mask, T)
-        # subset ranking follows the re-ordered list: members inside the first T take their new positions
-        hit = ranked[:, :T, None] == group_rows[:, None, :]       # [Q,T,6]
-        pos = torch.where(hit.any(dim=1), hit.float().argmax(dim=1), torch.full(group_rows.shape, -1))
-        sub_scores = torch.where(pos >= 0, 1e6 - pos.float(), sub_scores.float())
+        sub_scores = _subset_scores_after_rerank(ranked, group_rows, sub_scores, T)
         top_rows = ranked
     return cirr_recalls_from_topk(top_rows, ref_rows, tgt_rows, group_rows, sub_scores)
 
@@ -501,7 +528,11 @@ def generate_cirr_test_dicts(relative_test_dataset, blip_model, index_features, 
         subs.append(sub.cpu())
     top_rows, sub_scores = torch.cat(tops), torch.cat(subs)
     if rerank:
-        top_rows = rerank_topk(blip_model, index, top_rows, ref_rows, ids, mask, min(top, top_rows.shape[1]))
+        T = min(top, top_rows.shape[1])
+        top_rows = rerank_topk(blip_model, index, top_rows, ref_rows, ids, mask, T)
+        # :115-123 the subset ranking is the RE-ORDERED global list restricted to the group members: members inside
+        # the first T take their new positions (ahead of every member outside, whose first-stage order stands)
+        sub_scores = _subset_scores_after_rerank(top_rows, group_rows, sub_scores, T)
     return cirr_submission_from_topk(top_rows, ref_rows, group_rows, sub_scores, index.names, pairs_id)
 
 

@@ -138,3 +138,50 @@ def make_dyadic(shape, seed: int, device="cpu"):
     rankings are independent of summation order (SURVEY.md §7 "Bit-exact top-k")."""
     g = torch.Generator().manual_seed(seed)
     return (torch.randint(-4, 5, shape, generator=g).float() / 16.0).to(device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic vocabulary + caption STRINGS (the bert-base-uncased vocabulary is not available offline)
+# ---------------------------------------------------------------------------------------------------
+def _word_of(i: int) -> str:
+    """Distinct all-letter pseudo-word for vocabulary id i (consonant/vowel alternation, so BasicTokenizer never
+    splits it and lower-casing / accent stripping leave it alone)."""
+    cons, vow = "bcdfghjklmnprstvwz", "aeiou"
+    w, k = [], i
+    for pos in range(6):
+        if pos % 2 == 0:
+            w.append(cons[k % len(cons)])
+            k //= len(cons)
+        else:
+            w.append(vow[k % len(vow)])
+            k //= len(vow)
+    return "".join(w)
+
+
+def make_vocab():
+    """30 522 tokens laid out like bert-base-uncased: [PAD]=0, [unused*], [UNK]=100, [CLS]=101, [SEP]=102, [MASK]=103,
+    more [unused*] up to id 998, punctuation at 999.., then one whole-word token per id (`_word_of`) and a tail of
+    `##` continuation pieces.  Every id in [1000, 30000) is a whole word, so `make_captions` round-trips to
+    `make_token_ids` through any correct WordPiece tokenizer."""
+    toks = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    toks += [f"[unused{i}]" for i in range(99, 99 + 1000 - len(toks))]
+    assert len(toks) == 1000
+    toks += [_word_of(i) for i in range(1000, 30000)]
+    punct = list("!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~")
+    toks += punct
+    toks += ["##" + _word_of(i)[:3] for i in range(30000 + len(punct), 30522)]
+    assert len(toks) == 30522 and len(set(toks)) == 30522
+    return toks
+
+
+def write_vocab(path: str) -> str:
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(make_vocab()) + "\n")
+    return path
+
+
+def make_captions(n: int, seed: int = 4321, vocab=None):
+    """Caption strings whose WordPiece ids over `make_vocab()` are exactly `make_token_ids(n, seed)`."""
+    vocab = vocab or make_vocab()
+    ids, mask = make_token_ids(n, seed)
+    return [" ".join(vocab[int(t)] for t in row[1:int(m.sum()) - 1]) for row, m in zip(ids, mask)]

@@ -357,3 +357,103 @@ def test_tokenizer_matches_transformers_bert_tokenizer(tmp_path):
     bad = [(t, x.tolist(), y.tolist()) for t, x, y in zip(texts, a.input_ids, ids) if not torch.equal(x, y)]
     assert not bad, bad[:3]
     assert torch.equal(a.attention_mask, b.attention_mask)
+
+
+def _rerank_fixture(seed=5, N=60, Q=12, Dv=16, T=7):
+    """Small CPU world for the rerank drivers: oracle backend, bf16 index, deterministic token ids."""
+    from oracle import restatement as R
+    from test_dist_cpu import OracleBackend
+
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.nn.functional.normalize(torch.randn(N, 32, 256, generator=g), dim=-1).to(torch.bfloat16)
+    raws = torch.randn(N, 257, Dv, generator=g).to(torch.bfloat16)
+    be = OracleBackend(torch.randn(Dv, 256, generator=g))
+    be.max_pairs = 3 * T
+    hash_ = lambda c: sum(ord(ch) for ch in c)  # noqa: E731
+
+    class Tok:
+        def __call__(self, caps, **kw):
+            ids = torch.tensor([[101] + [1000 + (hash_(c) + j) % 20000 for j in range(30)] + [102] for c in caps])
+            return type("B", (), dict(input_ids=ids, attention_mask=torch.ones_like(ids)))()
+
+    be.tokenizer = Tok()
+    names = [f"n{i:03d}" for i in range(N)]
+    ref = torch.randint(0, N, (Q,), generator=g)
+    caps = [f"caption number {q}" for q in range(Q)]
+    ids, mask = RT._tokenize(be, caps)
+    fusion = be.encode_query(raws, ids, mask, ref_rows=ref)
+    sim = R.similarity(fusion.float(), feats.float())
+    order = R.ranking(sim)
+    index = RT.GalleryIndex(feats=feats, raws=raws, names=names)
+
+    def pair_scores(q, cand):
+        table = torch.cat([raws[ref[q:q + 1]], raws[cand]])
+        return be.rerank_rows(table, torch.tensor([0]), torch.arange(1, len(cand) + 1), ids[q:q + 1], mask[q:q + 1],
+                              len(cand))
+
+    return dict(be=be, index=index, names=names, ref=ref, caps=caps, order=order, sim=sim, pair_scores=pair_scores,
+                g=g)
+
+
+def test_cirr_test_dicts_with_rerank_match_reference_string_semantics():
+    """generate_cirr_test_dicts(rerank=True) against cirr_test_submission.py:80-130 spelled out on NAME arrays: full
+    argsort, first `top` names of every row re-ordered by the pair probability (reference still in the list), the
+    reference deleted, subset = the re-ordered list restricted to the group members (the subset must
+    follow the reranked order, not the first-stage similarity)."""
+    import numpy as np
+
+    fx = _rerank_fixture(seed=9, N=70, Q=16, T=10)
+    be, index, names, ref, caps, order = fx["be"], fx["index"], fx["names"], fx["ref"], fx["caps"], fx["order"]
+    N, Q, top = len(names), len(caps), 10
+    g = fx["g"]
+    # groups: reference + 5 members, several of them drawn from the first-stage top-`top` so that the rerank moves them
+    groups = []
+    for q in range(Q):
+        cand = [int(x) for x in order[q][:top] if int(x) != int(ref[q])]
+        pick = [cand[i] for i in torch.randperm(len(cand), generator=g)[:3].tolist()]
+        rest = [x for x in torch.randperm(N, generator=g).tolist() if x != int(ref[q]) and x not in pick][:2]
+        groups.append([int(ref[q])] + pick + rest)
+    groups = torch.tensor(groups)
+    pairs = list(range(500, 500 + Q))
+    # --- the reference's order of operations, on strings
+    sorted_names = np.array(names)[order.numpy()]
+    for q in range(Q):
+        p = fx["pair_scores"](q, order[q][:top])
+        o = torch.argsort(1 - p, dim=-1, stable=True).numpy()
+        sorted_names[q, :top] = sorted_names[q, :top][o]
+    ref_names = np.array(names)[ref.numpy()]
+    keep = sorted_names != np.repeat(ref_names, N).reshape(Q, -1)
+    sorted_names = sorted_names[keep].reshape(Q, N - 1)
+    gm = np.array(names)[groups.numpy()]
+    gmask = (sorted_names[..., None] == gm[:, None, :]).sum(-1).astype(bool)
+    sorted_group = sorted_names[gmask].reshape(Q, -1)
+    want_g = {str(p): r[:50].tolist() for p, r in zip(pairs, sorted_names)}
+    want_s = {str(p): r[:3].tolist() for p, r in zip(pairs, sorted_group)}
+    # --- ours
+    ds = [(pairs[q], names[int(ref[q])], caps[q], [names[int(m)] for m in groups[q]]) for q in range(Q)]
+    got_g, got_s = RT.generate_cirr_test_dicts(ds, be, index, names, {"eval": lambda c: c}, rerank=True, top=top)
+    assert got_g == want_g
+    assert got_s == want_s
+    # and the rerank really changes the subset order of this split (otherwise the test proves nothing)
+    _, plain_s = RT.generate_cirr_test_dicts(ds, be, index, names, {"eval": lambda c: c}, rerank=False)
+    assert plain_s != want_s
+
+
+def test_cirr_val_metrics_rerank_keeps_rank_50():
+    """with rerank_top in 1..50 the reference is removed before the rerank, so the ranking handed to the
+    recall tail has exactly 50 columns; a target sitting at rank 50 must still count for R@50."""
+    from oracle import restatement as R
+
+    fx = _rerank_fixture(seed=21, N=80, Q=10, T=7)
+    be, index, names, ref, caps, order = fx["be"], fx["index"], fx["names"], fx["ref"], fx["caps"], fx["order"]
+    Q = len(caps)
+    noref = [order[q][order[q] != ref[q]] for q in range(Q)]
+    tgt = torch.stack([r[49] for r in noref])                     # rank 50 after reference removal, outside the first T
+    members = torch.stack([torch.cat([ref[q:q + 1], tgt[q:q + 1], noref[q][60:64]]) for q in range(Q)])
+    ds = [(names[int(ref[q])], names[int(tgt[q])], caps[q], [names[int(m)] for m in members[q]]) for q in range(Q)]
+    txt = {"eval": lambda c: c}
+    plain = RT.compute_cirr_val_metrics(ds, be, index, names, txt)
+    rer = RT.compute_cirr_val_metrics(ds, be, index, names, txt, rerank_top=7)
+    assert plain[6] == 100.0 and plain[5] == 0.0
+    assert rer[6] == 100.0 and rer[5] == 0.0
+    assert plain == pytest.approx(R.cirr_recalls(order, ref, tgt, members))
