@@ -111,6 +111,11 @@ int sprc_sim_topk(sprc_handle* h, const void* queries_bf16, int Q, const void* g
  * cand_* are [P,Q,k]; output [Q,k] sorted by (score desc, idx asc). */
 int sprc_topk_merge(sprc_handle* h, const float* cand_score, const int32_t* cand_idx, int P, int Q, int k,
                     float* out_score, int32_t* out_idx, void* stream);
+/* The same merge straight off the exchange buffer of the multi-GPU step: cand is int32
+ * [P][2][Q][k] - for every source rank p the fp32 scores (bit pattern) of this rank's Q queries, then their global
+ * rows - exactly what ONE all-to-all of per-shard candidates delivers, so each rank merges only its own queries. */
+int sprc_topk_merge_packed(sprc_handle* h, const int32_t* cand, int P, int Q, int k, float* out_score,
+                           int32_t* out_idx, void* stream);
 
 /* sim of selected (query, row) pairs — CIRR subset members (validate_blip.py:268-271): rows int32 [Q,m]
  * (negative = skip, score -inf) -> out [Q,m]. */
@@ -182,9 +187,6 @@ int sprc_op_gemm(const void* A_bf16, const void* W_bf16, int M, int N, int K, in
 int sprc_op_gemm2w(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
                    const float* bias, const float* bias2, const float* residual, float* out_f32, void* out_bf16,
                    int act, void* stream);
-int sprc_op_gemm_ln(const void* A_bf16, const void* W_bf16, int M, int N, int K, int lda, int ldw, int grp_rows,
-                    int grp_stride, const float* bias, const float* residual, const float* gamma, const float* beta,
-                    float eps, float* out_f32, void* out_ln16, int ldc, void* stream);
 /* Q-Former self-attention over the ragged row layout (csrc/attention_qfr.cu): qkv [rows_total, 3*768] packed
  * Q|K|V, rows [0,32B) query rows, then per-sample text slots; pairs_dev int32 [ceil(B/2)][4] = {toff0, L0, toff1, L1}. */
 int sprc_op_attention_ragged(const void* qkv, int ldqkv, void* out, int ldo, int B, int rows_total,
@@ -195,35 +197,23 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
                       int Lk, int ldq, int ldk, int ldv, int ldo, int q_batch_rows, int kv_batch_rows,
                       const float* key_mask, float scale, void* stream);
 
-/* LayerNorm folded into the neighbouring GEMMs (opt-in schedule SPRC_LN_FOLD=1, csrc/ln_fold.cu, csrc/common.h
- * GemmFold; Qformer.py:291-295,373-381 post-LN sublayers).  Row statistics: 12 (mean, M2) float pairs per row of 768.
- * sprc_op_fold_weight: Wf = round16(W diag(gamma)), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n].
- * sprc_op_gemm_fold, consumer (fold->st_in set): out_bf16 = act(rstd (A Wf^T - mean c) + d), bias = d;
- * producer (fold->st_out set, N = 768): out_f32 = A W^T + bias + LN(resid) (resid as is when st_res is null),
- * fold->out16 = its raw 16-bit copy, fold->st_out = its row statistics.  Rows >= split take the *2 members. */
-typedef struct sprc_gemm_fold {
-  int32_t split;
-  float eps;
-  const void* st_in;
-  const void* st_in2;
-  const float* c;
-  const float* c2;
-  const float* resid;
-  const void* st_res;
-  const void* st_res2;
-  const float* res_g;
-  const float* res_b;
-  const float* res_g2;
-  const float* res_b2;
-  void* st_out;
-  void* st_out2;
-  void* out16;
-} sprc_gemm_fold;
-int sprc_op_fold_weight(const void* W_bf16, const float* gamma, const float* beta, const float* bias, int N, int K,
-                        void* Wf_bf16, float* c, float* d, void* stream);
-int sprc_op_gemm_fold(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
-                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
-                      const sprc_gemm_fold* fold, void* stream);
+/* ---------------------------------------------------------------------------------------------------
+ * Host-side caption tokenizer (csrc/tokenizer.cpp; no CUDA).  Replaces the per-batch Python tokenizer call inside
+ * `inference` (blip2_qformer_cir_align_prompt.py:323-329: `self.tokenizer(text, padding="max_length",
+ * truncation=True, max_length=32)` with the tokenizer of blip2.py:30-34 = transformers 4.36 BertTokenizer + [DEC]):
+ * BasicTokenizer + greedy WordPiece, [CLS] ... [SEP], truncated / zero-padded to max_len.
+ * sprc_tokenizer_create: vocab_utf8 = contents of a BERT vocab.txt (one token per line, id = line number), or
+ *   NULL / 0 for the synthetic hashed vocabulary used by string-driven synthetic runs (id = 1000 + FNV-1a % 29000).
+ * sprc_tokenize_host: texts = n UTF-8 captions back to back, caption i = bytes [offsets[i], offsets[i+1]);
+ *   ids / mask int64 [n, max_len] (HOST), lens int32 [n] live tokens (or NULL), complex_flags uint8 [n] (or NULL):
+ *   1 = the caption holds a character whose normalisation depends on its neighbours (combining marks, final sigma;
+ *   tools/gen_unicode_tables.py) - its row is zeroed, lens = -1, and the caller tokenises it with the exact
+ *   string-level path (sprc_b200/tokenizer.py).  threads <= 0: one per core, at most 16. */
+typedef struct sprc_tokenizer sprc_tokenizer;
+int sprc_tokenizer_create(const char* vocab_utf8, int64_t vocab_bytes, sprc_tokenizer** out);
+void sprc_tokenizer_destroy(sprc_tokenizer* t);
+int sprc_tokenize_host(const sprc_tokenizer* t, const char* texts, const int64_t* offsets, int n, int max_len,
+                       int threads, int64_t* ids, int64_t* mask, int32_t* lens, uint8_t* complex_flags);
 
 #ifdef __cplusplus
 }

@@ -145,6 +145,13 @@ int sprc_topk_merge(sprc_handle*, const float* cand_score, const int32_t* cand_i
   return topk_merge(cand_score, cand_idx, P, Q, k, out_score, out_idx, S(stream));
 }
 
+int sprc_topk_merge_packed(sprc_handle*, const int32_t* cand, int P, int Q, int k, float* out_score, int32_t* out_idx,
+                           void* stream) {
+  if (!cand) return set_error(-22, "sprc_topk_merge_packed: null argument");
+  const size_t qk = static_cast<size_t>(Q) * k;
+  return topk_merge(reinterpret_cast<const float*>(cand), cand + qk, P, Q, k, out_score, out_idx, S(stream), 2 * qk);
+}
+
 int sprc_gather_scores(sprc_handle*, const void* queries, int Q, const void* gallery, int64_t N,
                        const int32_t* rows, int m, float* out, void* stream) {
   if (!queries || !gallery || !rows || !out) return set_error(-22, "sprc_gather_scores: null argument");

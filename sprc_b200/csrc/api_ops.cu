@@ -74,26 +74,6 @@ int sprc_op_gemm2w(const void* A, const void* W, const void* W2, int M, int m_sp
   return gemm_bf16_tcgen05(d, static_cast<cudaStream_t>(stream));
 }
 
-int sprc_op_gemm_ln(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int grp_rows, int grp_stride,
-                    const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
-                    float* out_f32, void* out_ln16, int ldc, void* stream) {
-  GemmDesc d;
-  d.A = static_cast<const bf16*>(A);
-  d.W = static_cast<const bf16*>(W);
-  d.M = M;
-  d.N = N;
-  d.K = K;
-  d.lda = lda;
-  d.ldw = ldw;
-  d.grp_rows = grp_rows;
-  d.grp_stride = grp_stride;
-  d.bias = bias;
-  d.residual = residual;
-  d.out_f32 = out_f32;
-  d.ldc = ldc;
-  return gemm_ln_tcgen05(d, gamma, beta, eps, static_cast<bf16*>(out_ln16), static_cast<cudaStream_t>(stream));
-}
-
 int sprc_preprocess_targetpad(const uint8_t* pixels, const int64_t* desc, const int32_t* tables, int n, int dim,
                               int max_rows, uint8_t* tmp, const float* mean3, const float* std3, float* out,
                               void* stream) {
@@ -135,50 +115,6 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
   a.key_mask = key_mask;
   a.scale = scale;
   return attention(a, static_cast<cudaStream_t>(stream));
-}
-
-int sprc_op_fold_weight(const void* W, const float* gamma, const float* beta, const float* bias, int N, int K,
-                        void* Wf, float* c, float* d, void* stream) {
-  return fold_weight(static_cast<const bf16*>(W), gamma, beta, bias, N, K, static_cast<bf16*>(Wf), c, d,
-                     static_cast<cudaStream_t>(stream));
-}
-
-int sprc_op_gemm_fold(const void* A, const void* W, const void* W2, int M, int m_split, int N, int K,
-                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
-                      const sprc_gemm_fold* fold, void* stream) {
-  if (!A || !W || !fold) return set_error(-22, "sprc_op_gemm_fold: null argument");
-  GemmFold f;
-  f.split = fold->split;
-  f.eps = fold->eps;
-  f.st_in = static_cast<const float2*>(fold->st_in);
-  f.st_in2 = static_cast<const float2*>(fold->st_in2);
-  f.c = fold->c;
-  f.c2 = fold->c2;
-  f.resid = fold->resid;
-  f.st_res = static_cast<const float2*>(fold->st_res);
-  f.st_res2 = static_cast<const float2*>(fold->st_res2);
-  f.res_g = fold->res_g;
-  f.res_b = fold->res_b;
-  f.res_g2 = fold->res_g2;
-  f.res_b2 = fold->res_b2;
-  f.st_out = static_cast<float2*>(fold->st_out);
-  f.st_out2 = static_cast<float2*>(fold->st_out2);
-  f.out16 = static_cast<bf16*>(fold->out16);
-  GemmDesc d;
-  d.A = static_cast<const bf16*>(A);
-  d.W = static_cast<const bf16*>(W);
-  d.W2 = static_cast<const bf16*>(W2);
-  d.M = M;
-  d.m_split = m_split;
-  d.N = d.ldc = N;
-  d.K = d.lda = d.ldw = K;
-  d.bias = bias;
-  d.bias2 = bias2;
-  d.act = act;
-  d.out_f32 = out_f32;
-  d.out_bf16 = static_cast<bf16*>(out_bf16);
-  d.fold = &f;
-  return gemm_bf16_tcgen05(d, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -57,39 +57,10 @@ struct Gemm2Params {
   const float* bias2;
 };
 
-// LayerNorm folding (GemmFold, common.h) is a separate instantiation: FOLD = 0 is the kernel every default path runs
-// and compiles to the same code as before the fold existed (FoldArg<0> is empty, all fold code is `if constexpr`).
-template <int FOLD>
-struct FoldArg {};
-template <>
-struct FoldArg<1> {
-  GemmFold f;
-};
-
-// Chan merge of the `parts` (mean, M2) partials of one row (64 elements each) -> mean, rstd.  Two passes over the
-// partials (the second one hits L1): `parts` is 12 for the Q-Former's 768-wide rows, 16 / 22 for ViT-L / ViT-g.
-__device__ __forceinline__ void fold_row_stats(const float2* __restrict__ st, int parts, float eps, float& mean,
-                                               float& rstd) {
-  float m = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < parts; ++i) m += __ldg(st + i).x;
-  m /= static_cast<float>(parts);
-  float m2 = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < parts; ++i) {
-    const float2 pt = __ldg(st + i);
-    const float dlt = pt.x - m;
-    m2 += pt.y + 64.0f * dlt * dlt;
-  }
-  mean = m;
-  rstd = rsqrtf(m2 / (64.0f * static_cast<float>(parts)) + eps);
-}
-
-template <int FOLD>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmC,
-                              const Gemm2Params p, const FoldArg<FOLD> fa) {
+                              const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -213,34 +184,6 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       const int m0 = (tile / p.num_n_blocks) * (2 * BM) + static_cast<int>(crank) * BM + q * 32;
       const int n0 = (tile % p.num_n_blocks) * BN + cpart * (BN / 4);
       const float* bias = (p.m_split > 0 && m0 >= p.m_split) ? p.bias2 : p.bias;
-      // ---- LayerNorm fold: per-row statistics of this thread's row (lane = row of the 32-row slab) ----
-      const float* f_c = nullptr;      // consumer: row sums of the folded weight
-      float f_mu = 0.f, f_rs = 1.f;    // consumer: statistics of the A row
-      bool f_prod = false, f_norm = false, f_rowok = false;
-      float f_rmu = 0.f, f_rrs = 1.f;  // producer: statistics of the residual row
-      const float* f_rg = nullptr;
-      const float* f_rb = nullptr;
-      float f_mean = 0.f, f_m2 = 0.f;  // producer: running statistics of the 64 output columns of this thread
-      if constexpr (FOLD) {
-        const GemmFold& f = fa.f;
-        const int row = m0 + lane;
-        f_rowok = row < p.M;
-        const bool hi = f.split > 0 && m0 >= f.split;
-        if (f.st_in) {
-          f_c = (p.m_split > 0 && m0 >= p.m_split) ? f.c2 : f.c;
-          const int parts = p.K >> 6;   // statistics of the A rows: one partial per 64 of their K columns
-          if (f_rowok) fold_row_stats((hi ? f.st_in2 : f.st_in) + (size_t)row * parts, parts, f.eps, f_mu, f_rs);
-        }
-        if (f.st_out) {
-          f_prod = true;
-          const float2* sr = hi ? f.st_res2 : f.st_res;
-          f_norm = sr != nullptr;
-          f_rg = hi ? f.res_g2 : f.res_g;
-          f_rb = hi ? f.res_b2 : f.res_b;
-          const int parts = p.N >> 6;   // residual / output rows are N wide
-          if (f_norm && f_rowok) fold_row_stats(sr + (size_t)row * parts, parts, f.eps, f_rmu, f_rrs);
-        }
-      }
       int c1 = m0, c2 = 0;
       if (p.grp_rows > 0) {
         c2 = m0 >> p.grp_shift;
@@ -258,69 +201,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         if (out32) {
           tmem_ld16(t_row + cc * 16, o);
           tmem_ld_wait();
-          bool produced = false;
-          if constexpr (FOLD) {
-            if (f_prod && live) {
-              // s' = acc + bias + LN(residual row) for 16 columns; raw 16-bit copy; running (mean, M2) of the thread's
-              // 64 columns.  The residual may alias the output: this warp reads its 32 x 16 block before its TMA store.
-              const GemmFold& f = fa.f;
-              const size_t off = (size_t)(m0 + lane) * p.N + n;   // rows of exactly N (ldc == N)
-              float v[16];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (f_rowok) x = *(reinterpret_cast<const float4*>(f.resid + off) + j);
-                if (f_norm) {
-                  const float4 g = __ldg(reinterpret_cast<const float4*>(f_rg + n) + j);
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(f_rb + n) + j);
-                  x.x = (x.x - f_rmu) * f_rrs * g.x + bb.x;
-                  x.y = (x.y - f_rmu) * f_rrs * g.y + bb.y;
-                  x.z = (x.z - f_rmu) * f_rrs * g.z + bb.z;
-                  x.w = (x.w - f_rmu) * f_rrs * g.w + bb.w;
-                }
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
-                v[4 * j] = __uint_as_float(o[4 * j]) + b.x + x.x;
-                v[4 * j + 1] = __uint_as_float(o[4 * j + 1]) + b.y + x.y;
-                v[4 * j + 2] = __uint_as_float(o[4 * j + 2]) + b.z + x.z;
-                v[4 * j + 3] = __uint_as_float(o[4 * j + 3]) + b.w + x.w;
-              }
-              float cs = 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cs += v[j];
-              const float cm = cs * (1.0f / 16.0f);
-              float cm2 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float dl = v[j] - cm;
-                cm2 += dl * dl;
-              }
-              if (cc == 0) {
-                f_mean = cm;
-                f_m2 = cm2;
-              } else {   // Chan: nA = 16 cc elements so far, nB = 16
-                const float na = 16.0f * cc, nt = na + 16.0f;
-                const float dl = cm - f_mean;
-                f_mean += dl * (16.0f / nt);
-                f_m2 += cm2 + dl * dl * (na * 16.0f / nt);
-              }
-              if (f_rowok) {
-                uint4* q16 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(f.out16) + off);
-                q16[0] = make_uint4(pack_act(v[0], v[1], p.fp16), pack_act(v[2], v[3], p.fp16),
-                                    pack_act(v[4], v[5], p.fp16), pack_act(v[6], v[7], p.fp16));
-                q16[1] = make_uint4(pack_act(v[8], v[9], p.fp16), pack_act(v[10], v[11], p.fp16),
-                                    pack_act(v[12], v[13], p.fp16), pack_act(v[14], v[15], p.fp16));
-                if (cc == nchunks - 1) {
-                  float2* so = (f.split > 0 && m0 >= f.split) ? f.st_out2 : f.st_out;
-                  so[(size_t)(m0 + lane) * (p.N >> 6) + (n0 >> 6)] = make_float2(f_mean, f_m2);
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[j]);
-              produced = true;
-            }
-          }
-          if (live && !produced) {
+          if (live) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -347,15 +228,6 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
               float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
               float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
-              if constexpr (FOLD) {
-                if (f_c) {   // out = rstd * (acc - mean * c) + d   (d arrives as the bias)
-                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(f_c + n) + j);
-                  v0 = f_rs * (__uint_as_float(r[4 * j]) - f_mu * c4.x) + b.x;
-                  v1 = f_rs * (__uint_as_float(r[4 * j + 1]) - f_mu * c4.y) + b.y;
-                  v2 = f_rs * (__uint_as_float(r[4 * j + 2]) - f_mu * c4.z) + b.z;
-                  v3 = f_rs * (__uint_as_float(r[4 * j + 3]) - f_mu * c4.w) + b.w;
-                }
-              }
               if (p.act == ACT_GELU) {
                 const float2 g0 = gelu_erf2(make_float2(v0, v1)), g1 = gelu_erf2(make_float2(v2, v3));
                 v0 = g0.x, v1 = g0.y, v2 = g1.x, v3 = g1.y;
@@ -484,44 +356,18 @@ int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  static bool attr_set[2] = {false, false};
-  if (d.fold) {
-    // LayerNorm fold (GemmFold): dense rows; the producer form writes whole rows (ldc == N, N a multiple of 64)
-    const GemmFold& f = *d.fold;
-    const bool prod = f.st_out != nullptr, cons = f.st_in != nullptr;
-    SPRC_REQUIRE(prod || cons, "gemm fold: neither st_in nor st_out is set");
-    SPRC_REQUIRE(d.grp_rows == 0 && !d.out_col_block && d.N % 64 == 0 && f.split % 32 == 0,
-                 "gemm fold: dense rows, N %% 64 == 0 and split %% 32 == 0 needed (N=%d split=%d)", d.N, f.split);
-    SPRC_REQUIRE(!cons || (f.c && d.bias && d.K % 64 == 0 && d.out_bf16 && (!d.W2 || (f.c2 && d.bias2)) &&
-                           (f.split == 0 || f.st_in2)),
-                 "gemm fold consumer: K %% 64 == 0, 16-bit output, c/d vectors for every weight set, st_in2 with a split");
-    SPRC_REQUIRE(!prod || (d.ldc == d.N && d.out_f32 && !d.residual && f.resid && f.out16 &&
-                           d.act == ACT_NONE && (f.split == 0 || f.st_out2) &&
-                           (!f.st_res || (f.res_g && f.res_b)) && (!f.st_res2 || (f.res_g2 && f.res_b2))),
-                 "gemm fold producer: ldc = N, fp32 output, no TMA residual, resid/out16/statistics set");
-    if (!attr_set[1]) {
-      SPRC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM_TOTAL));
-      attr_set[1] = true;
-    }
-    FoldArg<1> fa;
-    fa.f = f;
-    prof_begin(st);
-    SPRC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<1>, tmA, tmB, tmB2, tmC, p, fa));
-  } else {
-    if (!attr_set[0]) {
-      SPRC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM_TOTAL));
-      attr_set[0] = true;
-    }
-    prof_begin(st);
-    SPRC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<0>, tmA, tmB, tmB2, tmC, p, FoldArg<0>()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPRC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMEM_TOTAL));
+    attr_set = true;
   }
+  prof_begin(st);
+  SPRC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel, tmA, tmB, tmB2, tmC, p));
   if (prof_enabled()) {
     char tag[56];
-    snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d 2cta%s%s", d.M, d.N, d.K, d.grp_rows, d.act,
-             d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.W2 ? " w2" : "",
-             !d.fold ? "" : (d.fold->st_out ? " lnP" : " lnC"));
+    snprintf(tag, sizeof(tag), "M%d N%d K%d g%d a%d r%d f%d 2cta%s", d.M, d.N, d.K, d.grp_rows, d.act,
+             d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.W2 ? " w2" : "");
     prof_end(PROF_GEMM, 2.0 * d.M * (double)d.N * d.K,
              2.0 * ((double)d.M * d.K + (double)d.N * d.K) + (double)d.M * d.N * (d.out_f32 ? 4.0 : 2.0), st, tag);
   }

@@ -374,7 +374,6 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
   SPRC_CUDA(cudaGetLastError());
   SPRC_CUDA(cudaDeviceSynchronize());
   s.loaded = true;
-  fold_ready = vit_fold_ready = false;   // folded weights (ln_fold.cu) are derived from the loaded ones
   return 0;
 }
 
@@ -411,18 +410,10 @@ static int linear(const bf16* A, int M, int K, int lda, const bf16* W, int N, co
 }
 
 // dense + residual + LayerNorm of a post-LN Q-Former sublayer (Qformer.py:291-295, 373-381): x (fp32, in place) and
-// xb (16-bit copy) <- LayerNorm(A W^T + bias + x).  Default: GEMM with TMA reduce-add into x, then the LayerNorm
-// kernel.  SPRC_FUSED_LN=1 selects the single cluster kernel of gemm_ln.cu: bit-compatible (tests/test_ops_gpu.py)
-// and 44 % less HBM traffic per sublayer, but measured SLOWER on B200 (137 us against 71 + 53 us at M = 37888,
-// K = 768: its extra 64-byte TMA store requests land on the per-SM TMA request rate that already paces the 768-wide
-// GEMMs, profiles/r01c_gemm_ln_*), so it stays opt-in until the mainloop moves to CTA pairs.
-static bool fused_ln_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("SPRC_FUSED_LN");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
+// xb (16-bit copy) <- LayerNorm(A W^T + bias + x): GEMM with TMA reduce-add into x, then the LayerNorm kernel.
+// Two fused forms were built and measured slower on B200, then removed (profiles/r01c_gemm_ln_*, profiles/r02a_*:
+// a 3-CTA cluster kernel exchanging row statistics through DSMEM, and LayerNorm folded algebraically into the
+// neighbouring GEMMs' epilogues - LayerNorm 7.3 -> 0.8 ms per step but GEMMs 43.7 -> 61.2 ms).
 static bool dual_ffn_enabled() {
   static const bool on = [] {
     const char* e = getenv("SPRC_DUAL_FFN");   // SPRC_DUAL_FFN=0: separate launches for query-row and text-row FFNs
@@ -432,25 +423,8 @@ static bool dual_ffn_enabled() {
 }
 static int linear_ln(const bf16* A, int M, int K, int lda, const bf16* W, const float* bias, const float* gamma,
                      const float* beta, float eps, float* x, bf16* xb, int grp_rows, int grp_stride, cudaStream_t st) {
-  if (!fused_ln_enabled()) {
-    SPRC_TRY(linear(A, M, K, lda, W, 768, bias, ACT_NONE, x, x, nullptr, 768, grp_rows, grp_stride, st));
-    return layernorm(x, M, 768, gamma, beta, eps, grp_rows, grp_stride, x, xb, st);
-  }
-  GemmDesc d;
-  d.A = A;
-  d.W = W;
-  d.M = M;
-  d.N = 768;
-  d.K = K;
-  d.lda = lda;
-  d.ldw = K;
-  d.grp_rows = grp_rows;
-  d.grp_stride = grp_stride;
-  d.bias = bias;
-  d.residual = x;
-  d.out_f32 = x;
-  d.ldc = 768;
-  return gemm_ln_tcgen05(d, gamma, beta, eps, xb, st);
+  SPRC_TRY(linear(A, M, K, lda, W, 768, bias, ACT_NONE, x, x, nullptr, 768, grp_rows, grp_stride, st));
+  return layernorm(x, M, 768, gamma, beta, eps, grp_rows, grp_stride, x, xb, st);
 }
 
 int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_bf16, cudaStream_t st) {
@@ -462,9 +436,7 @@ int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_b
   SPRC_TRY(vit_assemble_tokens(patch_out, cls, pos, B, Dv, x, st));
   if (vit_kind == SPRC_VIT_CLIP_L) SPRC_TRY(layernorm(x, T, Dv, ln_pre_g, ln_pre_b, 1e-5f, 0, 0, x, nullptr, st));
   const float scale = 1.0f / sqrtf((float)dh);
-  const bool fold = vit_fold_usable();   // SPRC_LN_FOLD=1: norm1 / norm2 folded into the GEMMs (ln_fold.cu)
-  if (fold) SPRC_TRY(vit_blocks_fold(B, st));
-  for (int i = fold ? depth : 0; i < depth; ++i) {
+  for (int i = 0; i < depth; ++i) {
     const VitBlock& b = blocks[i];
     SPRC_TRY(layernorm(x, T, Dv, b.ln1_g, b.ln1_b, vit_eps, 0, 0, nullptr, xn, st));
     SPRC_TRY(linear(xn, T, Dv, Dv, b.qkv_w, 3 * Dv, b.qkv_b, ACT_NONE, nullptr, nullptr, qkv, 3 * Dv, 0, 0, st));
@@ -520,13 +492,7 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
   const int g = (S == 64) ? 32 : 0;  // row grouping for "first/last 32 rows of each 64-row sample"
   const int gs = (S == 64) ? 64 : 0;
   const int ldkv = n_cross * 1536;
-  int first_layer = 0;
-  if (S == 32 && with_enc && !kv_idx0 && !key_mask && kv_rows > 0 && fold_usable(B, 0)) {
-    // gallery pass with SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu), then the last layer here
-    SPRC_TRY(qformer_layers_ragged_fold(B, 0, true, Lk, nullptr, nullptr, st));
-    first_layer = qf_layers - 1;
-  }
-  for (int l = first_layer; l < qf_layers; ++l) {
+  for (int l = 0; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     // Rows whose output nobody reads are not computed in the LAST layer (their keys/values still are): the
     // fusion pass is consumed through its 32 query rows only (align_prompt.py:343 `fusion_output[:, :32]`,
@@ -692,12 +658,7 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
   float* x_cls = qt;
   bf16* ctx_cls = qcq;
   bf16* x_cls_b = qcq + (size_t)B * 768;
-  int first_layer = 0;
-  if (fold_usable(B, T8)) {   // SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu)
-    SPRC_TRY(qformer_layers_ragged_fold(B, T8, with_enc, Lk, kv_idx0, kv_idx1, st));
-    first_layer = qf_layers - 1;
-  }
-  for (int l = first_layer; l < qf_layers; ++l) {
+  for (int l = 0; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     const bool last = l == qf_layers - 1;
     SPRC_TRY(linear(qhb, rows_all, 768, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, nullptr, nullptr, qqkv, 2304, 0, 0, st));
@@ -744,7 +705,7 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
         SPRC_TRY(attention(c, st));
         SPRC_TRY(linear_ln(qctx, qrows, 768, 768, L.co_w, L.co_b, L.co_g, L.co_beta, 1e-12f, qh, qhb, 0, 0, st));
       }
-      if (!last && T8 > 0 && qrows % 256 == 0 && dual_ffn_enabled() && !fused_ln_enabled()) {
+      if (!last && T8 > 0 && qrows % 256 == 0 && dual_ffn_enabled()) {
         // both FFNs as ONE grid per GEMM: query rows read the *_query weights, text rows the text weights
         // (GemmDesc::W2) - a 27.9k-row launch instead of an 18.9k-row one plus a half-empty 9k-row one
         GemmDesc d;

@@ -73,12 +73,6 @@ int l2norm_rows256(const float* in, size_t in_row_stride, int rows, float* out_f
 int itm_head_prob(const float* h, int rows_per_pair, int pairs, const float* w, const float* b, float* p,
                   cudaStream_t st);
 
-// ---- ln_fold.cu ------------------------------------------------------------------------------
-// LayerNorm fold (GemmFold, common.h): Wf = round16(W diag(gamma)), c = row sums of Wf, d = W beta + bias
-bool ln_fold_enabled();
-int fold_weight(const bf16* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf,
-                float* c, float* d, cudaStream_t st);
-
 // ---- preprocess.cu ---------------------------------------------------------------------------
 // TargetPad + bicubic Resize + CenterCrop + ToTensor + Normalize (data_utils.py:52-72, 91-105) on decoded RGB uint8
 // images, bit-exact with PIL/torchvision; descriptors and coefficient tables come from sprc_b200/preprocess.py.
@@ -116,7 +110,7 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
              cudaStream_t st);
 size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full);
 int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, int k, float* out_score,
-               int32_t* out_idx, cudaStream_t st);
+               int32_t* out_idx, cudaStream_t st, size_t pstride = 0);   // pstride: elements between lists (0 = Q*k)
 int gather_scores(const bf16* queries, int Q, const bf16* gallery, int64_t N, const int32_t* rows, int m,
                   float* out, cudaStream_t st);
 

@@ -316,11 +316,12 @@ __device__ __forceinline__ void bitonic_sort_desc(u64* s, int n) {
 }
 
 // merge: for each query, P*k candidates -> top-k sorted.  Candidates are either packed keys laid out
-// [P][k][qpad] (from scan_topk_kernel / row_topk_kernel) or (score, idx) pairs [P][Q][k] (C ABI).
+// [P][k][qpad] (from scan_topk_kernel / row_topk_kernel) or (score, idx) pairs [P][Q][k] (C ABI), list p starting
+// `pstride` elements after list p - 1 (Q * k when dense; 2 * Q * k for the exchange buffer [P][2][Q][k]).
 __global__ void __launch_bounds__(1024)
 topk_merge_kernel(const u64* __restrict__ cand_keys, size_t qpad, const float* __restrict__ cand_score,
-                  const int32_t* __restrict__ cand_idx, int P, int Q, int k, int npow2, float* __restrict__ out_score,
-                  int32_t* __restrict__ out_idx) {
+                  const int32_t* __restrict__ cand_idx, size_t pstride, int P, int Q, int k, int npow2,
+                  float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
   extern __shared__ u64 skeys[];
   const int q = blockIdx.x;
   const int total = P * k;
@@ -331,7 +332,7 @@ topk_merge_kernel(const u64* __restrict__ cand_keys, size_t qpad, const float* _
       if (cand_keys) {
         key = cand_keys[(static_cast<size_t>(pp) * k + j) * qpad + q];
       } else {
-        const size_t o = (static_cast<size_t>(pp) * Q + q) * k + j;
+        const size_t o = static_cast<size_t>(pp) * pstride + static_cast<size_t>(q) * k + j;
         const int32_t idx = cand_idx[o];
         key = idx < 0 ? 0 : make_key(cand_score[o], static_cast<uint32_t>(idx));
       }
@@ -371,7 +372,8 @@ static int next_pow2(int v) {
 }
 
 static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int32_t* ci, int P, int Q, int k,
-                        float* out_score, int32_t* out_idx, cudaStream_t st) {
+                        float* out_score, int32_t* out_idx, cudaStream_t st, size_t pstride = 0) {
+  if (pstride == 0) pstride = static_cast<size_t>(Q) * k;
   const int np2 = next_pow2(P * k < 2 ? 2 : P * k);
   const size_t smem = static_cast<size_t>(np2) * 8;
   SPRC_REQUIRE(smem <= 200 * 1024, "topk_merge: %d candidates per query exceed the merge capacity", P * k);
@@ -381,7 +383,7 @@ static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int
     configured = 200 * 1024;
   }
   prof_begin(st);
-  topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, P, Q, k, np2, out_score, out_idx);
+  topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, pstride, P, Q, k, np2, out_score, out_idx);
   prof_end(PROF_MERGE, 0.0, (double)P * k * Q * 8, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
@@ -389,9 +391,9 @@ static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int
 }
 
 int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, int k, float* out_score,
-               int32_t* out_idx, cudaStream_t st) {
+               int32_t* out_idx, cudaStream_t st, size_t pstride) {
   SPRC_REQUIRE(P > 0 && Q > 0 && k > 0, "topk_merge: empty problem");
-  return launch_merge(nullptr, 0, cand_score, cand_idx, P, Q, k, out_score, out_idx, st);
+  return launch_merge(nullptr, 0, cand_score, cand_idx, P, Q, k, out_score, out_idx, st, pstride);
 }
 
 // workspace: candidate keys of the fused path, or [full matrix +] segment candidates of the large-k path

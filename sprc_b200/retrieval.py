@@ -183,19 +183,39 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
         local = torch.where((subset_rows >= index.lo) & (subset_rows < index.hi), local, torch.full_like(local, -1))
         sub = backend.gather_scores(fusion, index.feats, local.to(torch.int32))
     if world > 1:
-        cs = torch.empty(world, Q, k, dtype=torch.float32, device=dev)
-        ci = torch.empty(world, Q, k, dtype=torch.int32, device=dev)
-        # ONE exchange of candidates: scores and ids travel in one buffer (int32 ids bit-cast to fp32 lanes)
-        packed = torch.cat([sc.contiguous().view(torch.int32), ix.contiguous()], dim=1)
-        allp = torch.empty(world * Q, 2 * k, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allp, packed)  # rank-major concatenation along dim 0
-        allp = allp.view(world, Q, 2 * k)
-        cs.copy_(allp[:, :, :k].contiguous().view(torch.float32))
-        ci.copy_(allp[:, :, k:])
-        sc, ix = backend.topk_merge(cs, ci)
+        sc, ix = exchange_and_merge(backend, sc, ix, dist, rank, world)
         if sub is not None:
             dist.all_reduce(sub, op=dist.ReduceOp.MAX)  # non-owners hold -inf
     return sc, ix, sub
+
+
+def exchange_and_merge(backend, sc: torch.Tensor, ix: torch.Tensor, dist, rank: int, world: int):
+    """Per-shard candidates (sc fp32 / ix int32 [Q,k], identical query order on every rank) -> merged [Q,k] on every
+    rank.  ONE all-to-all of one packed buffer delivers to rank r only the candidates of ITS slice of the queries
+    (c = ceil(Q / world) queries, P lists of k), rank r merges those c queries, and one all-gather of the merged
+    [c, 2k] block makes the (small) result identical everywhere: bytes received per rank 2 * Q * k * 8, flat in the
+    number of ranks (an all-gather of all candidates + a replicated merge would be world * Q * k * 8 and Q merges)."""
+    Q, k = sc.shape
+    dev = sc.device
+    c = (Q + world - 1) // world
+    send = torch.empty(world, 2, c, k, dtype=torch.int32, device=dev)
+    send[:, 0] = torch.tensor(float("-inf")).view(torch.int32).item()      # padding queries: (-inf, -1)
+    send[:, 1] = -1
+    flat_s, flat_i = send[:, 0].reshape(world * c, k), send[:, 1].reshape(world * c, k)   # copies when strided
+    flat_s[:Q] = sc.contiguous().view(torch.int32)
+    flat_i[:Q] = ix
+    send[:, 0] = flat_s.view(world, c, k)
+    send[:, 1] = flat_i.view(world, c, k)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)                                       # recv[p] = rank p's lists for MY queries
+    if hasattr(backend, "topk_merge_packed"):
+        msc, mix = backend.topk_merge_packed(recv)
+    else:
+        msc, mix = backend.topk_merge(recv[:, 0].contiguous().view(torch.float32), recv[:, 1].contiguous())
+    mine = torch.cat([msc.contiguous().view(torch.int32), mix.to(torch.int32)], dim=1)       # [c, 2k]
+    allm = torch.empty(world * c, 2 * k, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(allm, mine.contiguous())
+    return allm[:Q, :k].contiguous().view(torch.float32), allm[:Q, k:].contiguous()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -84,15 +84,86 @@ def _fnv1a(s: str) -> int:
     return h
 
 
+def _find_cached_vocab():
+    """vocab.txt of bert-base-uncased in the local Hugging Face cache (what `BertTokenizer.from_pretrained` would read
+    offline), or None."""
+    roots = [os.environ.get("HF_HUB_CACHE"), os.path.join(os.environ.get("HF_HOME", ""), "hub") if os.environ.get(
+        "HF_HOME") else None, os.path.expanduser("~/.cache/huggingface/hub")]
+    for r in roots:
+        if not r:
+            continue
+        base = os.path.join(r, "models--bert-base-uncased", "snapshots")
+        if os.path.isdir(base):
+            for snap in sorted(os.listdir(base)):
+                f = os.path.join(base, snap, "vocab.txt")
+                if os.path.isfile(f):
+                    return f
+    return None
+
+
 class OfflineBertTokenizer:
-    def __init__(self, vocab_file: str | None = None, max_word_chars: int = 100):
-        vocab_file = vocab_file or os.environ.get("SPRC_BERT_VOCAB")
+    """vocab_file (or SPRC_BERT_VOCAB, or a bert-base-uncased vocab.txt found in the local Hugging Face cache): real
+    WordPiece ids.  synthetic=True (or SPRC_SYNTHETIC_VOCAB=1): the hashed stand-in vocabulary, an explicit opt-in for
+    tests and synthetic benchmarks.  With neither, tokenising a STRING raises (a real checkpoint must never be driven
+    with made-up ids); pre-tokenised `TokenBatch` input always passes through.
+    native=True: strings go through the threaded C++ tokenizer of libsprc_b200 (sprc_tokenize_host); captions it flags
+    as neighbour-dependent (combining marks, final sigma) take the Python path below, which is the same algorithm on
+    whole strings."""
+
+    def __init__(self, vocab_file: str | None = None, max_word_chars: int = 100, synthetic: bool | None = None,
+                 native: bool = True, threads: int = 0):
+        vocab_file = vocab_file or os.environ.get("SPRC_BERT_VOCAB") or None
+        if synthetic is None:
+            synthetic = os.environ.get("SPRC_SYNTHETIC_VOCAB") == "1"
+        if not vocab_file and not synthetic:
+            vocab_file = _find_cached_vocab()
         self.vocab = None
+        self.vocab_file = vocab_file
         if vocab_file:
             with open(vocab_file, encoding="utf-8") as f:
                 self.vocab = {tok.rstrip("\n"): i for i, tok in enumerate(f)}
+        self.synthetic = bool(synthetic) and self.vocab is None
         self.max_word_chars = max_word_chars
         self.bos_token_id = VOCAB_SIZE  # "[DEC]"
+        self.native = native
+        self.threads = threads
+        self._nat = None
+
+    def _require_vocab(self):
+        if self.vocab is None and not self.synthetic:
+            raise RuntimeError(
+                "no BERT vocabulary: pass vocab_file=... (or set SPRC_BERT_VOCAB) with bert-base-uncased's vocab.txt; "
+                "for synthetic runs opt in to the hashed stand-in vocabulary with synthetic=True / "
+                "SPRC_SYNTHETIC_VOCAB=1 (the reference downloads the vocabulary, blip2.py:30-34; there is no network "
+                "here)")
+
+    def _native_handle(self):
+        if self._nat is None:
+            import ctypes
+
+            from . import _lib as L
+
+            lib = L.load()
+            h = ctypes.c_void_p()
+            if self.vocab is None:
+                L.check(lib.sprc_tokenizer_create(None, 0, ctypes.byref(h)))
+            else:
+                with open(self.vocab_file, "rb") as f:
+                    blob = f.read()
+                if blob.endswith(b"\n"):
+                    blob = blob[:-1]
+                L.check(lib.sprc_tokenizer_create(blob, len(blob), ctypes.byref(h)))
+            self._nat = (lib, h)
+        return self._nat
+
+    def __del__(self):
+        nat = getattr(self, "_nat", None)
+        if nat is not None:
+            try:
+                nat[0].sprc_tokenizer_destroy(nat[1])
+            except Exception:
+                pass
+            self._nat = None
 
     def __len__(self) -> int:
         return VOCAB_SIZE + 1
@@ -101,10 +172,12 @@ class OfflineBertTokenizer:
     def _basic(self, text: str):
         cleaned = []
         for ch in text:
-            if ch in "\t\n\r" or ch.isspace():
+            if ch in " \t\n\r":
                 cleaned.append(" ")
-            elif ord(ch) in (0, 0xFFFD) or unicodedata.category(ch) in ("Cc", "Cf"):
-                continue
+            elif ord(ch) in (0, 0xFFFD) or unicodedata.category(ch).startswith("C"):
+                continue   # _clean_text / _is_control: every C* category (Cc, Cf, Cn, Co, Cs) except \t \n \r
+            elif ch.isspace():
+                cleaned.append(" ")   # _is_whitespace (Zs) and the separators str.split() also splits on
             elif _is_cjk(ch):
                 cleaned.append(" " + ch + " ")
             else:
@@ -167,11 +240,49 @@ class OfflineBertTokenizer:
             return text
         if isinstance(text, str):
             text = [text]
+        self._require_vocab()
         n = len(text)
+        if self.native and n > 0:
+            return self._call_native(text, max_length)
         ids = torch.zeros(n, max_length, dtype=torch.long)
         mask = torch.zeros(n, max_length, dtype=torch.long)
         for i, t in enumerate(text):
-            e = self.encode(t, max_length)
-            ids[i, : len(e)] = torch.tensor(e, dtype=torch.long)
-            mask[i, : len(e)] = 1   # by length, not by id: a literal "[PAD]" in the text is a live token
+            self._fill_row(ids, mask, i, t, max_length)
         return TokenBatch(ids, mask)
+
+    def _fill_row(self, ids, mask, i, t, max_length):
+        e = self.encode(t, max_length)
+        ids[i].zero_()
+        mask[i].zero_()
+        ids[i, : len(e)] = torch.tensor(e, dtype=torch.long)
+        mask[i, : len(e)] = 1   # by length, not by id: a literal "[PAD]" in the text is a live token
+
+    def _call_native(self, text, max_length, pin=False):
+        import numpy as np
+
+        from . import _lib as L
+
+        lib, h = self._native_handle()
+        n = len(text)
+        enc, py_rows = [], []
+        for i, t in enumerate(text):
+            try:
+                enc.append(t.encode("utf-8"))
+            except UnicodeEncodeError:      # lone surrogates: not representable, Python path
+                enc.append(b"")
+                py_rows.append(i)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=offs[1:])
+        blob = b"".join(enc)
+        ids = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
+        mask = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
+        lens = torch.empty(n, dtype=torch.int32)
+        flags = torch.empty(n, dtype=torch.uint8)
+        L.check(lib.sprc_tokenize_host(h, blob, offs.ctypes.data, n, max_length, self.threads, L.ptr(ids), L.ptr(mask),
+                                       L.ptr(lens), L.ptr(flags)))
+        for i in set(py_rows) | set(flags.nonzero().flatten().tolist()):
+            self._fill_row(ids, mask, i, text[i], max_length)
+            lens[i] = int(mask[i].sum())
+        out = TokenBatch(ids, mask)
+        out.lens = lens
+        return out

@@ -18,12 +18,12 @@ model = Blip2QformerCirAlignPrompt(vit_model="clip_L", device=dev, max_images=8,
 sd = synth.make_state_dict("clip_L", 1, 12, seed=0)
 model.load_state_dict(sd, strict=False)
 N = 2048
-raws = torch.randn(N, 257, 1024, device=dev).bfloat16()
+raws = torch.randn(N, 257, 1024, device=dev).to(model.act_torch_dtype)
 ids, mask = synth.make_token_ids(Bq, seed=1)
 lens = mask.sum(dim=1).to(torch.int32).contiguous()   # host: caption lengths for the ragged passes
 ids, mask = ids.to(dev), mask.to(dev)
 rows = torch.randint(0, N, (Bq,), dtype=torch.int32).to(dev)
-fusion = torch.empty(Bq, 256, device=dev, dtype=torch.bfloat16)
+fusion = torch.empty(Bq, 256, device=dev, dtype=model.act_torch_dtype)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(iters):
     e0.record()

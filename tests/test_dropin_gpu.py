@@ -23,7 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGED = os.path.join(ROOT, "baseline", "_ref", "src")
 DROPIN = os.path.join(ROOT, "sprc_b200", "dropin")
 DROPIN_FAST = os.path.join(ROOT, "sprc_b200", "dropin_fast")
-DEPTH_ENV = {"SPRC_VIT_DEPTH": "2", "SPRC_QF_LAYERS": "2", "SPRC_MAX_IMAGES": "64", "SPRC_MAX_QUERIES": "32"}
+# no bert-base-uncased vocabulary offline: the scripts' caption strings use the hashed stand-in vocabulary (explicit opt-in)
+DEPTH_ENV = {"SPRC_VIT_DEPTH": "2", "SPRC_QF_LAYERS": "2", "SPRC_MAX_IMAGES": "64", "SPRC_MAX_QUERIES": "32",
+             "SPRC_SYNTHETIC_VOCAB": "1"}
 
 N_GALLERY, N_QUERIES = 56, 16
 PLANT_RANKS = [1, 1, 1, 1, 3, 3, 4, 5, 7, 8, 9, 10, 20, 30, 40, 52]  # rank of the target AFTER reference removal
@@ -50,7 +52,8 @@ def staged_tree(tmp_path_factory):
     from sprc_b200.model import Blip2QformerCirAlignPrompt
 
     root = str(tmp_path_factory.mktemp("sprc_dropin"))
-    shutil.copytree(STAGED, os.path.join(root, "src"))
+    shutil.copytree(STAGED, os.path.join(root, "src"), ignore=shutil.ignore_patterns("lavis"))  # driver scripts only
+    os.environ["SPRC_SYNTHETIC_VOCAB"] = "1"
     rng = np.random.default_rng(0)
     names = [f"dev-{i:03d}-img{i % 3}" for i in range(N_GALLERY)]
     # ---- images: CIRR dev split + FashionIQ images (same pixels, two directory layouts) ----
