@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="composed queries per CPU step (reference arm) / per repetition of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rerank", action="store_true", help="skip the C5 rerank row")
+    ap.add_argument("--no-vitg", action="store_true", help="skip the EVA-ViT-g rows (C3 / C4 shapes, ViT-g index rate)")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the PyTorch-eager-on-this-GPU reference row")
     ap.add_argument("--act-dtype", default="fp16", choices=["bf16", "fp16"],
                     help="16-bit tensor-core operand format: fp16 (default) = the reference's own autocast precision and "
                          "the mode whose embeddings meet the 1e-3 parity bar; bf16 runs at the same speed "
@@ -277,6 +280,225 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# in-process checks and extra rows of our arm
+# ---------------------------------------------------------------------------------------------------
+def parity_check(model, dev, index_batch):
+    """Parity of THIS process's model (full-depth synthetic checkpoint, the benchmarked operand mode) against the
+    reference's own outputs in tests/golden/recall_full_L.pt (oracle/make_golden.py:run_recall_full: the unmodified
+    reference class, fp32, 256 structured images, 512 composed queries): embeddings (relative Frobenius), similarity
+    (max abs), Recall@K on the labels planted from the reference's ranking (stored in the file), and a bit-exact top-k
+    check of the scan kernel on dyadic inputs against torch's stable sort.  Reads a data file; no oracle code."""
+    from sprc_b200 import retrieval as RT
+    from sprc_b200 import synth
+
+    path = os.path.join(ROOT, "tests", "golden", "recall_full_L.pt")
+    if not os.path.exists(path):
+        return {"error": "tests/golden/recall_full_L.pt missing"}
+    g = torch.load(path)
+    c = g["case"]
+    if c["vit"] != model.vit_name:
+        return {"skipped": f"golden is {c['vit']}, bench model is {model.vit_name}"}
+    images = synth.make_structured_images(c["n_images"], seed=c["image_seed"])
+    f16, r16, f32, r32 = [], [], [], []
+    for s in range(0, c["n_images"], index_batch):
+        o = model.encode_gallery(images[s:s + index_batch].to(dev), want_f32=True, want_bf16=True, want_raws_f32=True,
+                                 want_raws_bf16=True)
+        f16.append(o["feats_bf16"]), r16.append(o["raws_bf16"]), f32.append(o["feats"][:4]), r32.append(o["raws"][:4])
+    feats, raws = torch.cat(f16), torch.cat(r16)
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm())  # noqa: E731
+    e_feats = rel(f32[0][:4], g["feats_rows"])
+    e_raws = rel(r32[0][:4][:, g["raw_rows"]], g["raws_rows"])
+    ids, mask, ref = g["input_ids"], g["attention_mask"], g["ref_rows"]
+    Q = ids.shape[0]
+    fusion = model.encode_query(raws, ids, mask, ref_rows=ref.to(dev))
+    sc, ix, full = model.sim_topk(fusion, feats, k=51, want_full=True)
+    sub = model.gather_scores(fusion, feats, g["members"].to(torch.int32))
+    torch.cuda.synchronize()
+    e_sim = float((full.cpu() - g["sim"]).abs().max())
+    rec = RT.cirr_recalls_from_topk(ix.cpu(), ref, g["target"], g["members"], sub.cpu())
+    rec_ref = tuple(float(x) for x in g["recalls_ref"])
+    d_rec = max(abs(a - b) for a, b in zip(rec, rec_ref))
+    # scan kernel, integer part: dyadic inputs (exact dot products) -> rows must equal torch's stable descending sort
+    gen = torch.Generator().manual_seed(3)
+    qd = (torch.randint(-4, 5, (160, 256), generator=gen).float() / 16).to(dev)
+    gd = (torch.randint(-4, 5, (3000, 32, 256), generator=gen).float() / 16).to(dev)
+    _, ixd, _ = model.sim_topk(qd.to(model.act_torch_dtype), gd.to(model.act_torch_dtype).contiguous(), k=50)
+    simd = torch.einsum("qd,ntd->qnt", qd, gd).max(dim=-1).values
+    want = torch.argsort(-simd, dim=1, stable=True)[:, :50]
+    tol_e, tol_r = 1e-3, 0.05
+    return {"golden": "tests/golden/recall_full_L.pt (the reference's own fp32 outputs: full-depth ViT-L + 12-layer "
+                      "Q-Former, %d structured images, %d composed queries)" % (c["n_images"], Q),
+            "dtype": model.act_dtype, "relF_raws": e_raws, "relF_feats": e_feats, "max_abs_dsim": e_sim,
+            "recalls_reference": rec_ref, "recalls_ours": tuple(float(x) for x in rec), "max_recall_delta": d_rec,
+            "label_margin": float(g["margin"]), "topk_bit_exact_dyadic": bool(torch.equal(ixd.long(), want)),
+            "tolerance": {"embeddings_rel": tol_e, "recall_abs": tol_r},
+            "pass": bool(e_raws < tol_e and e_feats < tol_e and e_sim < tol_e and d_rec <= tol_r
+                         and torch.equal(ixd.long(), want))}
+
+
+def rerank_probe(args, sd, raws, feats, dev, pk, clocks, R_=8, T_=100, steps=5):
+    """C5: pairs/s of `inference_rerank` for R_ queries x their top-T_ candidates from the resident index (per-image
+    cross-attention K/V hoisted out of the pair loop), CUDA events, max over nothing (per GPU; queries split over ranks
+    at N > 1 with no data-path collective)."""
+    from sprc_b200 import synth
+    from sprc_b200.model import Blip2QformerCirRerank
+
+    m = Blip2QformerCirRerank(vit_model=args.vit, device=dev, max_images=8, max_queries=R_, max_pairs=R_ * T_,
+                              act_dtype=args.act_dtype, vit_depth=1)
+    m.load_state_dict({k_: v for k_, v in sd.items()}, strict=False)
+    ids, mask = synth.make_token_ids(R_, seed=99)
+    n = raws.shape[0]
+    ref = torch.randint(0, n, (R_,), generator=torch.Generator().manual_seed(5)).to(torch.int32).to(dev)
+    fusion = m.encode_query(raws, ids, mask, ref_rows=ref)
+    _, cand, _ = m.sim_topk(fusion, feats, k=T_)
+    cand = cand.reshape(-1).contiguous()
+    for _ in range(2):
+        p = m.rerank_rows(raws, ref, cand, ids, mask, T_)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    a.record()
+    for _ in range(steps):
+        p = m.rerank_rows(raws, ref, cand, ids, mask, T_)
+    b.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = a.elapsed_time(b) / steps
+    naive = {"clip_L": 21.48e9, "eva_clip_g": 25.12e9}[args.vit]
+    hoisted = 11.8e9 * naive / 25.12e9 if args.vit == "clip_L" else 11.8e9
+    pairs_s = R_ * T_ / (ms / 1e3)
+    out = {"pairs_per_s_per_gpu": pairs_s, "reranked_queries_per_s_per_gpu": R_ / (ms / 1e3), "R": R_, "T": T_,
+           "ms_per_call": ms, "finite": bool(torch.isfinite(p).all()),
+           "tflops_reference_count": pairs_s * naive / 1e12, "tflops_executed_hoisted": pairs_s * hoisted / 1e12,
+           "frac_of_sustained_peak_executed": pairs_s * hoisted / 1e12 / pk["tf_sust"],
+           "clocks": clocks.window(t0, t1),
+           "note": "FLOPs per pair: the reference recomputes the K/V projection of all 514 image tokens for every pair "
+                   "(SURVEY 8d: %.2f GF); executed work after hoisting per-image K/V ~ %.1f GF" % (naive / 1e9,
+                                                                                                  hoisted / 1e9)}
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_gpu_rows(args, sd, feats, dev):
+    """SURVEY 8d "PyTorch eager on the same B200": the UNMODIFIED reference `inference` (+ argsort) with torch's stock
+    CUDA kernels, fp32 and under fp16 autocast, one reference-sized batch of 16 queries per step."""
+    rows = {}
+    try:
+        model = reference_model(args.vit, sd, device=str(dev))
+        if model is None:
+            return {"unavailable": "staged reference sources not found (baseline/_ref/src)"}
+        gal = feats.float()
+        for name, ac in (("fp32", False), ("fp16_autocast", True)):
+            qps, sec = reference_query_sample(model, args.vit, 16, gal, steps=3, warmup=1, device=str(dev), autocast=ac)
+            rows[name] = {"value": qps, "unit": UNIT, "s_per_batch_of_16": sec}
+        del model, gal
+        torch.cuda.empty_cache()
+    except Exception as e:  # the row is informative, never fatal
+        rows["error"] = f"{type(e).__name__}: {e}"[:300]
+    return rows
+
+
+def vitg_rows(args, world, rank, dev, pk, dist):
+    """BASELINE.json configs[2] / [3] with the EVA-ViT-g model (Dv 1408, 39 blocks): index-build rate, and the query job
+    of C3 (N = 1: 6 000 composed queries x 75 000-row gallery, batches of 2 000) or of C4's shape (N > 1: 200 000-row
+    gallery sharded row-wise over the ranks, the 6 000 queries split over them, all-to-all of candidates).  Gallery
+    features for the scan are synthetic unit-norm rows (SURVEY 8d allows that for scan-side measurements); reference
+    raw embeds come from images this model encodes.  Device-resident inputs, CUDA events, max over ranks."""
+    from sprc_b200 import _lib as L
+    from sprc_b200 import synth
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+
+    lib = L.load()
+    k, IB = args.k, 64
+    Qtot = 6000
+    nb = 3 if world == 1 else 1
+    Bq = Qtot // (nb * world)
+    n_rows = 75000 if world == 1 else 200000 // world
+    lo = 0 if world == 1 else rank * n_rows
+    m = Blip2QformerCirAlignPrompt(vit_model="eva_clip_g", device=dev, max_images=IB, max_queries=Bq,
+                                   act_dtype=args.act_dtype)
+    t0 = time.time()
+    sd = synth.make_state_dict("eva_clip_g", None, 12, seed=0)
+    assert m.load_state_dict(sd, strict=False).missing_keys == []
+    del sd
+    t_load = time.time() - t0
+    h, adt = m._h, m.act_torch_dtype
+    st = lambda: L.c_void_p(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
+    n_img = 1024
+    raws = torch.empty(n_img, 257, 1408, device=dev, dtype=adt)
+    ftmp = torch.empty(n_img, 32, 256, device=dev, dtype=adt)
+    img = torch.empty(IB, 3, 224, 224, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):                      # first pass warms up, second is timed
+        a.record()
+        for s in range(0, n_img, IB):
+            img.normal_(generator=gen).clamp_(-2.2, 2.2)
+            L.check(lib.sprc_encode_gallery(h, L.ptr(img), IB, None, L.ptr(ftmp[s:]), None, L.ptr(raws[s:]), st()))
+        b.record()
+        torch.cuda.synchronize()
+    ips = n_img / (a.elapsed_time(b) / 1e3)
+    feats = synth.make_gallery_features(n_rows, seed=99 + rank, device=dev, dtype=adt)
+    ids, lens, rows = [], [], []
+    for j in range(nb):
+        i_, m_ = synth.make_token_ids(Bq, seed=777 + 10 * rank + j)
+        ids.append(i_.to(dev))
+        lens.append(m_.sum(dim=1).to(torch.int32).contiguous())
+        rows.append(torch.randint(0, n_img, (Bq,), generator=torch.Generator().manual_seed(j + rank)).to(torch.int32).to(dev))
+    fusion = torch.empty(Bq, 256, device=dev, dtype=adt)
+    fusion_all = torch.empty(world * Bq, 256, device=dev, dtype=adt)
+    sc = torch.empty(Bq, k, device=dev)
+    ix = torch.empty(Bq, k, device=dev, dtype=torch.int32)
+    send = torch.empty(world, 2, Bq, k, device=dev, dtype=torch.int32)
+    recv = torch.empty_like(send)
+
+    def job():
+        for j in range(nb):
+            L.check(lib.sprc_encode_query_lens(h, L.ptr(raws), L.BF16, L.ptr(rows[j]), L.ptr(ids[j]), L.ptr(lens[j]), Bq,
+                                               None, L.ptr(fusion), st()))
+            if world == 1:
+                L.check(lib.sprc_sim_topk(h, L.ptr(fusion), Bq, L.ptr(feats), n_rows, 0, k, L.ptr(sc), L.ptr(ix), None,
+                                          st()))
+            else:
+                dist.all_gather_into_tensor(fusion_all, fusion)
+                for r in range(world):
+                    L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all[r * Bq:]), Bq, L.ptr(feats), n_rows, lo, k,
+                                              L.ptr(send[r, 0]), L.ptr(send[r, 1]), None, st()))
+                dist.all_to_all_single(recv, send)
+                L.check(lib.sprc_topk_merge_packed(h, L.ptr(recv), world, Bq, k, L.ptr(sc), L.ptr(ix), st()))
+
+    job()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        job()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        t = torch.tensor([ms, -ips], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ips = t[0].item(), -t[1].item()
+    ok = bool(torch.isfinite(sc).all() and (ix >= 0).all())
+    out = {"model": "eva_clip_g (1408 x 39 blocks), synthetic seed 0", "load_s": t_load,
+           "index_images_per_s_per_gpu": ips,
+           "index_frac_of_vit_gemm_roofline": ips * FLOP_PER_IMAGE["eva_clip_g"] / (pk["tf_sust"] * 1e12),
+           "config": ("C3: 6000 queries x 75000-row gallery, 1 GPU" if world == 1 else
+                      "C4 shape: 6000 queries x 200000-row gallery sharded row-wise over %d GPUs (%d rows each), "
+                      "one all-to-all of candidates" % (world, n_rows)),
+           "queries_per_s": Qtot / (ms / 1e3), "ms_per_6000_queries": ms, "results_finite": ok}
+    del m, raws, feats, ftmp
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def main():
@@ -301,8 +523,17 @@ def main():
     pk = peaks()
 
     Bq, k, N = args.batch, args.k, args.gallery
+    # caption STRINGS over the generated vocabulary (no bert-base-uncased offline): the library's C++ WordPiece
+    # tokenizer maps them back to exactly the ids the device-resident loop uses (checked below)
+    import tempfile
+
+    from sprc_b200.tokenizer import OfflineBertTokenizer
+
+    vocab = synth.make_vocab()
+    vocab_file = synth.write_vocab(os.path.join(tempfile.mkdtemp(prefix="sprc_vocab_"), "vocab.txt"))
     model = Blip2QformerCirAlignPrompt(vit_model=args.vit, device=dev, max_images=args.index_batch,
-                                       max_queries=Bq, act_dtype=args.act_dtype)
+                                       max_queries=Bq, act_dtype=args.act_dtype,
+                                       tokenizer=OfflineBertTokenizer(vocab_file))
     adt = model.act_torch_dtype
     sd = synth.make_state_dict(args.vit, None, 12, seed=0)
     assert model.load_state_dict(sd, strict=False).missing_keys == []
@@ -346,60 +577,76 @@ def main():
     ids_h = torch.empty(pool, Bq, 32, dtype=torch.int64).pin_memory()
     mask_h = torch.empty(pool, Bq, 32, dtype=torch.int64).pin_memory()
     rows_h = torch.empty(pool, Bq, dtype=torch.int32).pin_memory()
+    caps_pool = []
     for p_ in range(pool):
         i, m = synth.make_token_ids(Bq, seed=4321 + 100 * rank + p_)
         ids_h[p_], mask_h[p_] = i, m
+        caps_pool.append([" ".join(vocab[int(t)] for t in row[1:int(n_) - 1]) for row, n_ in zip(i.tolist(),
+                                                                                                  m.sum(dim=1).tolist())])
         rows_h[p_] = torch.randint(0, n_index, (Bq,), generator=torch.Generator().manual_seed(7 + 100 * rank + p_))
+    tb = model.tokenizer(caps_pool[0])
+    strings_equal_ids = bool(torch.equal(tb.input_ids, ids_h[0]) and torch.equal(tb.attention_mask, mask_h[0]))
+    assert strings_equal_ids, "the caption strings must tokenise to the ids of the device-resident loop"
     ids_d, mask_d, rows_d = ids_h.to(dev), mask_h.to(dev), rows_h.to(dev)
     # caption lengths stay on the host, where the tokenizer produced them (sprc_encode_query_lens)
     lens_h = mask_h.sum(dim=2).to(torch.int32).contiguous()
     ragged = os.environ.get("SPRC_RAGGED", "1") != "0"
     out_sc_h = torch.empty(Bq, k, dtype=torch.float32).pin_memory()
     out_ix_h = torch.empty(Bq, k, dtype=torch.int32).pin_memory()
-    out_sc_h2 = [torch.empty(Bq, k, dtype=torch.float32).pin_memory() for _ in range(2)]   # pipelined e2e: 2 in flight
-    out_ix_h2 = [torch.empty(Bq, k, dtype=torch.int32).pin_memory() for _ in range(2)]
-    # SPRC_E2E_PIPELINE=1: two batches in flight through _submit/_wait; measured equal to the serial call within noise
-    # (36.2-36.5k q/s both, profiles/r01l_*): the step is GPU-bound, there is no host bubble to hide
-    pipelined = os.environ.get("SPRC_E2E_PIPELINE", "0") == "1"
+    out_sc_h2 = [torch.empty(Bq, k, dtype=torch.float32).pin_memory() for _ in range(3)]   # pipelined e2e: 2 in flight
+    out_ix_h2 = [torch.empty(Bq, k, dtype=torch.int32).pin_memory() for _ in range(3)]
+    # end to end FROM STRINGS (what `inference` receives): batch i+1 is tokenised (C++ threads) and enqueued while the
+    # GPU works on batch i (two batches in flight through sprc_query_topk_strings_submit / sprc_query_topk_host_wait).
+    # SPRC_E2E_IDS=1: the round-1 path from pre-tokenised host ids (serial sprc_query_topk_host)
+    e2e_from_ids = os.environ.get("SPRC_E2E_IDS", "0") == "1"
     inflight = [0]
+    ids_stage = [torch.empty(Bq, 32, dtype=torch.int64).pin_memory() for _ in range(2)]    # N > 1: tokenizer output
+    mask_stage = [torch.empty(Bq, 32, dtype=torch.int64).pin_memory() for _ in range(2)]
+    lens_stage = [torch.empty(Bq, dtype=torch.int32) for _ in range(2)]
 
     fusion = torch.empty(Bq, 256, device=dev, dtype=adt)
     fusion_all = torch.empty(world * Bq, 256, device=dev, dtype=adt)
-    sc = torch.empty(world * Bq, k, device=dev)
-    ix = torch.empty(world * Bq, k, device=dev, dtype=torch.int32)
-    cand_sc = torch.empty(world, world * Bq, k, device=dev)
-    cand_ix = torch.empty(world, world * Bq, k, device=dev, dtype=torch.int32)
-    msc = torch.empty(world * Bq, k, device=dev)
-    mix = torch.empty(world * Bq, k, device=dev, dtype=torch.int32)
+    sc = torch.empty(Bq, k, device=dev)
+    ix = torch.empty(Bq, k, device=dev, dtype=torch.int32)
+    # N > 1: ONE exchange buffer [dest rank][scores | rows][Bq][k]; the scan of rank r's queries writes straight into
+    # slot r, one all-to-all delivers to every rank the `world` candidate lists of ITS OWN Bq queries, and each rank
+    # merges only those (sprc_topk_merge_packed reads the received buffer in place)
+    cand_send = torch.empty(world, 2, Bq, k, device=dev, dtype=torch.int32)
+    cand_recv = torch.empty(world, 2, Bq, k, device=dev, dtype=torch.int32)
+    msc = torch.empty(Bq, k, device=dev)
+    mix = torch.empty(Bq, k, device=dev, dtype=torch.int32)
 
-    def step_device(i):
+    def step_device(i, ids_src=None, lens_src=None, mask_src=None):
         p_ = i % pool
+        ids_ = ids_d[p_] if ids_src is None else ids_src
         if ragged:
-            L.check(lib.sprc_encode_query_lens(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]),
-                                               L.ptr(lens_h[p_]), Bq, None, L.ptr(fusion), st()))
+            L.check(lib.sprc_encode_query_lens(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_),
+                                               L.ptr(lens_h[p_] if lens_src is None else lens_src), Bq, None,
+                                               L.ptr(fusion), st()))
         else:
-            L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_d[p_]),
-                                          L.ptr(mask_d[p_]), Bq, None, L.ptr(fusion), st()))
+            L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_),
+                                          L.ptr(mask_d[p_] if mask_src is None else mask_src), Bq, None, L.ptr(fusion),
+                                          st()))
         if world == 1:
             L.check(lib.sprc_sim_topk(h, L.ptr(fusion), Bq, L.ptr(feats), n_local, 0, k, L.ptr(sc), L.ptr(ix), None,
                                       st()))
         else:
             dist.all_gather_into_tensor(fusion_all, fusion)
-            L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all), world * Bq, L.ptr(feats), n_local, lo, k, L.ptr(sc),
-                                      L.ptr(ix), None, st()))
-            dist.all_gather_into_tensor(cand_sc, sc)
-            dist.all_gather_into_tensor(cand_ix, ix)
-            L.check(lib.sprc_topk_merge(h, L.ptr(cand_sc), L.ptr(cand_ix), world, world * Bq, k, L.ptr(msc),
-                                        L.ptr(mix), st()))
+            for r in range(world):
+                L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all[r * Bq:]), Bq, L.ptr(feats), n_local, lo, k,
+                                          L.ptr(cand_send[r, 0]), L.ptr(cand_send[r, 1]), None, st()))
+            dist.all_to_all_single(cand_recv, cand_send)
+            L.check(lib.sprc_topk_merge_packed(h, L.ptr(cand_recv), world, Bq, k, L.ptr(msc), L.ptr(mix), st()))
+
+    ids_dev_stage = torch.empty(Bq, 32, dtype=torch.int64, device=dev)
+    mask_dev_stage = torch.empty(Bq, 32, dtype=torch.int64, device=dev)
 
     def step_host(i):
         p_ = i % pool
-        if world == 1 and pipelined:
-            # submit step i (H2D + kernels + D2H enqueued), THEN wait for step i-1: the host prepares and enqueues the
-            # next batch while the GPU works on the previous one; every step's copies are inside the timed region
-            L.check(lib.sprc_query_topk_host_submit(h, L.ptr(raws), L.ptr(feats), n_local, L.ptr(rows_h[p_]),
-                                                    L.ptr(ids_h[p_]), L.ptr(mask_h[p_]), Bq, k,
-                                                    L.ptr(out_sc_h2[i & 1]), L.ptr(out_ix_h2[i & 1]), st()))
+        if world == 1 and not e2e_from_ids:
+            # strings in: tokenise + enqueue step i (H2D + kernels + D2H), THEN wait for step i-1; every step's
+            # tokenisation and copies are inside the timed region
+            model.query_topk_strings_submit(raws, feats, rows_h[p_], caps_pool[p_], k, out_sc_h2[i % 3], out_ix_h2[i % 3])
             inflight[0] += 1
             if inflight[0] == 2:
                 L.check(lib.sprc_query_topk_host_wait(h))
@@ -409,12 +656,17 @@ def main():
                                              L.ptr(ids_h[p_]), L.ptr(mask_h[p_]), Bq, k, L.ptr(out_sc_h),
                                              L.ptr(out_ix_h), st()))
         else:
-            ids_d[p_].copy_(ids_h[p_], non_blocking=True)
-            mask_d[p_].copy_(mask_h[p_], non_blocking=True)
+            # strings in on every rank: C++ tokenizer into pinned staging, H2D, the device step (all-gather of query
+            # vectors, local scans, all-to-all of candidates, merge of this rank's queries), D2H of its top-k
+            s_ = i & 1
+            model.tokenizer.tokenize_into(caps_pool[p_], ids_stage[s_], mask_stage[s_], lens_stage[s_])
+            ids_dev_stage.copy_(ids_stage[s_], non_blocking=True)
+            if not ragged:
+                mask_dev_stage.copy_(mask_stage[s_], non_blocking=True)
             rows_d[p_].copy_(rows_h[p_], non_blocking=True)
-            step_device(i)
-            out_sc_h.copy_(msc[rank * Bq:(rank + 1) * Bq], non_blocking=True)
-            out_ix_h.copy_(mix[rank * Bq:(rank + 1) * Bq], non_blocking=True)
+            step_device(i, ids_src=ids_dev_stage, lens_src=lens_stage[s_], mask_src=mask_dev_stage)
+            out_sc_h.copy_(msc, non_blocking=True)
+            out_ix_h.copy_(mix, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
 
     def barrier():
@@ -465,7 +717,24 @@ def main():
     # the value/e2e gap is the host path and how much the power state of a longer run shows in this repeat
     ms_rep, _, _ = timed(step_device, K, W)
     value_repeat = world * Bq * K / (ms_rep / 1e3)
-    clocks.stop()
+
+    # ---- N > 1: the sharded pipeline must give what ONE GPU gives on the whole gallery (bit-exact, query sample) ----
+    sharded_equals_single = None
+    if world > 1 and N % world == 0:
+        step_device(0)
+        whole = torch.empty(N, 32, 256, device=dev, dtype=adt)
+        dist.all_gather_into_tensor(whole, feats)
+        nq = min(256, Bq)
+        sc1 = torch.empty(nq, k, device=dev)
+        ix1 = torch.empty(nq, k, device=dev, dtype=torch.int32)
+        L.check(lib.sprc_sim_topk(h, L.ptr(fusion), nq, L.ptr(whole), N, 0, k, L.ptr(sc1), L.ptr(ix1), None, st()))
+        torch.cuda.synchronize()
+        ok = torch.tensor([int(torch.equal(ix1, mix[:nq]) and torch.equal(sc1, msc[:nq]))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sharded_equals_single = bool(ok.item())
+        assert sharded_equals_single, "sharded scan + all-to-all + merge differs from the single-GPU scan"
+        del whole
+        torch.cuda.empty_cache()
 
     # ---- roofline: a second pass of the same K steps with per-launch CUDA events (library profiler) ----
     import ctypes
@@ -536,18 +805,53 @@ def main():
     breakdown = {"gemm_ms": gemm["ms"] / K, "attention_ms": attn["ms"] / K, "layernorm_ms": lnorm["ms"] / K,
                  "scan_ms": scan["ms"] / K, "merge_ms": merge["ms"] / K}
 
+    # ---- parity of this very model against the reference's golden outputs; rerank (C5) row ----
+    parity = parity_check(model, dev, args.index_batch) if rank == 0 else None
+    rerank = None
+    if not args.no_rerank:
+        rerank = rerank_probe(args, sd, raws, feats, dev, pk, clocks)
+        if world > 1:
+            t = torch.tensor([rerank["pairs_per_s_per_gpu"]], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            rerank["pairs_per_s_all_gpus"] = world * t.item()   # slowest rank x ranks: queries split contiguously
+    vitg = None
+    if not args.no_vitg and args.vit == "clip_L":
+        del cand_send, cand_recv
+        torch.cuda.empty_cache()
+        vitg = vitg_rows(args, world, rank, dev, pk, dist)
+    clocks.stop()
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
     cpu = None
+    eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import psutil
+
         cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
         gal_cpu = feats.float().cpu()
         t_cpu0 = time.perf_counter()
-        qps, sec = cpu_query_sample(args.vit, args.cpu_sample, gal_cpu, sd, steps=1, warmup=1, min_seconds=12.0)
-        cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"repetitions of {args.cpu_sample} composed queries (reference batch size 16) vs the same "
-                         f"{N}-row gallery for >= 12 s after one warm-up ({time.perf_counter() - t_cpu0:.1f} s in all), "
-                         f"fp32 torch restatement of the reference (oracle port) on {cores} host threads, "
-                         f"{sec:.2f} s per repetition"}
+        ref_model = reference_model(args.vit, sd)
+        if ref_model is not None:
+            nq = reference_batch_for_memory(N, 16, psutil.virtual_memory().available)
+            qps, sec = reference_query_sample(ref_model, args.vit, nq, gal_cpu, steps=1, warmup=1, min_seconds=12.0)
+            cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"repetitions of ONE reference-sized batch of {nq} composed queries (caption strings) "
+                             f"through the UNMODIFIED reference Blip2QformerCirAlignPrompt.inference (tokeniser, two "
+                             f"fp32 Q-Former passes, its broadcast matmul + max) + argsort(1 - sim).cpu() against the "
+                             f"same {N}-row gallery (our index as fp32) for >= 12 s after one warm-up "
+                             f"({time.perf_counter() - t_cpu0:.1f} s in all incl. model construction), torch CPU "
+                             f"eager on {cores} host threads, {sec:.2f} s per batch"}
+            del ref_model
+        else:
+            qps, sec = cpu_query_sample(args.vit, args.cpu_sample, gal_cpu, sd, steps=1, warmup=1, min_seconds=12.0)
+            cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"repetitions of {args.cpu_sample} composed queries (batch 16) vs the same {N}-row gallery "
+                             f"for >= 12 s, fp32 torch restatement (oracle port; staged reference sources not found) "
+                             f"on {cores} host threads, {sec:.2f} s per repetition"}
+        del gal_cpu
+        if not args.no_eager_gpu:
+            eager = eager_gpu_rows(args, sd, feats, dev)
 
     if world == 1 and ragged:
         # what sprc_query_topk_host* copies: ids int64 [Bq,32], ref rows int32 [Bq], the ragged row tables built from
@@ -555,12 +859,15 @@ def main():
         lp = lens_h[0].clamp_min(1).view(-1, 2).sum(dim=1) if Bq % 2 == 0 else lens_h[0].clamp_min(1)
         t8 = int(((lp + 7) // 8 * 8).sum())
         h2d_bytes = Bq * 32 * 8 + Bq * 4 + 4 * (3 * Bq + t8 + 4 * ((Bq + 1) // 2))
-        e2e_api = ("sprc_query_topk_host_submit/_wait, two batches in flight (pinned host ids/mask/ref rows -> top-k "
-                   "on host; batch i+1 is enqueued before batch i's results are awaited)" if pipelined else
-                   "sprc_query_topk_host (pinned host ids/mask/ref rows -> top-k on host)")
+        e2e_api = ("sprc_query_topk_host (pinned host ids/mask/ref rows -> top-k on host)" if e2e_from_ids else
+                   "model.query_topk_strings_submit / query_topk_host_wait = sprc_query_topk_strings_submit + "
+                   "sprc_query_topk_host_wait: caption STRINGS + host reference rows in (C++ WordPiece tokenizer "
+                   "inside the timed region), top-k on the host out; two batches in flight so batch i+1 is tokenised "
+                   "and enqueued while the GPU works on batch i")
     else:
-        h2d_bytes = world * Bq * (32 * 8 * 2 + 4)
-        e2e_api = "pinned host ids/mask/ref rows -> device step (all-gathers + merge) -> top-k rows of this rank on host"
+        h2d_bytes = world * (Bq * (32 * 8 * (1 if ragged else 2) + 4))
+        e2e_api = ("caption STRINGS -> C++ tokenizer -> pinned ids -> device step (all-gather of query vectors, local "
+                   "scans, ONE all-to-all of candidates, merge of this rank's queries) -> top-k rows of this rank on host")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -576,8 +883,8 @@ def main():
                                    "%s" % (float(lens_h.float().mean()),
                                            "query passes over live text rows only (ragged layout)" if ragged
                                            else "all 64 padded rows per query computed"),
-                       "layernorm": ("folded into the neighbouring GEMMs (SPRC_LN_FOLD=1, csrc/ln_fold.cu)"
-                                     if os.environ.get("SPRC_LN_FOLD") == "1" else "kernel per sublayer (default)")},
+                       "text": "e2e starts from caption strings over a generated 30 522-token vocabulary "
+                               "(strings_equal_ids: %s)" % strings_equal_ids},
             "clocks": clk,
             "value_repeat_after_e2e": value_repeat,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -593,6 +900,19 @@ def main():
                             "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (pk["tf_sust"] * 1e12),
                             "images_encoded_per_gpu": n_index, "launches": launches_index},
             "cpu_baseline": cpu,
+            "parity": parity,
+            "rerank": rerank,
+            "eager_gpu": eager,
+            "sharded_equals_single": sharded_equals_single,
+            "roofline_vit": {args.vit: {"images_per_s_per_gpu": index_ips,
+                                        "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (
+                                            pk["tf_sust"] * 1e12)},
+                             **({"eva_clip_g": {"images_per_s_per_gpu": vitg["index_images_per_s_per_gpu"],
+                                                "frac_of_vit_gemm_roofline": vitg["index_frac_of_vit_gemm_roofline"]}}
+                                if vitg else {}),
+                             "note": "images/s x the reference's FLOPs per image (ViT + Q-Former gallery pass, SURVEY "
+                                     "8d) / sustained bf16 peak"},
+            "vit_g": vitg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -149,6 +149,17 @@ int sprc_query_topk_host_submit(sprc_handle* h, const void* raws_bf16, const voi
                                 const int64_t* attention_mask_host, int Bq, int k, float* out_score_host,
                                 int32_t* out_idx_host, void* stream);
 int sprc_query_topk_host_wait(sprc_handle* h);
+/* The same step from caption STRINGS, as `inference` receives them (align_prompt.py:312-329: text is list[str],
+ * tokenised inside the call): the batch is tokenised by `tok` (sprc_tokenize_host, `threads` workers) straight into
+ * pinned staging owned by the handle, then submitted like sprc_query_topk_host_submit; pair with
+ * sprc_query_topk_host_wait.  While the GPU works on batch i the host tokenises batch i+1.  texts / offsets as in
+ * sprc_tokenize_host; ref_rows_host is copied before returning.  Returns -84 if a caption needs the string-level
+ * host path (nothing is submitted then). */
+typedef struct sprc_tokenizer sprc_tokenizer;
+int sprc_query_topk_strings_submit(sprc_handle* h, const sprc_tokenizer* tok, const void* raws_bf16,
+                                   const void* gallery_bf16, int64_t N, const int32_t* ref_rows_host, const char* texts,
+                                   const int64_t* offsets, int Bq, int k, int threads, float* out_score_host,
+                                   int32_t* out_idx_host, void* stream);
 
 /* Number of kernels this library has launched on behalf of the calling process (bench `gpu_launches`). */
 int64_t sprc_launch_count(void);
@@ -209,7 +220,6 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
  *   1 = the caption holds a character whose normalisation depends on its neighbours (combining marks, final sigma;
  *   tools/gen_unicode_tables.py) - its row is zeroed, lens = -1, and the caller tokenises it with the exact
  *   string-level path (sprc_b200/tokenizer.py).  threads <= 0: one per core, at most 16. */
-typedef struct sprc_tokenizer sprc_tokenizer;
 int sprc_tokenizer_create(const char* vocab_utf8, int64_t vocab_bytes, sprc_tokenizer** out);
 void sprc_tokenizer_destroy(sprc_tokenizer* t);
 int sprc_tokenize_host(const sprc_tokenizer* t, const char* texts, const int64_t* offsets, int n, int max_len,

@@ -151,12 +151,91 @@ def run_spread(name="spread_L"):
     return out
 
 
+def run_recall_full(name="recall_full_L", n_images=256, n_queries=512, n_rerank=(2, 16)):
+    """Full-depth pins: (i) the reference's own `inference` similarity [512, 256] with the FULL ViT-L (23
+    blocks) and the full 12-layer Q-Former on the standard synthetic checkpoint, structured images
+    (synth.make_structured_images: similarities spread over ~0.2), 512 composed queries; the GPU test plants labels
+    from THIS matrix with margins (restatement.plant_targets_with_margin) and compares Recall@K; (ii) the reference's
+    own `inference_rerank` probabilities for R = 2 queries x T = 16 candidates at the same full depth."""
+    t0 = time.time()
+    cfg = dict(vit="clip_L", vit_depth=None, qf_layers=12, n_images=n_images, n_queries=n_queries, image_seed=2468)
+    sd = synth.make_state_dict(cfg["vit"], None, 12, seed=0)
+    model = ref_loader.build_reference_model(cfg["vit"], seed=0)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys
+    images = synth.make_structured_images(n_images, seed=cfg["image_seed"])
+    ids, mask = synth.make_token_ids(n_queries, seed=4321)
+    ref_rows = torch.randint(0, n_images, (n_queries,), generator=torch.Generator().manual_seed(7))
+    feats, raws = [], []
+    with torch.no_grad():
+        for s in range(0, n_images, 64):                                      # utils.py:54 batch size
+            f, r = model.extract_target_features(images[s:s + 64])
+            feats.append(f)
+            raws.append(r)
+            print(f"[golden] {name}: indexed {s + 64}/{n_images} ({time.time() - t0:.0f}s)", flush=True)
+        feats, raws = torch.vstack(feats), torch.vstack(raws)
+        sim = torch.cat([ref_loader.call_inference(model, raws[ref_rows[i:i + 32]], feats, ids[i:i + 32],
+                                                   mask[i:i + 32]).reshape(-1, n_images)
+                         for i in range(0, n_queries, 32)])                    # validate_blip.py:373 batch size
+    out = dict(case=dict(cfg, name=name, seed=0), sim=sim.clone(), ref_rows=ref_rows, input_ids=ids, attention_mask=mask,
+               feats_rows=feats[:4].clone(), raws_rows=raws[:4][:, RAW_ROWS].clone(), raw_rows=RAW_ROWS)
+    torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"[golden] {name}: sim {tuple(sim.shape)} range [{sim.min():.3f}, {sim.max():.3f}] per-query std "
+          f"{sim.std(dim=1).mean():.3e} in {time.time() - t0:.0f}s", flush=True)
+    return finish_recall_full(name, n_rerank=n_rerank, raws=raws)
+
+
+def finish_recall_full(name="recall_full_L", n_rerank=(2, 16), margin=2e-3, itm_scale=0.1, raws=None):
+    """Second half of `run_recall_full` (can be re-run on an existing file): labels planted from the reference's
+    similarity with margin 2e-3 = twice the north star's embedding tolerance (restatement.plant_targets_with_margin),
+    the reference's recalls on them, and the full-depth `inference_rerank` probabilities.  The rerank part scales
+    itm_head.weight by `itm_scale` (recorded in the case): at the checkpoint's 0.2-std head every probability saturates
+    above 0.9 and a comparison of p would be blind to logit errors."""
+    from . import restatement as R
+
+    t0 = time.time()
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    out = torch.load(path)
+    cfg = out["case"]
+    sim, ref_rows, ids, mask = out["sim"], out["ref_rows"], out["input_ids"], out["attention_mask"]
+    target, ranks, members = R.plant_targets_with_margin(sim, ref_rows, margin)
+    out.update(target=target, ranks=ranks, members=members, margin=margin,
+               recalls_ref=torch.tensor(R.cirr_recalls(R.ranking(sim), ref_rows, target, members)))
+    R_, T_ = n_rerank
+    order = torch.argsort(1 - sim[:R_], dim=-1)
+    cand_rows = order[:, :T_].reshape(-1)                                      # each query's own top-T, as the drivers do
+    sd = synth.make_state_dict(cfg["vit"], None, 12, seed=0)
+    sd["itm_head.weight"] = sd["itm_head.weight"] * itm_scale
+    rr_model = ref_loader.build_reference_model(cfg["vit"], seed=0, kind="rerank")
+    rr_model.load_state_dict(sd, strict=False)
+    need = torch.cat([ref_rows[:R_], cand_rows])
+    uniq, inv = torch.unique(need, return_inverse=True)
+    with torch.no_grad():
+        if raws is None:
+            images = synth.make_structured_images(cfg["n_images"], seed=cfg["image_seed"])
+            _, table = rr_model.extract_target_features(images[uniq])
+        else:
+            table = raws[uniq]
+        p = rr_model.inference_rerank(table[inv[:R_]], table[inv[R_:]], ref_loader.TokenBatch(ids[:R_], mask[:R_]))
+    out["case"] = dict(cfg, itm_scale=itm_scale)
+    out["rerank"] = dict(R=R_, T=T_, ref_rows=ref_rows[:R_].clone(), cand_rows=cand_rows.clone(), p=p.clone())
+    torch.save(out, path)
+    print(f"[golden] {name}: planted ranks hist {torch.bincount(ranks.clamp_max(60))[:12].tolist()}..., recalls_ref "
+          f"{[round(float(x), 2) for x in out['recalls_ref']]}; rerank p {p.min():.3f}..{p.max():.3f} "
+          f"(spread {p.std():.3e}) in {time.time() - t0:.0f}s", flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tiny_L_cat", "spread_L"])
+    names = sys.argv[1:] or (list(CASES) + ["tiny_L_cat", "spread_L", "recall_full_L"])
     for n in names:
         if n == "tiny_L_cat":
             run_cat()
         elif n == "spread_L":
             run_spread()
+        elif n == "recall_full_L":
+            run_recall_full()
+        elif n == "recall_full_L:finish":
+            finish_recall_full()
         else:
             run_case(n, CASES[n])

@@ -271,6 +271,63 @@ def plant_targets(order, reference_idx, seed=11):
     return target, ranks, members
 
 
+def plant_targets_with_margin(sim, reference_idx, margin, seed=11, cutoffs=(1, 5, 10, 50)):
+    """`plant_targets` on an oracle SIMILARITY matrix, with every label planted where the oracle's own ranking is
+    robust: after the reference is removed, the target's score differs by >= `margin` from the score of the item on
+    the other side of every cut-off K (the item at rank K+1 if the target is inside the top K, the item at rank K if
+    it is outside), and from the scores of the 4 other group members.  With margin = 2 x the embedding tolerance two
+    implementations whose similarities agree to that tolerance MUST produce identical hit/miss decisions, so
+    "Recall@K within +-0.05" is testable as written; ranks keep the 20/50/70/95 % bands of `plant_targets`.
+    Returns (target_idx [Q], ranks [Q], group_members [Q,6])."""
+    g = torch.Generator().manual_seed(seed)
+    order = ranking(sim)
+    Q, N = order.shape
+    hi = min(100, N - 1)
+    bands = [(1, 1, .2), (2, 5, .3), (6, 10, .2), (11, min(50, hi), .25), (min(51, hi), hi, .05)]
+    keep = order != reference_idx[:, None]
+    ranked = order[keep].view(Q, N - 1)
+    s_ranked = torch.gather(sim, 1, ranked)
+
+    def robust(j, r):   # r 1-based
+        st = float(s_ranked[j, r - 1])
+        for K in cutoffs:
+            if K >= N - 1:
+                continue
+            if r <= K and st - float(s_ranked[j, K]) < margin:
+                return False
+            if r > K and float(s_ranked[j, K - 1]) - st < margin:
+                return False
+        return True
+
+    target = torch.empty(Q, dtype=torch.long)
+    ranks = torch.empty(Q, dtype=torch.long)
+    members = torch.empty(Q, 6, dtype=torch.long)
+    for j in range(Q):
+        chosen = None
+        for _ in range(64):
+            u, acc = float(torch.rand(1, generator=g)), 0.0
+            for lo, up, p in bands:
+                acc += p
+                if u < acc or (lo, up, p) == bands[-1]:
+                    cand = [r for r in torch.randperm(up - lo + 1, generator=g).add(lo).tolist() if robust(j, r)]
+                    if cand:
+                        chosen = cand[0]
+                    break
+            if chosen is not None:
+                break
+        if chosen is None:
+            raise RuntimeError(f"query {j}: no rank with margin {margin} at every cut-off")
+        ranks[j] = chosen
+        target[j] = ranked[j, chosen - 1]
+        st = float(s_ranked[j, chosen - 1])
+        others = [int(x) for x in torch.randperm(N, generator=g)
+                  if int(x) not in (int(reference_idx[j]), int(target[j])) and abs(float(sim[j, int(x)]) - st) >= margin][:4]
+        if len(others) < 4:
+            raise RuntimeError(f"query {j}: fewer than 4 group members with margin {margin}")
+        members[j] = torch.tensor([int(reference_idx[j]), int(target[j])] + others)
+    return target, ranks, members
+
+
 def target_ranks(sim, reference_idx, target_idx):
     """1-based rank of each query's target in argsort(1 - sim) after the reference row is removed."""
     order = ranking(sim)

@@ -91,6 +91,11 @@ SIGNATURES = {
          c_void_p],
     ),
     "sprc_query_topk_host_wait": (c_int, [c_void_p]),
+    "sprc_query_topk_strings_submit": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_char_p, c_void_p, c_int, c_int, c_int, c_void_p,
+         c_void_p, c_void_p],
+    ),
     "sprc_launch_count": (c_int64, []),
     "sprc_set_act_dtype": (c_int, [c_int]),
     "sprc_profile": (c_int, [c_int]),

@@ -16,6 +16,8 @@ struct sprc_handle {
   static constexpr int kInflight = 4;
   cudaEvent_t done[kInflight] = {nullptr, nullptr, nullptr, nullptr};
   unsigned submitted = 0, awaited = 0;
+  // sprc_query_topk_strings_submit: pinned ids / mask / reference-row staging, one slot per batch in flight
+  int64_t* tok_stage[kInflight] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -64,6 +66,8 @@ void sprc_destroy(sprc_handle* h) {
   if (!h) return;
   for (cudaEvent_t ev : h->done)
     if (ev) cudaEventDestroy(ev);
+  for (int64_t* p : h->tok_stage)
+    if (p) cudaFreeHost(p);
   delete h;
 }
 
@@ -221,6 +225,35 @@ int sprc_query_topk_host_submit(sprc_handle* h, const void* raws_bf16, const voi
   SPRC_CUDA(cudaEventRecord(ev, st));
   ++h->submitted;
   return 0;
+}
+
+int sprc_query_topk_strings_submit(sprc_handle* h, const sprc_tokenizer* tok, const void* raws_bf16,
+                                   const void* gallery_bf16, int64_t N, const int32_t* ref_rows_host, const char* texts,
+                                   const int64_t* offsets, int Bq, int k, int threads, float* out_score_host,
+                                   int32_t* out_idx_host, void* stream) {
+  if (!h || !tok || !texts || !offsets || !ref_rows_host)
+    return set_error(-22, "sprc_query_topk_strings_submit: null argument");
+  if (h->submitted - h->awaited >= (unsigned)sprc_handle::kInflight)
+    return set_error(-11, "sprc_query_topk_strings_submit: %d batches already in flight, call _wait first",
+                     sprc_handle::kInflight);
+  Model& m = h->m;
+  SPRC_REQUIRE(Bq > 0 && Bq <= m.max_queries, "sprc_query_topk_strings: Bq=%d outside (0, %d]", Bq, m.max_queries);
+  // the slot's previous batch (submitted - kInflight) has been awaited, so its H2D copies are done
+  int64_t*& stage = h->tok_stage[h->submitted % sprc_handle::kInflight];
+  const size_t row = (size_t)m.max_queries * 32;
+  if (!stage) SPRC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&stage), (2 * row + m.max_queries) * 8, cudaHostAllocDefault));
+  int64_t* ids = stage;
+  int64_t* mask = stage + row;
+  int32_t* rows = reinterpret_cast<int32_t*>(stage + 2 * row);
+  std::vector<uint8_t> flags((size_t)Bq);
+  SPRC_TRY(sprc_tokenize_host(tok, texts, offsets, Bq, 32, threads, ids, mask, nullptr, flags.data()));
+  for (int i = 0; i < Bq; ++i)
+    if (flags[i])
+      return set_error(-84, "sprc_query_topk_strings: caption %d holds neighbour-dependent characters (combining "
+                            "marks / final sigma); tokenise this batch on the host and use sprc_query_topk_host_submit", i);
+  for (int i = 0; i < Bq; ++i) rows[i] = ref_rows_host[i];   // the caller's buffer need not outlive this call
+  return sprc_query_topk_host_submit(h, raws_bf16, gallery_bf16, N, rows, ids, mask, Bq, k, out_score_host,
+                                     out_idx_host, stream);
 }
 
 int sprc_query_topk_host_wait(sprc_handle* h) {

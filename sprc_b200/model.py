@@ -314,6 +314,47 @@ class Blip2QformerCirAlignPrompt:
     def query_topk_host_wait(self):
         L.check(self._lib.sprc_query_topk_host_wait(self._h))
 
+    def query_topk_strings_submit(self, raws_bf16, gallery_bf16, ref_rows_host, captions, k, out_score_host,
+                                  out_idx_host):
+        """One end-to-end step from caption STRINGS (what `inference` receives, align_prompt.py:312-329): the C++
+        tokenizer fills pinned staging inside the library while earlier batches run on the GPU, then the batch is
+        enqueued (H2D, fusion, scan, top-k, D2H).  Pair with `query_topk_host_wait`.  A batch holding a caption the C++
+        tokenizer hands back (combining marks, final sigma) is tokenised here and submitted from ids."""
+        import numpy as np
+
+        tok = self.tokenizer
+        if not hasattr(tok, "_native_handle"):
+            raise L.SprcError("query_topk_strings needs the library tokenizer (sprc_b200.tokenizer.OfflineBertTokenizer)")
+        tok._require_vocab()
+        _, th = tok._native_handle()
+        n = len(captions)
+        try:
+            enc = [c.encode("utf-8") for c in captions]
+        except UnicodeEncodeError:
+            enc = None
+        rc = -84
+        if enc is not None:
+            offs = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([len(e) for e in enc], out=offs[1:])
+            with torch.cuda.device(self._device):
+                rc = self._lib.sprc_query_topk_strings_submit(
+                    self._h, th, L.ptr(raws_bf16), L.ptr(gallery_bf16), gallery_bf16.shape[0], L.ptr(ref_rows_host),
+                    b"".join(enc), offs.ctypes.data, n, k, tok.threads, L.ptr(out_score_host), L.ptr(out_idx_host),
+                    self._stream())
+        if rc == -84:
+            b = tok(list(captions), max_length=self.max_txt_len)
+            keep = getattr(self, "_strings_keepalive", [])
+            ids, mask = b.input_ids.pin_memory(), b.attention_mask.pin_memory()
+            self._strings_keepalive = (keep + [(ids, mask)])[-8:]     # host buffers must outlive the async copies
+            return self.query_topk_host_submit(raws_bf16, gallery_bf16, ref_rows_host, ids, mask, k, out_score_host,
+                                               out_idx_host)
+        L.check(rc)
+
+    def query_topk_strings(self, raws_bf16, gallery_bf16, ref_rows_host, captions, k, out_score_host, out_idx_host):
+        self.query_topk_strings_submit(raws_bf16, gallery_bf16, ref_rows_host, captions, k, out_score_host,
+                                       out_idx_host)
+        self.query_topk_host_wait()
+
     # ------------------------------------------------------------------ the reference's method surface
     def _tokenize(self, text):
         if isinstance(text, TokenBatch):

@@ -185,3 +185,18 @@ def make_captions(n: int, seed: int = 4321, vocab=None):
     vocab = vocab or make_vocab()
     ids, mask = make_token_ids(n, seed)
     return [" ".join(vocab[int(t)] for t in row[1:int(m.sum()) - 1]) for row, m in zip(ids, mask)]
+
+
+def make_structured_images(n: int, seed: int = 2468):
+    """Images with low-frequency content (per image a random 1x1 / 2x2 / 4x4 colour-block field, nearest-upsampled,
+    plus 30 % pixel noise), clamped to the post-Normalize range.  White-noise images (`make_images`) all look alike
+    to a randomly initialised ViT (similarities of a query to the whole gallery spread by 6e-3); these spread them by
+    3e-2 at the same numerical noise, which is what a Recall@K comparison needs (tests/golden/recall_full_L.pt)."""
+    g = torch.Generator().manual_seed(seed)
+    out = torch.empty(n, 3, 224, 224)
+    for i in range(n):
+        cells = (1, 2, 4)[int(torch.randint(0, 3, (1,), generator=g))]
+        low = torch.randn(1, 3, cells, cells, generator=g)
+        up = torch.nn.functional.interpolate(low, size=(224, 224), mode="nearest")
+        out[i] = (up[0] * 1.54 + 0.3 * torch.randn(3, 224, 224, generator=g)).clamp_(-2.2, 2.2)
+    return out

@@ -257,7 +257,20 @@ class OfflineBertTokenizer:
         ids[i, : len(e)] = torch.tensor(e, dtype=torch.long)
         mask[i, : len(e)] = 1   # by length, not by id: a literal "[PAD]" in the text is a live token
 
-    def _call_native(self, text, max_length, pin=False):
+    def tokenize_into(self, text, ids: torch.Tensor, mask: torch.Tensor, lens: torch.Tensor | None = None):
+        """Tokenise `text` (list of n strings) straight into caller-owned HOST buffers: ids / mask int64 [n, max_len]
+        (e.g. the pinned staging buffers of `query_topk_host_submit`), lens int32 [n] (optional).  C++ threads; no
+        allocation of the big buffers per call."""
+        self._require_vocab()
+        n, max_length = ids.shape
+        assert len(text) == n and mask.shape == ids.shape and ids.dtype == mask.dtype == torch.int64
+        assert ids.is_contiguous() and mask.is_contiguous() and ids.device.type == "cpu"
+        out = self._call_native(text, max_length, ids=ids, mask=mask)
+        if lens is not None:
+            lens.copy_(out.lens)
+        return out
+
+    def _call_native(self, text, max_length, pin=False, ids=None, mask=None):
         import numpy as np
 
         from . import _lib as L
@@ -274,8 +287,9 @@ class OfflineBertTokenizer:
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum([len(e) for e in enc], out=offs[1:])
         blob = b"".join(enc)
-        ids = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
-        mask = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
+        if ids is None:
+            ids = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
+            mask = torch.empty(n, max_length, dtype=torch.long, pin_memory=pin)
         lens = torch.empty(n, dtype=torch.int32)
         flags = torch.empty(n, dtype=torch.uint8)
         L.check(lib.sprc_tokenize_host(h, blob, offs.ctypes.data, n, max_length, self.threads, L.ptr(ids), L.ptr(mask),

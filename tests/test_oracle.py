@@ -189,3 +189,61 @@ def test_spread_golden_restatement_and_planted_recalls():
     Q = ranks.numel()
     assert rec[3:] == tuple(100.0 * int((ranks <= k).sum()) / Q for k in (1, 5, 10, 50))
     assert 5 < rec[3] < 40 and 30 < rec[4] < 70 and 50 < rec[5] < 90 and rec[6] > 85 and all(r > 0 for r in rec)
+
+
+def test_restatement_rederives_full_g_golden():
+    """VERDICT r1: the full-depth ViT-g golden re-derived by the restatement (39 EVA blocks, 3 images, 3 queries;
+    about 20 s of CPU work), not only checked for self-consistency."""
+    g, c, sd = _case("full_g")
+    images = synth.make_images(c["n_images"])
+    with torch.no_grad():
+        feats, raws = R.extract_target_features(sd, images)
+        fusion = R.fusion_features(sd, raws[g["ref_rows"]], g["input_ids"], g["attention_mask"])
+        sim = R.similarity(fusion, feats)
+    assert (raws[:, g["raw_rows"]] - g["raws_rows"]).abs().max().item() < 1e-4
+    assert (feats - g["feats"]).abs().max().item() < 4e-6
+    assert (fusion - g["fusion"]).abs().max().item() < 4e-6
+    assert (sim - g["sim"]).abs().max().item() < 4e-6
+
+
+def test_recall_full_golden_restatement_labels_and_rerank():
+    """tests/golden/recall_full_L.pt (full-depth ViT-L + 12-layer Q-Former, 256 structured images, 512 queries; the
+    reference's own similarity, labels planted from it with margin 2e-3, full-depth inference_rerank for 2 x 16 pairs):
+    the restatement reproduces a sample of the similarity matrix and the rerank probabilities at FULL depth, the
+    stored labels are what `plant_targets_with_margin` gives, each label really has the margin at every cut-off, and
+    the stored recalls are the recall tail's on those labels."""
+    g = torch.load(os.path.join(GOLDEN, "recall_full_L.pt"))
+    c = g["case"]
+    sim_ref, ref = g["sim"], g["ref_rows"]
+    assert sim_ref.shape == (512, 256) and sim_ref.max() - sim_ref.min() > 0.15
+    tgt, ranks, members = R.plant_targets_with_margin(sim_ref, ref, g["margin"])
+    assert torch.equal(tgt, g["target"]) and torch.equal(ranks, g["ranks"]) and torch.equal(members, g["members"])
+    assert torch.equal(R.target_ranks(sim_ref, ref, tgt), ranks)
+    rec = R.cirr_recalls(R.ranking(sim_ref), ref, tgt, members)
+    assert rec == pytest.approx(tuple(float(x) for x in g["recalls_ref"]))
+    assert all(r > 0 for r in rec) and 30 < rec[4] < 70 and rec[6] > 85
+    masked = sim_ref.clone()
+    masked[torch.arange(512), ref] = float("-inf")
+    srt = masked.sort(dim=1, descending=True).values
+    s_t = sim_ref[torch.arange(512), tgt]
+    for K in (1, 5, 10, 50):
+        other = torch.where(ranks <= K, srt[:, K], srt[:, K - 1])
+        assert float((s_t - other).abs().min()) >= g["margin"] - 1e-7
+    # full depth through the restatement: the images of the first 6 queries' references + the rerank pairs
+    rr = g["rerank"]
+    q = torch.arange(6)
+    need = torch.cat([ref[q], rr["ref_rows"], rr["cand_rows"], torch.arange(4)])
+    uniq, inv = torch.unique(need, return_inverse=True)
+    images = synth.make_structured_images(c["n_images"], seed=c["image_seed"])[uniq]
+    sd = synth.make_state_dict(c["vit"], None, 12, seed=0)
+    with torch.no_grad():
+        feats, raws = R.extract_target_features(sd, images)
+        sim = R.inference(sd, raws[inv[:6]], feats, g["input_ids"][q], g["attention_mask"][q])
+        sd_r = dict(sd)
+        sd_r["itm_head.weight"] = sd["itm_head.weight"] * c["itm_scale"]
+        R_, T_ = rr["R"], rr["T"]
+        p = R.inference_rerank(sd_r, raws[inv[6:6 + R_]], raws[inv[6 + R_:6 + R_ + R_ * T_]], g["input_ids"][:R_],
+                               g["attention_mask"][:R_])
+    assert (sim - sim_ref[q][:, uniq]).abs().max().item() < 1e-5
+    assert (feats[inv[-4:]] - g["feats_rows"]).abs().max().item() < 4e-6
+    assert (p - rr["p"]).abs().max().item() < 1e-5 and float(rr["p"].std()) > 1e-2
