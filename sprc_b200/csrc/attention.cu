@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
 }
 
 int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
+bool attention_vit_eligible(const AttnDesc& a);             // attention_vit.cu
+int attention_vit(const AttnDesc& a, cudaStream_t st);
 bool attention_tc_eligible(const AttnDesc& a);               // attention_tc.cu
 bool attention_qf_eligible(const AttnDesc& a);               // attention_qf.cu
 int attention_qf(const AttnDesc& a, cudaStream_t st);
@@ -225,7 +227,9 @@ int attention(const AttnDesc& a, cudaStream_t st) {
   if (!legacy && attention_qf_eligible(a)) return attention_qf(a, st);  // Q-Former self / cross: tcgen05
   SPRC_REQUIRE(a.kv_head_stride == 0, "attention: head-major K/V is only read by the tcgen05 cross-attention kernel");
   if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // remaining small shapes (rerank two-segment keys)
-  if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT: tcgen05
+  static const bool vit_v1 = getenv("SPRC_VIT_ATTN_V1") != nullptr;     // A/B switch: first-generation ViT kernel
+  if (!legacy && !vit_v1 && attention_vit_eligible(a)) return attention_vit(a, st);  // ViT: two tiles in flight
+  if (!legacy && attention_tc_eligible(a)) return attention_tc(a, st);  // ViT, first generation
   if (act_fp16()) return a.dh <= 64 ? launch_attention<64, true>(a, st) : launch_attention<96, true>(a, st);
   if (a.dh <= 64) return launch_attention<64, false>(a, st);
   return launch_attention<96, false>(a, st);

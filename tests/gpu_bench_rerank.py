@@ -17,7 +17,7 @@ lib = L.load()
 m = Blip2QformerCirRerank(vit_model="clip_L", device=dev, max_images=8, max_queries=8, max_pairs=R * T, vit_depth=1)
 m.load_state_dict(synth.make_state_dict("clip_L", 1, 12, seed=0))
 N = 4096
-raws = torch.randn(N, 257, 1024, device=dev).bfloat16()
+raws = torch.randn(N, 257, 1024, device=dev).to(m.act_torch_dtype)
 ids, mask = synth.make_token_ids(R, seed=1)
 ref = torch.randint(0, N, (R,), dtype=torch.int32, device=dev)
 cand = torch.randint(0, N, (R * T,), dtype=torch.int32, device=dev)

@@ -140,3 +140,68 @@ def test_gemm_two_weight_sets_match_torch(lib, M, split, N, K, act, res):
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err < (1e-3 if res else 6e-2), err
+
+
+def _attention_ref(q, k, v, scale, mask=None):
+    s = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * scale
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    return torch.einsum("bhqk,bhkd->bhqd", s.softmax(dim=-1), v.float())
+
+
+@pytest.mark.parametrize("B,dh,fp16", [(1, 64, False), (3, 64, False), (150, 64, True), (2, 88, False), (37, 88, True)])
+def test_vit_attention_matches_torch(lib, B, dh, fp16):
+    """ViT MHSA (eva_vit.py:128-145, clip_vit.py:134) on the packed QKV activation [B*257, 3*Dv]: the two-tiles-in-flight
+    tcgen05 kernel (csrc/attention_vit.cu: query 256 and key 256 on CUDA cores) against torch fp32 on the same 16-bit
+    operands, incl. the rows / keys that never touch the tensor core, for both head dims and both operand formats."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    H, T = 16, 257
+    Dv = H * dh
+    dt = torch.float16 if fp16 else torch.bfloat16
+    L.check(so.sprc_set_act_dtype(1 if fp16 else 0))
+    try:
+        g = torch.Generator(device=dev).manual_seed(B * 100 + dh)
+        qkv = (torch.randn(B * T, 3 * Dv, device=dev, generator=g) * 1.5).to(dt)
+        out = torch.full((B * T, Dv), float("nan"), device=dev).to(dt)
+        scale = dh ** -0.5
+        L.check(so.sprc_op_attention(L.ptr(qkv), L.ptr(qkv[:, Dv:]), L.ptr(qkv[:, 2 * Dv:]), L.ptr(out), B, H, dh, T, T,
+                                     3 * Dv, 3 * Dv, 3 * Dv, Dv, T, T, None, scale, L.cur_stream()))
+        torch.cuda.synchronize()
+        x = qkv.view(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+        ref = _attention_ref(x[0], x[1], x[2], scale).permute(0, 2, 1, 3).reshape(B * T, Dv)
+        got = out.float()
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs().max().item()
+        err_last = (got.view(B, T, Dv)[:, 256] - ref.view(B, T, Dv)[:, 256]).abs().max().item()
+        print(f"\n[vit attention B={B} dh={dh} {'fp16' if fp16 else 'bf16'}] max err {err:.2e} (row 256: {err_last:.2e})")
+        assert err < (4e-3 if fp16 else 2.5e-2)     # |out| <~ 1: one rounding of P (2^-9 / 2^-12 relative) and of the output
+    finally:
+        L.check(so.sprc_set_act_dtype(0))
+
+
+def test_vit_attention_key_256_and_row_256_matter(lib):
+    """The odd key and the odd query are handled off the tensor core: make them decisive.  Key 256 carries a huge
+    score for every query (so every output row must equal V[256]); query 256 attends sharply to key 7."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    B, H, dh, T = 2, 16, 64, 257
+    Dv = H * dh
+    g = torch.Generator(device=dev).manual_seed(1)
+    q = torch.randn(B, T, H, dh, device=dev, generator=g)
+    k = torch.randn(B, T, H, dh, device=dev, generator=g) * 0.1
+    v = torch.randn(B, T, H, dh, device=dev, generator=g)
+    k[0, 256] = q[0].mean(dim=0) * 0 + 3.0 * torch.sign(q[0, :, :, :].mean(dim=0))   # image 0: key 256 is generic
+    k[1, 7] = 4.0 * q[1, 256]                                                        # image 1: query 256 -> key 7
+    qkv = torch.stack([q, k, v], dim=2).reshape(B * T, 3 * Dv).bfloat16()
+    out = torch.zeros(B * T, Dv, device=dev, dtype=torch.bfloat16)
+    L.check(so.sprc_op_attention(L.ptr(qkv), L.ptr(qkv[:, Dv:]), L.ptr(qkv[:, 2 * Dv:]), L.ptr(out), B, H, dh, T, T,
+                                 3 * Dv, 3 * Dv, 3 * Dv, Dv, T, T, None, dh ** -0.5, L.cur_stream()))
+    torch.cuda.synchronize()
+    x = qkv.view(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = _attention_ref(x[0], x[1], x[2], dh ** -0.5).permute(0, 2, 1, 3).reshape(B, T, H, dh)
+    got = out.float().view(B, T, H, dh)
+    assert (got - ref).abs().max().item() < 3e-2
+    w = (x[0][1, :, 256].float() @ x[1][1, :, 7].float().transpose(-1, -2) if False else None)  # noqa: F841
+    # query 256 of image 1 really is dominated by key 7
+    assert (got[1, 256] - x[2][1, :, 7].float()).abs().max().item() < 0.15
