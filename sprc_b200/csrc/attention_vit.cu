@@ -20,7 +20,9 @@
 //   warps 18,19  tail: query row 256
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
+#include "mma_sync.cuh"
 #include "ops.h"
 #include "ptx.cuh"
 
@@ -43,7 +45,7 @@ constexpr int VA_REGION = 256;         // TMEM columns per tile
 constexpr int VA_COL_O = 64;           // O inside a region (after the scores have been consumed)
 constexpr int VA_COL_PHI = 192;        // P of keys 128..255 inside a region
 constexpr int VA_XCH_FLOATS = 2 * 12 * 128;   // per tile: max[4][128], part[4][128], sum[4][128]
-constexpr int VA_TAIL_FLOATS = VA_LK + 2 * 96 + 8;
+constexpr int VA_TAIL_FLOATS = 2 * 96 + 8;
 
 struct VitAttnParams {
   int B, H;
@@ -95,25 +97,25 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   constexpr int NCH = DH / 8;                 // 16-byte chunks per head row (8 / 11)
   constexpr int CH = DHP / 32;                // chunks of the key-256 dot product per softmax thread (2 / 3)
   constexpr int OC = DHP / 4;                 // output columns per softmax thread (16 / 24)
+  constexpr int NBUF = DH <= 64 ? 2 : 1;      // operand buffers: the whole NEXT item streams in behind this one
+  constexpr int ITEM_BYTES = DHB * (2 * VA_QBYTES + 2 * VA_KBYTES);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // [2 tiles][DHB blocks]
-  uint8_t* sK = sQ + 2 * DHB * VA_QBYTES;
-  uint8_t* sV = sK + DHB * VA_KBYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + DHB * VA_KBYTES);
-  uint64_t* k_full = bars + 0;
-  uint64_t* k_empty = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* v_empty = bars + 3;
-  uint64_t* q_full = bars + 4;    // [2]
-  uint64_t* q_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;    // [2]
-  uint64_t* p_full = bars + 10;   // [2]
-  uint64_t* o_full = bars + 12;   // [2]
-  uint64_t* o_empty = bars + 14;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  const uint32_t xch = smem_u32(bars + 18);                       // VA_XCH_FLOATS floats
-  const uint32_t tsm = xch + VA_XCH_FLOATS * 4;                   // tail warps: p[272], partial O[2][96], max/sum[8]
+  // per buffer: Q [2 tiles][DHB blocks] | K [DHB] | V [DHB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NBUF * ITEM_BYTES);
+  uint64_t* k_full = bars + 0;    // [2]
+  uint64_t* k_empty = bars + 2;   // [2]
+  uint64_t* v_full = bars + 4;    // [2]
+  uint64_t* v_empty = bars + 6;   // [2]
+  uint64_t* q_full = bars + 8;    // [2 buffers][2 tiles]
+  uint64_t* q_empty = bars + 12;  // [2][2]
+  uint64_t* s_full = bars + 16;   // [2 tiles]
+  uint64_t* p_full = bars + 18;
+  uint64_t* o_full = bars + 20;
+  uint64_t* o_empty = bars + 22;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t xch = smem_u32(bars + 26);                       // VA_XCH_FLOATS floats
+  const uint32_t tsm = xch + VA_XCH_FLOATS * 4;                   // tail warps: partial O[2][96], max[2], sum[2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.B * p.H;
@@ -122,13 +124,17 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(k_full, 1);
-    mbar_init(k_empty, 2);   // the MMA warp's commit + the tail warps
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 2);
+    for (int bf = 0; bf < 2; ++bf) {
+      mbar_init(&k_full[bf], 1);
+      mbar_init(&k_empty[bf], 2 + VA_SM_WARPS);   // MMA commit + tail warps + every softmax warp (key 256 row)
+      mbar_init(&v_full[bf], 1);
+      mbar_init(&v_empty[bf], 2 + VA_SM_WARPS);   // MMA commit + tail warps + every softmax warp (value 256 row)
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(&q_full[bf * 2 + t], 1);
+        mbar_init(&q_empty[bf * 2 + t], 1 + VA_SM_WARPS);   // MMA commit + every softmax warp (its query rows)
+      }
+    }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&q_full[t], 1);
-      mbar_init(&q_empty[t], 1);
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], VA_SM_WARPS);
       mbar_init(&o_full[t], 1);
@@ -144,6 +150,10 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   griddep_wait();
   griddep_launch();
 
+  // buffer of item iteration `it`, and the parity of its n-th use
+#define VA_BUF(it) (NBUF == 2 ? ((it) & 1) : 0)
+#define VA_USE(it) (NBUF == 2 ? (((it) >> 1) & 1) : ((it) & 1))
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -152,28 +162,33 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int itm = p.rev ? n_items - 1 - item : item;
         const int b = itm / p.H, h = itm % p.H;
         const int row0 = b * VA_L;
-        const uint32_t ph = (it & 1) ^ 1;
-        mbar_wait(k_empty, ph);
-        mbar_expect_tx(k_full, DHB * VA_KBYTES);
+        const int bf = VA_BUF(it);
+        const uint32_t ph = VA_USE(it) ^ 1;
+        uint8_t* sQ = smem + bf * ITEM_BYTES;
+        uint8_t* sK = sQ + 2 * DHB * VA_QBYTES;
+        uint8_t* sV = sK + DHB * VA_KBYTES;
+        mbar_wait(&k_empty[bf], ph);
+        mbar_expect_tx(&k_full[bf], DHB * VA_KBYTES);
 #pragma unroll
         for (int kb = 0; kb < DHB; ++kb) {
-          tma_load_3d(&tmK, k_full, sK + kb * VA_KBYTES, kb * 64, row0, h, kEvictNormal);
-          tma_load_3d(&tmK, k_full, sK + kb * VA_KBYTES + VA_HALF * 128, kb * 64, row0 + VA_HALF, h, kEvictNormal);
+          tma_load_3d(&tmK, &k_full[bf], sK + kb * VA_KBYTES, kb * 64, row0, h, kEvictNormal);
+          tma_load_3d(&tmK, &k_full[bf], sK + kb * VA_KBYTES + VA_HALF * 128, kb * 64, row0 + VA_HALF, h, kEvictNormal);
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&q_empty[t], ph);
-          mbar_expect_tx(&q_full[t], DHB * VA_QBYTES);
+          mbar_wait(&q_empty[bf * 2 + t], ph);
+          mbar_expect_tx(&q_full[bf * 2 + t], DHB * VA_QBYTES);
 #pragma unroll
           for (int kb = 0; kb < DHB; ++kb)
-            tma_load_3d(&tmQ, &q_full[t], sQ + (t * DHB + kb) * VA_QBYTES, kb * 64, row0 + t * 128, h, kEvictNormal);
+            tma_load_3d(&tmQ, &q_full[bf * 2 + t], sQ + (t * DHB + kb) * VA_QBYTES, kb * 64, row0 + t * 128, h,
+                        kEvictNormal);
         }
-        mbar_wait(v_empty, ph);
-        mbar_expect_tx(v_full, DHB * VA_KBYTES);
+        mbar_wait(&v_empty[bf], ph);
+        mbar_expect_tx(&v_full[bf], DHB * VA_KBYTES);
 #pragma unroll
         for (int kb = 0; kb < DHB; ++kb) {
-          tma_load_3d(&tmV, v_full, sV + kb * VA_KBYTES, kb * 64, row0, h, kEvictNormal);
-          tma_load_3d(&tmV, v_full, sV + kb * VA_KBYTES + VA_HALF * 128, kb * 64, row0 + VA_HALF, h, kEvictNormal);
+          tma_load_3d(&tmV, &v_full[bf], sV + kb * VA_KBYTES, kb * 64, row0, h, kEvictNormal);
+          tma_load_3d(&tmV, &v_full[bf], sV + kb * VA_KBYTES + VA_HALF * 128, kb * 64, row0 + VA_HALF, h, kEvictNormal);
         }
       }
     }
@@ -184,10 +199,15 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      mbar_wait(k_full, ph);
+      const int bf = VA_BUF(it);
+      const uint32_t bph = VA_USE(it);
+      uint8_t* sQ = smem + bf * ITEM_BYTES;
+      uint8_t* sK = sQ + 2 * DHB * VA_QBYTES;
+      uint8_t* sV = sK + DHB * VA_KBYTES;
+      mbar_wait(&k_full[bf], bph);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(&q_full[t], ph);
+        mbar_wait(&q_full[bf * 2 + t], bph);
         mbar_wait(&o_empty[t], ph ^ 1);   // the previous item's epilogue has read this region's O
         tc_fence_after();
         if (elect_one()) {
@@ -198,13 +218,13 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const uint64_t db = umma_desc_k_sw128(smem_u32(sK + kb * VA_KBYTES)) + 2 * kk;
             umma_bf16(tmem_base + t * VA_REGION, da, db, idesc_s, ks != 0 ? 1u : 0u);
           }
-          umma_commit(&q_empty[t]);
+          umma_commit(&q_empty[bf * 2 + t]);
           umma_commit(&s_full[t]);
-          if (t == 1) umma_commit(k_empty);
+          if (t == 1) umma_commit(&k_empty[bf]);
         }
         __syncwarp();
       }
-      mbar_wait(v_full, ph);
+      mbar_wait(&v_full[bf], bph);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         mbar_wait(&p_full[t], ph);   // P of this tile is in TMEM, its scores are consumed
@@ -218,7 +238,7 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             umma_bf16_ts(reg + VA_COL_O, pa, db, idesc_pv, ks != 0 ? 1u : 0u);
           }
           umma_commit(&o_full[t]);
-          if (t == 1) umma_commit(v_empty);
+          if (t == 1) umma_commit(&v_empty[bf]);
         }
         __syncwarp();
       }
@@ -236,18 +256,38 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int b = itm / p.H, h = itm % p.H;
       const size_t row0 = static_cast<size_t>(b) * VA_L;
       const uint32_t ph = it & 1;
-      const unsigned short* k256 = p.K + (row0 + 256) * p.ld + h * DH;
-      float p256[2];
+      const int bf = VA_BUF(it);
+      const uint32_t bph = VA_USE(it);
+      const uint32_t sQa = smem_u32(smem + bf * ITEM_BYTES);
+      const uint32_t sKa = sQa + 2 * DHB * VA_QBYTES;
+      const uint32_t sVa = sKa + DHB * VA_KBYTES;
+      // ---- this thread's share of the key-256 scores of its two query rows, from the staged tiles ----
+      float part[2] = {0.f, 0.f};
+      mbar_wait(&k_full[bf], bph);
+      uint4 kc[CH];
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc) {
+        const int c = seg * CH + cc;   // row 256 of a swizzled tile: 256 & 7 == 0, chunks in place
+        kc[cc] = c < NCH ? lds128(sKa + (c >> 3) * VA_KBYTES + 256 * 128 + ((c & 7) << 4)) : make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&k_empty[bf]);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        // ---- this thread's share of the key-256 score (operands through L2; issued before the wait below) ----
-        const unsigned short* qrow = p.Q + (row0 + t * 128 + row_in_tile) * p.ld + h * DH;
-        float part = 0.f;
+        mbar_wait(&q_full[bf * 2 + t], bph);
 #pragma unroll
         for (int cc = 0; cc < CH; ++cc) {
           const int c = seg * CH + cc;
-          if (c < NCH) part += dot8(ldg128(qrow + c * 8), ldg128(k256 + c * 8), p.fp16);
+          if (c < NCH)
+            part[t] += dot8(lds128(sQa + (t * DHB + (c >> 3)) * VA_QBYTES + row_in_tile * 128 +
+                                   (((c & 7) ^ (row_in_tile & 7)) << 4)), kc[cc], p.fp16);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[bf * 2 + t]);
+      }
+      float p256[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
         const uint32_t xt = xch + t * (12 * 128 * 4);
         mbar_wait(&s_full[t], ph);
         tc_fence_after();
@@ -264,7 +304,7 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
         for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
         sts32f(xt + (seg * 128 + row_in_tile) * 4, mx);
-        sts32f(xt + ((4 + seg) * 128 + row_in_tile) * 4, part);
+        sts32f(xt + ((4 + seg) * 128 + row_in_tile) * 4, part[t]);
         tc_fence_before();
         asm volatile("bar.sync 1, 512;" ::: "memory");   // every score of this tile has been read: P may overwrite S
         tc_fence_after();
@@ -296,16 +336,22 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");     // the row sums of both tiles are visible
-      const unsigned short* v256 = p.V + (row0 + 256) * p.ld + h * DH + seg * OC;
+      // value row 256 (rank-1 update of O) from the staged V tile, then this warp is done with the tile
+      mbar_wait(&v_full[bf], bph);
+      uint4 vv[OC / 8];
+#pragma unroll
+      for (int c = 0; c < OC / 8; ++c) {
+        const int col = seg * OC + c * 8;
+        vv[c] = col < DH ? lds128(sVa + (col >> 6) * VA_KBYTES + 256 * 128 + (((col >> 3) & 7) << 4))
+                         : make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_empty[bf]);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const uint32_t xt = xch + t * (12 * 128 * 4);
         const float inv = 1.0f / ((lds32f(xt + (8 * 128 + row_in_tile) * 4) + lds32f(xt + (9 * 128 + row_in_tile) * 4)) +
                                   (lds32f(xt + (10 * 128 + row_in_tile) * 4) + lds32f(xt + (11 * 128 + row_in_tile) * 4)));
-        uint4 vv[OC / 8];
-#pragma unroll
-        for (int c = 0; c < OC / 8; ++c)
-          vv[c] = seg * OC + c * 8 < DH ? ldg128(v256 + c * 8) : make_uint4(0, 0, 0, 0);
         mbar_wait(&o_full[t], ph);
         tc_fence_after();
         uint32_t r[OC];
@@ -340,101 +386,135 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else {
-    // ===================== tail warps: query row 256 on CUDA cores =====================
-    const int tw = warp - (2 + VA_SM_WARPS);       // 0 / 1: keys [0,136) / [136,257)
-    const int key_lo = tw * VA_HALF;
-    const int key_hi = tw == 0 ? VA_HALF : VA_L;
-    const uint32_t t_p = tsm;                      // float p[272]
-    const uint32_t t_o = tsm + VA_LK * 4;          // float partial O [2][96]
+    // ===================== tail warps: query row 256 on warp-level MMAs (m16n8k16, row 0 of the A tile) =====================
+    constexpr int DT = DHP / 8;                    // output n-tiles
+    const int tw = warp - (2 + VA_SM_WARPS);       // 0 / 1: keys [0,136) / [136,272)
+    const int kbase = tw * VA_HALF;
+    const uint32_t t_o = tsm;                      // float partial O [2][96]
     const uint32_t t_x = t_o + 2 * 96 * 4;         // float max[2], sum[2]
-    const uint32_t sKa = smem_u32(sK), sVa = smem_u32(sV);
+    const bool arow = lane < 4;                    // lanes holding row 0 of the fragments
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int itm = p.rev ? n_items - 1 - item : item;
       const int b = itm / p.H, h = itm % p.H;
       const size_t row0 = static_cast<size_t>(b) * VA_L;
-      const uint32_t ph = it & 1;
-      const unsigned short* qg = p.Q + (row0 + 256) * p.ld + h * DH;
-      uint4 qv[NCH];
+      const int bf = VA_BUF(it);
+      const uint32_t bph = VA_USE(it);
+      const uint32_t sKa = smem_u32(smem + bf * ITEM_BYTES) + 2 * DHB * VA_QBYTES;
+      const uint32_t sVa = sKa + DHB * VA_KBYTES;
+      // A fragments of query row 256: a[0] = (row 0, k 2*(lane%4)..+1), a[2] = (row 0, k + 8); rows 8.. are zero
+      const uint32_t* qw = reinterpret_cast<const uint32_t*>(p.Q + (row0 + 256) * p.ld + h * DH);
+      uint32_t aq[KSTEPS][4];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) qv[c] = ldg128(qg + c * 8);
-      mbar_wait(k_full, ph);
-      float sc[5];
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const int w0 = ks * 8 + (lane & 3), w1 = w0 + 4;
+        aq[ks][0] = (arow && 2 * w0 < DH) ? __ldg(qw + w0) : 0u;
+        aq[ks][1] = 0u;
+        aq[ks][2] = (arow && 2 * w1 < DH) ? __ldg(qw + w1) : 0u;
+        aq[ks][3] = 0u;
+      }
+      mbar_wait(&k_full[bf], bph);
+      // ---- scores of this warp's 136 keys: 9 pairs of n-tiles (16 keys); lanes 0..3 hold row 0 ----
+      float sc[9][4];
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int key = key_lo + lane + 32 * j;
-        float d = 0.f;
-        if (key < key_hi) {
+      for (int j = 0; j < 9; ++j) {
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        int key = kbase + 16 * j + (lane & 7) + ((lane >> 4) << 3);
+        key = key < VA_LK ? key : VA_LK - 1;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c)
-            d += dot8(qv[c], lds128(sKa + (c >> 3) * VA_KBYTES + key * 128 + (((c & 7) ^ (key & 7)) << 4)), p.fp16);
-          d *= p.scale_log2;
-          mx = fmaxf(mx, d);
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const int c = 2 * ks + ((lane >> 3) & 1);
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4(sKa + (c >> 3) * VA_KBYTES + key * 128 + (((c & 7) ^ (key & 7)) << 4), r0, r1, r2, r3);
+          if (p.fp16) {
+            mma_16816<true>(s0, aq[ks], r0, r1);
+            mma_16816<true>(s1, aq[ks], r2, r3);
+          } else {
+            mma_16816<false>(s0, aq[ks], r0, r1);
+            mma_16816<false>(s1, aq[ks], r2, r3);
+          }
         }
-        sc[j] = d;
+        // this lane's keys: n-tile 0 -> kbase + 16 j + 2 (lane % 4) + {0, 1}; n-tile 1 -> + 8
+        const int k0 = kbase + 16 * j + 2 * (lane & 3);
+        const int khi = tw == 0 ? VA_HALF : VA_L;
+        sc[j][0] = (arow && k0 < khi) ? s0[0] * p.scale_log2 : -INFINITY;
+        sc[j][1] = (arow && k0 + 1 < khi) ? s0[1] * p.scale_log2 : -INFINITY;
+        sc[j][2] = (arow && k0 + 8 < khi) ? s1[0] * p.scale_log2 : -INFINITY;
+        sc[j][3] = (arow && k0 + 9 < khi) ? s1[1] * p.scale_log2 : -INFINITY;
+        mx = fmaxf(fmaxf(mx, fmaxf(sc[j][0], sc[j][1])), fmaxf(sc[j][2], sc[j][3]));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (lane == 0) sts32f(t_x + tw * 4, mx);
       asm volatile("bar.sync 2, 64;" ::: "memory");     // both tail warps have read K
-      if (tw == 0 && lane == 0) mbar_arrive(k_empty);
+      if (tw == 0 && lane == 0) mbar_arrive(&k_empty[bf]);
       mx = fmaxf(lds32f(t_x), lds32f(t_x + 4));
       float sum = 0.f;
+      uint32_t pa[9][4];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int key = key_lo + lane + 32 * j;
-        if (key < key_hi) {
-          const float e = ex2_approx(sc[j] - mx);
-          sum += e;
-          sts32f(t_p + key * 4, e);
-        }
+      for (int j = 0; j < 9; ++j) {
+        const float e0 = ex2_approx(sc[j][0] - mx), e1 = ex2_approx(sc[j][1] - mx);
+        const float e2 = ex2_approx(sc[j][2] - mx), e3 = ex2_approx(sc[j][3] - mx);
+        sum += (e0 + e1) + (e2 + e3);
+        pa[j][0] = pack_act(e0, e1, p.fp16);   // the C layout of two n-tiles is the A layout of one k-step
+        pa[j][1] = 0u;
+        pa[j][2] = pack_act(e2, e3, p.fp16);
+        pa[j][3] = 0u;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0) sts32f(t_x + 8 + tw * 4, sum);
-      __syncwarp();
-      mbar_wait(v_full, ph);
-      // O[d] = sum_key p[key] V[key][d]: lane owns columns 2*lane, 2*lane+1 of every 64-column block
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const uint32_t voff = static_cast<uint32_t>(lane & 3) * 4;
-      for (int key = key_lo; key < key_hi; ++key) {
-        const float pj = lds32f(t_p + key * 4);
-        const uint32_t ra = sVa + key * 128 + ((static_cast<uint32_t>(lane >> 2) ^ (key & 7)) << 4) + voff;
-        const float2 v0 = unpack2(lds32u(ra), p.fp16);
-        a0 = fmaf(pj, v0.x, a0);
-        a1 = fmaf(pj, v0.y, a1);
-        if constexpr (DHB == 2) {
-          if (lane < 16) {
-            const float2 v1 = unpack2(lds32u(ra + VA_KBYTES), p.fp16);
-            a2 = fmaf(pj, v1.x, a2);
-            a3 = fmaf(pj, v1.y, a3);
+      mbar_wait(&v_full[bf], bph);
+      // ---- O[row 0] = P V over this warp's keys ----
+      float oacc[DT][4];
+#pragma unroll
+      for (int d = 0; d < DT; ++d) oacc[d][0] = oacc[d][1] = oacc[d][2] = oacc[d][3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        int key = kbase + 16 * j + ((lane >> 3) & 1) * 8 + (lane & 7);
+        key = key < VA_LK ? key : VA_LK - 1;
+#pragma unroll
+        for (int dp = 0; dp < DT / 2; ++dp) {
+          const int c = 2 * dp + (lane >> 4);
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4_t(sVa + (c >> 3) * VA_KBYTES + key * 128 + (((c & 7) ^ (key & 7)) << 4), r0, r1, r2, r3);
+          if (p.fp16) {
+            mma_16816<true>(oacc[2 * dp], pa[j], r0, r1);
+            mma_16816<true>(oacc[2 * dp + 1], pa[j], r2, r3);
+          } else {
+            mma_16816<false>(oacc[2 * dp], pa[j], r0, r1);
+            mma_16816<false>(oacc[2 * dp + 1], pa[j], r2, r3);
           }
         }
       }
-      sts32f(t_o + (tw * 96 + 2 * lane) * 4, a0);
-      sts32f(t_o + (tw * 96 + 2 * lane + 1) * 4, a1);
-      if (DHB == 2 && lane < 16) {
-        sts32f(t_o + (tw * 96 + 64 + 2 * lane) * 4, a2);
-        sts32f(t_o + (tw * 96 + 64 + 2 * lane + 1) * 4, a3);
+      if (arow) {
+#pragma unroll
+        for (int d = 0; d < DT; ++d) {
+          sts32f(t_o + (tw * 96 + d * 8 + 2 * lane) * 4, oacc[d][0]);
+          sts32f(t_o + (tw * 96 + d * 8 + 2 * lane + 1) * 4, oacc[d][1]);
+        }
       }
       asm volatile("bar.sync 2, 64;" ::: "memory");     // both tail warps have read V; partial sums are visible
       if (tw == 0) {
-        if (lane == 0) mbar_arrive(v_empty);
+        if (lane == 0) mbar_arrive(&v_empty[bf]);
         const float inv = 1.0f / (lds32f(t_x + 8) + lds32f(t_x + 12));
         unsigned short* orow = p.O + (row0 + 256) * p.ldo + h * DH;
-        const float o0 = (lds32f(t_o + (2 * lane) * 4) + lds32f(t_o + (96 + 2 * lane) * 4)) * inv;
-        const float o1 = (lds32f(t_o + (2 * lane + 1) * 4) + lds32f(t_o + (96 + 2 * lane + 1) * 4)) * inv;
-        *reinterpret_cast<uint32_t*>(orow + 2 * lane) = pack_act(o0, o1, p.fp16);
-        if (DHB == 2 && 64 + 2 * lane < DH) {
-          const float o2 = (lds32f(t_o + (64 + 2 * lane) * 4) + lds32f(t_o + (96 + 64 + 2 * lane) * 4)) * inv;
-          const float o3 = (lds32f(t_o + (64 + 2 * lane + 1) * 4) + lds32f(t_o + (96 + 64 + 2 * lane + 1) * 4)) * inv;
-          *reinterpret_cast<uint32_t*>(orow + 64 + 2 * lane) = pack_act(o2, o3, p.fp16);
+#pragma unroll
+        for (int c0 = 0; c0 < DHP; c0 += 64) {
+          const int col = c0 + 2 * lane;
+          if (col < DH) {
+            const float o0 = (lds32f(t_o + col * 4) + lds32f(t_o + (96 + col) * 4)) * inv;
+            const float o1 = (lds32f(t_o + (col + 1) * 4) + lds32f(t_o + (96 + col + 1) * 4)) * inv;
+            *reinterpret_cast<uint32_t*>(orow + col) = pack_act(o0, o1, p.fp16);
+          }
         }
       }
       asm volatile("bar.sync 2, 64;" ::: "memory");     // the tail buffers are free for the next item
     }
   }
+#undef VA_BUF
+#undef VA_USE
 
   tc_fence_before();
   __syncthreads();
@@ -447,7 +527,9 @@ vit_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 template <int DH>
 int launch_v2(const AttnDesc& a, cudaStream_t st) {
   constexpr int DHB = (DH + 63) / 64;
-  const size_t smem = (size_t)DHB * (2 * VA_QBYTES + 2 * VA_KBYTES) + 18 * 8 + (VA_XCH_FLOATS + VA_TAIL_FLOATS) * 4 + 1024;
+  constexpr int NBUF = DH <= 64 ? 2 : 1;
+  const size_t smem = (size_t)NBUF * DHB * (2 * VA_QBYTES + 2 * VA_KBYTES) + 26 * 8 +
+                      (VA_XCH_FLOATS + VA_TAIL_FLOATS) * 4 + 1024;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t rows = (uint64_t)a.B * a.Lq;
   SPRC_TRY(make_tmap_bf16(&tmQ, a.Q, DH, rows, a.H, a.ldq, DH, 64, 128, 1, 3));
