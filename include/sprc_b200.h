@@ -208,6 +208,14 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
                       int Lk, int ldq, int ldk, int ldv, int ldo, int q_batch_rows, int kv_batch_rows,
                       const float* key_mask, float scale, void* stream);
 
+/* Cross-attention of inference_rerank (blip2_qformer_cir_rerank.py:419-436): sample b's 32 query rows attend over
+ * cat(image kv_idx0[b], image kv_idx1[b]) = 514 keys of a K/V table with kv_rows_total rows (257 per image); heads are
+ * 64-column slices of ldk/ldv-pitch rows (kv_head_stride = 0) or contiguous [kv_rows_total, 64] blocks kv_head_stride
+ * elements apart.  dh = 64. */
+int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O, int B, int H, int ldq, int ldk, int ldv,
+                            int ldo, int q_batch_rows, const int32_t* kv_idx0, const int32_t* kv_idx1,
+                            int64_t kv_rows_total, int64_t kv_head_stride, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Host-side caption tokenizer (csrc/tokenizer.cpp; no CUDA).  Replaces the per-batch Python tokenizer call inside
  * `inference` (blip2_qformer_cir_align_prompt.py:323-329: `self.tokenizer(text, padding="max_length",

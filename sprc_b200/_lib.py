@@ -115,6 +115,11 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_void_p],
     ),
+    "sprc_op_attention_pairs": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+         c_int64, c_int64, c_float, c_void_p],
+    ),
     "sprc_tokenizer_create": (c_int, [c_char_p, c_int64, POINTER(c_void_p)]),
     "sprc_tokenizer_destroy": (None, [c_void_p]),
     "sprc_tokenize_host": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -74,6 +74,35 @@ int sprc_op_gemm2w(const void* A, const void* W, const void* W2, int M, int m_sp
   return gemm_bf16_tcgen05(d, static_cast<cudaStream_t>(stream));
 }
 
+int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O, int B, int H, int ldq, int ldk, int ldv,
+                            int ldo, int q_batch_rows, const int32_t* kv_idx0, const int32_t* kv_idx1,
+                            int64_t kv_rows_total, int64_t kv_head_stride, float scale, void* stream) {
+  if (!Q || !K || !V || !O || !kv_idx0 || !kv_idx1) return set_error(-22, "sprc_op_attention_pairs: null argument");
+  AttnDesc a;
+  a.Q = static_cast<const bf16*>(Q);
+  a.K = static_cast<const bf16*>(K);
+  a.V = static_cast<const bf16*>(V);
+  a.O = static_cast<bf16*>(O);
+  a.B = B;
+  a.H = H;
+  a.dh = 64;
+  a.Lq = 32;
+  a.Lk = 514;
+  a.Lk1 = 257;
+  a.ldq = ldq;
+  a.ldk = ldk;
+  a.ldv = ldv;
+  a.ldo = ldo;
+  a.q_batch_rows = q_batch_rows;
+  a.kv_batch_rows = 257;
+  a.kv_idx0 = kv_idx0;
+  a.kv_idx1 = kv_idx1;
+  a.kv_rows_total = kv_rows_total;
+  a.kv_head_stride = kv_head_stride;
+  a.scale = scale;
+  return attention(a, static_cast<cudaStream_t>(stream));
+}
+
 int sprc_preprocess_targetpad(const uint8_t* pixels, const int64_t* desc, const int32_t* tables, int n, int dim,
                               int max_rows, uint8_t* tmp, const float* mean3, const float* std3, float* out,
                               void* stream) {

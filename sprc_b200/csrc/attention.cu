@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnDes
 }
 
 int attention_small(const AttnDesc& a, cudaStream_t st);  // attention_small.cu
+bool attention_cross2_eligible(const AttnDesc& a);          // attention_cross.cu
+int attention_cross2(const AttnDesc& a, cudaStream_t st);
 bool attention_vit_eligible(const AttnDesc& a);             // attention_vit.cu
 int attention_vit(const AttnDesc& a, cudaStream_t st);
 bool attention_tc_eligible(const AttnDesc& a);               // attention_tc.cu
@@ -224,7 +226,9 @@ int attention(const AttnDesc& a, cudaStream_t st) {
                "attention: row pitches must keep 16-byte alignment");
   SPRC_REQUIRE(a.B <= 65535, "attention: B=%d exceeds grid limit", a.B);
   static const bool legacy = getenv("SPRC_ATTN_MMA_SYNC") != nullptr;  // A/B switch for tests
-  if (!legacy && attention_qf_eligible(a)) return attention_qf(a, st);  // Q-Former self / cross: tcgen05
+  static const bool cross_v1 = getenv("SPRC_CROSS_ATTN_V1") != nullptr;  // A/B switch: first-generation cross kernel
+  if (!legacy && !cross_v1 && attention_cross2_eligible(a)) return attention_cross2(a, st);  // 257 / 514 keys
+  if (!legacy && attention_qf_eligible(a)) return attention_qf(a, st);  // Q-Former self (/ cross, first generation)
   SPRC_REQUIRE(a.kv_head_stride == 0, "attention: head-major K/V is only read by the tcgen05 cross-attention kernel");
   if (a.dh == 64 && a.Lq <= 64) return attention_small(a, st);  // remaining small shapes (rerank two-segment keys)
   static const bool vit_v1 = getenv("SPRC_VIT_ATTN_V1") != nullptr;     // A/B switch: first-generation ViT kernel

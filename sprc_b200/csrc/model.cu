@@ -465,8 +465,8 @@ int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_b
 
 // K/V projections of all cross-attention layers in one GEMM.  head_major: every (layer, K|V, head) block is written as
 // a contiguous [n_img * 257, 64] matrix (GemmDesc::out_col_block), which the tcgen05 cross-attention kernel reads as
-// whole 33 KB blocks per (sample, head) instead of 128-byte pieces of 18 KB-pitch rows; the rerank path (two-segment
-// keys through sample index tables, attention_small) keeps plain rows.
+// whole 33 KB blocks per (sample, head) instead of 128-byte pieces of 18 KB-pitch rows (all callers use it now: the
+// rerank path addresses the blocks of its reference / candidate images through image index tables).
 int Model::cross_kv(const bf16* raws_bf16, int n_img, bool head_major, cudaStream_t st) {
   SPRC_REQUIRE(n_img > 0 && n_img <= enc_cap, "cross_kv: %d images outside (0, %d]", n_img, enc_cap);
   GemmDesc d;
@@ -481,6 +481,8 @@ int Model::cross_kv(const bf16* raws_bf16, int n_img, bool head_major, cudaStrea
   d.out_bf16 = kv;
   d.ldc = n_cross * 1536;
   d.out_col_block = head_major ? 64 : 0;
+  kv_table_rows = (long long)n_img * 257;
+  kv_head_major = head_major;
   return gemm_bf16_tcgen05(d, st);
 }
 
@@ -533,10 +535,12 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
         SPRC_TRY(linear(qhb, B * 32, 768, 768, L.cq_w, 768, L.cq_b, ACT_NONE, nullptr, nullptr, qcq, 768, g, gs, st));
         AttnDesc c;
         c.Q = qcq;
+        if (kv_idx0 && kv_head_major) kv_rows = kv_table_rows;   // rerank: image index tables over the whole table
         if (kv_rows > 0) {  // head-major blocks (cross_kv): block index = ci * 24 + {K: 0, V: 12} + head
           c.K = kv + (size_t)ci * 24 * kv_rows * 64;
           c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
           c.kv_head_stride = kv_rows * 64;
+          c.kv_rows_total = kv_rows;
         } else {
           c.K = kv + (size_t)ci * 1536;
           c.V = kv + (size_t)ci * 1536 + 768;
@@ -674,17 +678,20 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
     if (with_enc) {
       if (L.has_cross) {
         const int ci = l / 2;
-        const long long kv_rows = (long long)B * 257;
+        const long long kv_rows = kv_idx0 ? kv_table_rows : (long long)B * 257;
         SPRC_TRY(linear(qhb, qrows, 768, 768, L.cq_w, 768, L.cq_b, ACT_NONE, nullptr, nullptr, qcq, 768, 0, 0, st));
         AttnDesc c;
         c.Q = qcq;
-        if (kv_idx0) {   // rerank: plain K/V rows, keys = cat(reference image, candidate image)
+        c.kv_rows_total = kv_rows;
+        if (kv_idx0 && !kv_head_major) {   // rerank over plain K/V rows, keys = cat(reference image, candidate image)
           c.K = kv + (size_t)ci * 1536;
           c.V = kv + (size_t)ci * 1536 + 768;
           c.ldk = c.ldv = n_cross * 1536;
           c.kv_idx0 = kv_idx0;
           c.kv_idx1 = kv_idx1;
-        } else {         // head-major blocks (cross_kv)
+        } else {         // head-major blocks (cross_kv); rerank: image index tables over them
+          c.kv_idx0 = kv_idx0;
+          c.kv_idx1 = kv_idx1;
           c.K = kv + (size_t)ci * 24 * kv_rows * 64;
           c.V = kv + ((size_t)ci * 24 + 12) * kv_rows * 64;
           c.kv_head_stride = kv_rows * 64;
@@ -880,7 +887,7 @@ int Model::rerank(const bf16* raws_table, const int32_t* ref_rows, const int32_t
     SPRC_TRY(gather_rows_bf16(raws_table, SPRC_BF16, ref_rows + r0, r, row_elems, raws, st));
     SPRC_TRY(gather_rows_bf16(raws_table, SPRC_BF16, cand_rows + (size_t)r0 * T, pairs, row_elems,
                               raws + (size_t)r * row_elems, st));
-    SPRC_TRY(cross_kv(raws, n_img, false, st));
+    SPRC_TRY(cross_kv(raws, n_img, true, st));   // head-major: every (image, head) K / V block is contiguous
     // pair i reads the K/V rows of image i / T (its reference) and of image r + i (its candidate): written on the
     // device, so the call enqueues only (no host staging, no synchronisation)
     rerank_pair_images_kernel<<<(pairs + 255) / 256, 256, 0, st>>>(d_rows, d_rows2, pairs, T, r);

@@ -135,6 +135,8 @@ struct Model {
                    const int64_t* mask, int Bq, float* fusion_f32, bf16* fusion_bf16, cudaStream_t st);
   // Same result over the RAGGED row layout (attention_qfr.cu): only the live text rows of every caption are
   // computed.  text_len_host[b] = number of live tokens of caption b (sum of its attention mask), host memory.
+  long long kv_table_rows = 0;   // rows / layout of the cross-attention K/V table the last cross_kv call wrote
+  bool kv_head_major = false;
   int encode_query_ragged(const void* ref_raws, int ref_dtype, const int32_t* ref_rows, const int64_t* ids,
                           const int32_t* text_len_host, int Bq, float* fusion_f32, bf16* fusion_bf16, cudaStream_t st);
   // kv_idx0 / kv_idx1 (rerank): two-segment keys cat(ref, target) through sample index tables over plain K/V rows

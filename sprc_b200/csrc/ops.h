@@ -101,6 +101,8 @@ struct AttnDesc {
   // > 0: K and V are head-major (GemmDesc::out_col_block layout): head h starts kv_head_stride elements after head
   // h - 1 and its rows are ldk = ldv = 64 elements apart.  0: heads are 64-column slices of ldk/ldv-pitch rows.
   long long kv_head_stride = 0;
+  // rows of the K/V table the sample index tables kv_idx0 / kv_idx1 point into (bounds of the TMA tensor map)
+  long long kv_rows_total = 0;
 };
 int attention(const AttnDesc& a, cudaStream_t st);
 

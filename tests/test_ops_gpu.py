@@ -205,3 +205,77 @@ def test_vit_attention_key_256_and_row_256_matter(lib):
     w = (x[0][1, :, 256].float() @ x[1][1, :, 7].float().transpose(-1, -2) if False else None)  # noqa: F841
     # query 256 of image 1 really is dominated by key 7
     assert (got[1, 256] - x[2][1, :, 7].float()).abs().max().item() < 0.15
+
+
+@pytest.mark.parametrize("B,fp16,qrows", [(1, False, 32), (5, False, 32), (300, True, 32), (7, True, 64)])
+def test_cross_attention_257_keys_matches_torch(lib, B, fp16, qrows):
+    """Q-Former cross-attention (Qformer.py:191-194,438-450): 32 query rows per sample over the 257 visual tokens of
+    that sample, 12 heads x 64, K/V as column slices of wide rows (csrc/attention_cross.cu: key 256 of every image on
+    CUDA cores; the head-major K/V layout is covered by the 514-key test and by the model-level parity tests)."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    H, dh, T = 12, 64, 257
+    dt = torch.float16 if fp16 else torch.bfloat16
+    L.check(so.sprc_set_act_dtype(1 if fp16 else 0))
+    try:
+        g = torch.Generator(device=dev).manual_seed(B + 17)
+        q = torch.randn(B, qrows, H * dh, device=dev, generator=g).to(dt)     # rows >= 32 of a sample are not queries
+        k = (torch.randn(B, T, H, dh, device=dev, generator=g) * 1.5).to(dt)
+        v = torch.randn(B, T, H, dh, device=dev, generator=g).to(dt)
+        out = torch.full((B, qrows, H * dh), float("nan"), device=dev).to(dt)
+        kv = torch.cat([k.reshape(B * T, H * dh), v.reshape(B * T, H * dh)], dim=1).contiguous()
+        ld = 2 * H * dh
+        L.check(so.sprc_op_attention(L.ptr(q), L.ptr(kv), L.ptr(kv[:, H * dh:]), L.ptr(out), B, H, dh, 32, T, H * dh, ld,
+                                     ld, H * dh, qrows, T, None, 0.125, L.cur_stream()))
+        torch.cuda.synchronize()
+        ref = _attention_ref(q[:, :32].reshape(B, 32, H, dh).permute(0, 2, 1, 3), k.permute(0, 2, 1, 3),
+                             v.permute(0, 2, 1, 3), 0.125).permute(0, 2, 1, 3).reshape(B, 32, H * dh)
+        got = out[:, :32].float()
+        err = (got - ref).abs().max().item()
+        print(f"\n[cross 257 B={B} q rows per sample {qrows} {'fp16' if fp16 else 'bf16'}] max err {err:.2e}")
+        assert torch.isfinite(got).all() and err < (4e-3 if fp16 else 2.5e-2)
+        if qrows > 32:
+            assert torch.isnan(out[:, 32:].float()).all()      # rows that are not queries stay untouched
+    finally:
+        L.check(so.sprc_set_act_dtype(0))
+
+
+@pytest.mark.parametrize("B,n_img,head_major,fp16", [(1, 2, True, False), (6, 4, False, False), (200, 37, True, True),
+                                                     (33, 9, False, True)])
+def test_cross_attention_514_keys_matches_torch(lib, B, n_img, head_major, fp16):
+    """inference_rerank's cross-attention (blip2_qformer_cir_rerank.py:419-436): sample b attends over
+    cat(image idx0[b], image idx1[b]) = 514 keys of a K/V table, one softmax over both segments."""
+    L, so = lib
+    dev = torch.device("cuda:0")
+    H, dh, T = 12, 64, 257
+    dt = torch.float16 if fp16 else torch.bfloat16
+    L.check(so.sprc_set_act_dtype(1 if fp16 else 0))
+    try:
+        g = torch.Generator(device=dev).manual_seed(B * 3 + n_img)
+        q = torch.randn(B, 32, H * dh, device=dev, generator=g).to(dt)
+        k = (torch.randn(n_img, T, H, dh, device=dev, generator=g) * 1.5).to(dt)
+        v = torch.randn(n_img, T, H, dh, device=dev, generator=g).to(dt)
+        i0 = torch.randint(0, n_img, (B,), device=dev, generator=g, dtype=torch.int32)
+        i1 = torch.randint(0, n_img, (B,), device=dev, generator=g, dtype=torch.int32)
+        out = torch.zeros(B, 32, H * dh, device=dev, dtype=dt)
+        if head_major:
+            K = k.permute(2, 0, 1, 3).contiguous()
+            V = v.permute(2, 0, 1, 3).contiguous()
+            ld, hs = 64, n_img * T * 64
+        else:
+            kv = torch.cat([k.reshape(n_img * T, H * dh), v.reshape(n_img * T, H * dh)], dim=1).contiguous()
+            K, V = kv, kv[:, H * dh:]
+            ld, hs = 2 * H * dh, 0
+        L.check(so.sprc_op_attention_pairs(L.ptr(q), L.ptr(K), L.ptr(V), L.ptr(out), B, H, H * dh, ld, ld, H * dh, 32,
+                                           L.ptr(i0), L.ptr(i1), n_img * T, hs, 0.125, L.cur_stream()))
+        torch.cuda.synchronize()
+        kk = torch.cat([k[i0.long()], k[i1.long()]], dim=1).permute(0, 2, 1, 3)      # [B, H, 514, dh]
+        vv = torch.cat([v[i0.long()], v[i1.long()]], dim=1).permute(0, 2, 1, 3)
+        ref = _attention_ref(q.view(B, 32, H, dh).permute(0, 2, 1, 3), kk, vv, 0.125).permute(0, 2, 1, 3).reshape(
+            B, 32, H * dh)
+        err = (out.float() - ref).abs().max().item()
+        print(f"\n[cross 514 B={B} images={n_img} {'head-major' if head_major else 'wide rows'} "
+              f"{'fp16' if fp16 else 'bf16'}] max err {err:.2e}")
+        assert torch.isfinite(out.float()).all() and err < (4e-3 if fp16 else 2.5e-2)
+    finally:
+        L.check(so.sprc_set_act_dtype(0))
