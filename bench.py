@@ -641,16 +641,28 @@ def main():
     ids_dev_stage = torch.empty(Bq, 32, dtype=torch.int64, device=dev)
     mask_dev_stage = torch.empty(Bq, 32, dtype=torch.int64, device=dev)
 
+    # e2e diagnostics: host seconds spent inside submit / wait, and an event pair around every submitted batch (the GPU's
+    # busy time per batch and the idle gaps between consecutive batches)
+    e2e_diag = {"submit_s": 0.0, "wait_s": 0.0, "ev": []}
+
     def step_host(i):
         p_ = i % pool
         if world == 1 and not e2e_from_ids:
             # strings in: tokenise + enqueue step i (H2D + kernels + D2H), THEN wait for step i-1; every step's
             # tokenisation and copies are inside the timed region
+            t0 = time.perf_counter()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
             model.query_topk_strings_submit(raws, feats, rows_h[p_], caps_pool[p_], k, out_sc_h2[i % 3], out_ix_h2[i % 3])
+            eb.record()
+            e2e_diag["ev"].append((ea, eb))
+            t1 = time.perf_counter()
             inflight[0] += 1
             if inflight[0] == 2:
                 L.check(lib.sprc_query_topk_host_wait(h))
                 inflight[0] -= 1
+            e2e_diag["submit_s"] += t1 - t0
+            e2e_diag["wait_s"] += time.perf_counter() - t1
         elif world == 1:
             L.check(lib.sprc_query_topk_host(h, L.ptr(raws), L.ptr(feats), n_local, L.ptr(rows_h[p_]),
                                              L.ptr(ids_h[p_]), L.ptr(mask_h[p_]), Bq, k, L.ptr(out_sc_h),
@@ -713,6 +725,19 @@ def main():
 
     ms_e2e, _, _ = timed(step_host, K, W, drain=drain_host)
     e2e_value = world * Bq * K / (ms_e2e / 1e3)
+    e2e_host = None
+    if e2e_diag["ev"]:
+        ev = e2e_diag["ev"][-K:]
+        busy = [a_.elapsed_time(b_) for a_, b_ in ev]
+        gaps = [ev[j][1].elapsed_time(ev[j + 1][0]) for j in range(len(ev) - 1)]
+        n_all = len(e2e_diag["ev"])
+        e2e_host = {"host_submit_ms_per_step": e2e_diag["submit_s"] / n_all * 1e3,
+                    "host_wait_ms_per_step": e2e_diag["wait_s"] / n_all * 1e3,
+                    "gpu_busy_ms_per_step": sum(busy) / len(busy),
+                    "gpu_gap_ms_per_step": sum(gaps) / max(1, len(gaps)),
+                    "note": "event pair around every submitted batch: busy = first copy to last copy of a batch on the "
+                            "GPU, gap = idle time between consecutive batches; host_* = wall time inside submit "
+                            "(tokenizer + enqueue) and wait"}
     # the device-resident loop once more AFTER the e2e loop: the GPU is power-capped in this workload, and how much of
     # the value/e2e gap is the host path and how much the power state of a longer run shows in this repeat
     ms_rep, _, _ = timed(step_device, K, W)
@@ -889,7 +914,7 @@ def main():
             "value_repeat_after_e2e": value_repeat,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": world * Bq * k * 8, "ms_per_step": ms_e2e / K,
-                    "api": e2e_api},
+                    "api": e2e_api, "pipeline": e2e_host},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_scan": roofline_scan, "roofline_scan_hbm": roofline_scan_hbm,
             "step_breakdown_ms": breakdown,
