@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-rerank", action="store_true", help="skip the C5 rerank row")
     ap.add_argument("--no-vitg", action="store_true", help="skip the EVA-ViT-g rows (C3 / C4 shapes, ViT-g index rate)")
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the PyTorch-eager-on-this-GPU reference row")
+    ap.add_argument("--no-index-feed", action="store_true", help="skip the indexing-from-PNG-files row")
     ap.add_argument("--act-dtype", default="fp16", choices=["bf16", "fp16"],
                     help="16-bit tensor-core operand format: fp16 (default) = the reference's own autocast precision and "
                          "the mode whose embeddings meet the 1e-3 parity bar; bf16 runs at the same speed "
@@ -396,6 +397,114 @@ def eager_gpu_rows(args, sd, feats, dev):
         torch.cuda.empty_cache()
     except Exception as e:  # the row is informative, never fatal
         rows["error"] = f"{type(e).__name__}: {e}"[:300]
+    return rows
+
+
+def index_feed_rows(args, model, dev, n_files=384, w=640, h=480):
+    """SURVEY 8f N2, input side: gallery indexing FROM FILES.  `n_files` synthetic photo-like PNGs (640 x 480 RGB) on
+    local disk, indexed (a) through the native feed - file names -> C++ PNG decode into a pinned arena (all host cores)
+    -> one H2D copy -> GPU TargetPad / bicubic resize / normalise -> ViT + Q-Former; (b) through the reference's feed -
+    `DataLoader(num_workers=2)` whose workers run PIL decode + `targetpad_transform` (utils.py:54-64,
+    data_utils.py:91-105) in front of the same encoder.  Plus the two decoders alone (host only)."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import PIL.Image
+    from torch.utils.data import DataLoader
+
+    from sprc_b200 import retrieval as RT
+    from sprc_b200.preprocess import PngBatchDecoder, PngIndexFeeder, TargetPadPreprocessor
+
+    rows = {}
+    tmp = tempfile.mkdtemp(prefix="sprc_feed_")
+    try:
+        rng = np.random.default_rng(0)
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = []
+        for _ in range(16):   # 16 distinct photo-like images, saved n_files / 16 times each under different names
+            ch = []
+            for _c in range(3):
+                a, b, ph = rng.uniform(0.005, 0.08, 3)
+                ch.append(np.clip(127 + 80 * np.sin(a * xx + 40 * ph) * np.cos(b * yy) + rng.normal(0, 10, (h, w)), 0, 255))
+            base.append(np.stack(ch, -1).astype(np.uint8))
+        files = []
+        for i in range(n_files):
+            f = os.path.join(tmp, f"im{i:05d}.png")
+            if i < 16:
+                PIL.Image.fromarray(base[i], "RGB").save(f)
+            else:
+                shutil.copyfile(files[i % 16], f)
+            files.append(f)
+        mb = sum(os.path.getsize(f) for f in files) / 1e6
+        cores = os.cpu_count() or 1
+
+        class Folder:   # classic-mode protocol of the reference's datasets (data_utils.py:253-270)
+            def __init__(self, preprocess):
+                self.preprocess = preprocess
+
+            def __len__(self):
+                return len(files)
+
+            def __getitem__(self, i):
+                return os.path.basename(files[i]), self.preprocess(PIL.Image.open(files[i]))
+
+        # decoders alone
+        dec = PngBatchDecoder(threads=0)
+        dec.decode(files[:32])
+        t0 = time.perf_counter()
+        for s_ in range(0, n_files, 128):
+            b = dec.decode(files[s_:s_ + 128])
+            assert int(b.status.max()) == 0
+        t_nat = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for f in files[:64]:
+            np.asarray(PIL.Image.open(f).convert("RGB"))
+        t_pil = (time.perf_counter() - t0) / 64
+        rows["decode_only"] = {"native_images_per_s": n_files / t_nat, "native_threads": min(cores, 32),
+                               "pillow_images_per_s_one_core": 1.0 / t_pil}
+        # whole feed in front of the encoder
+        feeder = PngIndexFeeder(TargetPadPreprocessor(1.25, 224, device=str(dev)), threads=0)
+        RT.build_index(Folder(RT.image_path), model, batch_size=128, png_feeder=feeder, keep_raws=False)   # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ia = RT.build_index(Folder(RT.image_path), model, batch_size=128, png_feeder=feeder, keep_raws=False)
+        torch.cuda.synchronize()
+        t_a = time.perf_counter() - t0
+        rows["native_feed"] = {"images_per_s": n_files / t_a,
+                               "path": "file names -> sprc_png_decode_files (pinned arena) -> H2D -> "
+                                       "sprc_preprocess_targetpad -> sprc_encode_gallery, decode of batch i+1 under the "
+                                       "GPU work of batch i"}
+        ref_tf = None
+        src = staged_reference_src()
+        if src:
+            sys.path.insert(0, src)
+            try:
+                import importlib
+
+                du = importlib.import_module("data_utils")
+                ref_tf = du.targetpad_transform(1.25, 224)
+            except Exception:  # noqa: BLE001
+                ref_tf = None
+            finally:
+                sys.path.remove(src)
+        if ref_tf is not None:
+            n_ref = min(n_files, 192)
+            sub = torch.utils.data.Subset(Folder(ref_tf), range(n_ref))
+            t0 = time.perf_counter()
+            ib = RT.build_index(sub, model, batch_size=32, num_workers=2, keep_raws=False)   # utils.py:54: batch 32, 2 workers
+            torch.cuda.synchronize()
+            t_b = time.perf_counter() - t0
+            rows["reference_feed"] = {"images_per_s": n_ref / t_b,
+                                      "path": "the reference's DataLoader(batch_size=32, num_workers=2) with PIL decode + "
+                                              "targetpad_transform in the workers, same encoder"}
+            rows["same_index"] = bool(torch.equal(ia.feats[:n_ref], ib.feats))
+        rows["files"] = f"{n_files} PNG files {w}x{h} RGB, {mb / n_files:.2f} MB each, local disk (page cache warm)"
+        rows["host_cores"] = cores
+    except Exception as e:  # informative row, never fatal
+        rows["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     return rows
 
 
@@ -839,6 +948,9 @@ def main():
             t = torch.tensor([rerank["pairs_per_s_per_gpu"]], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             rerank["pairs_per_s_all_gpus"] = world * t.item()   # slowest rank x ranks: queries split contiguously
+    index_feed = None
+    if rank == 0 and world == 1 and not args.no_index_feed:
+        index_feed = index_feed_rows(args, model, dev)
     vitg = None
     if not args.no_vitg and args.vit == "clip_L":
         del cand_send, cand_recv
@@ -928,6 +1040,7 @@ def main():
             "parity": parity,
             "rerank": rerank,
             "eager_gpu": eager,
+            "index_feed": index_feed,
             "sharded_equals_single": sharded_equals_single,
             "roofline_vit": {args.vit: {"images_per_s_per_gpu": index_ips,
                                         "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (

@@ -233,6 +233,24 @@ void sprc_tokenizer_destroy(sprc_tokenizer* t);
 int sprc_tokenize_host(const sprc_tokenizer* t, const char* texts, const int64_t* offsets, int n, int max_len,
                        int threads, int64_t* ids, int64_t* mask, int32_t* lens, uint8_t* complex_flags);
 
+/* ---- indexing feed: PNG files -> packed RGB8 (host; csrc/png.cpp) --------------------------------------------
+ * Replaces the decode half of the reference's index DataLoader (src/utils.py:54-64 `DataLoader(num_workers=2)` whose
+ * workers run `PIL.Image.open(path)` + `convert("RGB")`, src/data_utils.py:91-105,167-186,253-270): `threads` C++
+ * workers decode a batch of files straight into `out` (a pinned arena in practice; the GPU resize kernels of
+ * sprc_preprocess_targetpad read it after ONE copy).  Pixel values are Pillow's `Image.open(p).convert("RGB")`,
+ * bit for bit (tests/test_png.py), for non-interlaced PNGs with 8-bit gray / gray+alpha / RGB / RGBA / palette samples
+ * and 1/2/4-bit gray / palette.
+ * paths = n UTF-8 file names back to back, file i = bytes [path_offsets[i], path_offsets[i+1]);
+ * pixel_offsets int64 [n+1]: image i occupies out[pixel_offsets[i] .. +3*w*h); wh int32 [n][3] = (width, height,
+ * the mode Pillow opens the file in: 0 "RGB", 1 "L", 2 "1", 3 "P", 4 "LA", 5 "RGBA" - resize-then-convert, the
+ * reference's transform order, equals convert-then-resize only for 0 and 1);
+ * status int32 [n]: 0 decoded, 1 not taken by this decoder (16-bit samples, Adam7, not a PNG: the caller decodes the
+ * file with Pillow), 2 corrupt, 3 unreadable (Pillow decides; the reference's datasets drop such images).
+ * Returns -34 without decoding when the batch needs more than out_capacity bytes (pixel_offsets[n] = bytes needed).
+ * threads <= 0: one per core, at most 32. */
+int sprc_png_decode_files(const char* paths, const int64_t* path_offsets, int n, int threads, uint8_t* out,
+                          int64_t out_capacity, int64_t* pixel_offsets, int32_t* wh, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

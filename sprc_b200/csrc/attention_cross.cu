@@ -17,6 +17,7 @@
 //   warp 0  TMA producer     warp 1  tcgen05.mma issuer     warps 2..5  softmax (+ epilogue in the lane-quarter-0 warp)
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ops.h"
 #include "ptx.cuh"
@@ -348,6 +349,314 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One segment (257 keys), TWO softmax groups.  ncu on the kernel above (profiles/r02n_ncu_cross_attention_summary.txt):
+// 14.6 % issue activity, 52 % of DRAM throughput, 4.6 k cycles per item - an item is a serial chain
+// (load -> S MMA -> softmax -> P V MMA -> epilogue) and one group of four softmax warps can only walk one chain at a
+// time, so the time of a launch follows the SM clock.  Here warps 2..5 own the even items of the CTA (stage 0, TMEM
+// region 0) and warps 6..9 the odd ones (stage 1, region 1): two chains per SM in antiphase, each with its own P
+// buffer, exchange scratch, staging tile and named barrier.  The MMA issuer is ONE polling thread that serves whichever
+// chain is ready (scores of a loaded stage, or P V of a finished softmax) instead of sleeping on one barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int XG_THREADS = 10 * 32;
+constexpr int XG_PGROUP = 4 * 4096;                 // P of one group: four 64-key blocks 4 KB apart
+constexpr int XG_PBYTES = 2 * XG_PGROUP + 12288;    // + the rows 32..127 the last block's MMA also reads
+constexpr int XG_XCH = 3 * 128 * 4;                 // per group: max[4][32], part[4][32], sum[4][32]
+constexpr int XG_SMEM = XG_PBYTES + 2 * XC_STAGE + 2 * XC_OBYTES + 256 + 128 + 2 * XG_XCH + 1024;
+
+__global__ void __launch_bounds__(XG_THREADS, 1)
+qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                             const CrossParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem;
+  uint8_t* stages = smem + XG_PBYTES;
+  uint8_t* sO = stages + 2 * XC_STAGE;              // [2][XC_OBYTES]
+  uint8_t* sV256 = sO + 2 * XC_OBYTES;              // [2][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV256 + 256);
+  uint64_t* full = bars;         // [2] stage g loaded
+  uint64_t* empty = bars + 2;    // [2] stage g free
+  uint64_t* s_full = bars + 4;   // [2] scores of group g's item are in region g
+  uint64_t* rfree = bars + 6;    // [2] region g may take new scores
+  uint64_t* p_full = bars + 8;   // [2] P of group g's item is in shared memory
+  uint64_t* o_full = bars + 10;  // [2] O of group g's item is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const uint32_t xch0 = smem_u32(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.B * p.H;
+  const int n_my = n_items > static_cast<int>(blockIdx.x)
+                       ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                       : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&rfree[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 0) {
+    // ===================== TMA producer: item `it` -> stage it & 1 =====================
+    if (elect_one()) {
+      for (int it = 0; it < n_my; ++it) {
+        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+        const int itm = p.rev ? n_items - 1 - item : item;
+        const int b = itm / p.H, h = itm % p.H;
+        const int st = it & 1;
+        uint8_t* sb = stages + st * XC_STAGE;
+        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], XC_STAGE);
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep)
+          tma_load_2d(&tmQ, &full[st], sb + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
+        const int kr = b * p.kv_batch_rows;
+        tma_load_3d(&tmK, &full[st], sb + XC_QBYTES, 0, kr, h, kEvictFirst);
+        tma_load_3d(&tmK, &full[st], sb + XC_QBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+        tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES, 0, kr, h, kEvictFirst);
+        tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one polling thread, two chains =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_16(128, 256, p.fp16);
+      const uint32_t idesc_pv = umma_idesc_16(128, 64, p.fp16) | (1u << 16);  // B operand MN-major
+      int s_next[2] = {0, 1}, pv_next[2] = {0, 1};   // next item of each group whose scores / P V are to be issued
+      while (pv_next[0] < n_my || pv_next[1] < n_my) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* sb = stages + g * XC_STAGE;
+          int it = s_next[g];
+          if (it < n_my) {
+            const uint32_t n = (it >> 1) & 1;
+            if (mbar_test(&full[g], n) && mbar_test(&rfree[g], n ^ 1)) {
+              tc_fence_after();
+              const uint64_t da = umma_desc_k_sw128(smem_u32(sb));
+              const uint64_t db = umma_desc_k_sw128(smem_u32(sb + XC_QBYTES));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tmem_base + g * XC_REGION, da + 2 * kk, db + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+              umma_commit(&s_full[g]);
+              s_next[g] = it + 2;
+            }
+          }
+          it = pv_next[g];
+          if (it < n_my && it < s_next[g] && mbar_test(&p_full[g], (it >> 1) & 1)) {
+            tc_fence_after();
+            const uint32_t sv = smem_u32(sb + XC_QBYTES + XC_KBYTES);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+              const uint64_t da = umma_desc_k_sw128(smem_u32(sP + g * XG_PGROUP + (ks >> 2) * 4096)) + 2 * (ks & 3);
+              const uint64_t db = umma_desc_mn_sw128(sv + ks * 16 * 128, XC_KBYTES);
+              umma_bf16(tmem_base + g * XC_REGION, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(&o_full[g]);
+            umma_commit(&empty[g]);
+            pv_next[g] = it + 2;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;   // TMEM lane quarter = 64-key block this warp owns
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t prow = smem_u32(sP) + g * XG_PGROUP + lane * 128;
+    const uint32_t x_max = xch0 + g * XG_XCH, x_part = x_max + 128 * 4, x_sum = x_max + 2 * 128 * 4;
+    const uint32_t sb = smem_u32(stages + g * XC_STAGE);
+    const uint32_t sv256 = smem_u32(sV256) + g * 128;
+    const uint32_t so = smem_u32(sO) + g * XC_OBYTES;
+    const uint32_t region = tmem_base + g * XC_REGION;
+    for (int it = g; it < n_my; it += 2) {
+      const uint32_t par = (it >> 1) & 1;
+      const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      const int itm = p.rev ? n_items - 1 - item : item;
+      const int b = itm / p.H, h = itm % p.H;
+      uint32_t sr[64];
+      mbar_wait(&s_full[g], par);   // the stage is loaded too (the MMA has read it)
+      tc_fence_after();
+      {
+        uint32_t(&a0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
+        uint32_t(&a1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[32]);
+        const uint32_t s_addr = region + lane_addr + q * 64;
+        tmem_ld32(s_addr, a0);
+        tmem_ld32(s_addr + 32, a1);
+      }
+      // this warp's 16 dims of the key-256 score of row `lane` (replica 0 of Q, K row 256: chunks in place)
+      float part = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * q + cc;
+        part += xc_dot8(lds128(sb + lane * 128 + ((c ^ (lane & 7)) << 4)),
+                        lds128(sb + XC_QBYTES + 256 * 128 + (c << 4)), p.fp16);
+      }
+      tmem_ld_wait();
+      float mxl = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) mxl = fmaxf(mxl, __uint_as_float(sr[j]));
+      sts32f(x_part + (q * 32 + lane) * 4, part);
+      sts32f(x_max + (q * 32 + lane) * 4, mxl);
+      tc_fence_before();
+      if (g == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // every score of the item has been read
+      else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      tc_fence_after();
+      float mx = fmaxf(fmaxf(lds32f(x_max + lane * 4), lds32f(x_max + (32 + lane) * 4)),
+                       fmaxf(lds32f(x_max + (64 + lane) * 4), lds32f(x_max + (96 + lane) * 4)));
+      const float s256 = (lds32f(x_part + lane * 4) + lds32f(x_part + (32 + lane) * 4)) +
+                         (lds32f(x_part + (64 + lane) * 4) + lds32f(x_part + (96 + lane) * 4));
+      mx = fmaxf(mx, s256);
+      const float moff = mx * p.scale_log2;
+      if (it >= 2) mbar_wait(&o_full[g], par ^ 1);   // the group's previous P V has read the P buffer
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c * 8 + j]), p.scale_log2, -moff));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c * 8 + j + 1]), p.scale_log2, -moff));
+          sum += e0 + e1;
+          pk[j / 2] = pack_act(e0, e1, p.fp16);
+        }
+        // K-major A operand: key block kb at +kb*4096, row `lane`, 16-byte chunk c (8 keys), 128B swizzle
+        sts128(prow + q * 4096 + ((c ^ (lane & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+      const float p256 = ex2_approx(fmaf(s256, p.scale_log2, -moff));
+      if (q == 0) sum += p256;
+      sts32f(x_sum + (q * 32 + lane) * 4, sum);
+      if (q == 0 && lane < 8) {
+        // value row 256 -> side buffer (the stage is recycled before the epilogue runs)
+        const uint4 v = lds128(sb + XC_QBYTES + XC_KBYTES + 256 * 128 + (lane << 4));
+        sts128(sv256 + (lane << 4), v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async();   // P (generic-proxy writes) -> tcgen05.mma (async proxy)
+      if (g == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (q == 0) {
+        // ---- epilogue (lanes 0..31 hold the real rows): (O + p256 V256) / l -> 16 bit -> staging -> TMA store ----
+        mbar_wait(&o_full[g], par);
+        tc_fence_after();
+        uint32_t r[64];
+        {
+          uint32_t(&a0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          uint32_t(&a1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+          tmem_ld32(region, a0);
+          tmem_ld32(region + 32, a1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&rfree[g]);
+          bulk_wait_read0();  // the group's previous store has read the staging tile
+        }
+        __syncwarp();
+        const float inv = 1.0f / ((lds32f(x_sum + lane * 4) + lds32f(x_sum + (32 + lane) * 4)) +
+                                  (lds32f(x_sum + (64 + lane) * 4) + lds32f(x_sum + (96 + lane) * 4)));
+        const uint32_t stg = so + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(r[8 * c + j]);
+          const uint4 v = lds128(sv256 + (c << 4));
+          const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 v2 = xc_unpack2(vw[j], p.fp16);
+            o[2 * j] = fmaf(p256, v2.x, o[2 * j]);
+            o[2 * j + 1] = fmaf(p256, v2.y, o[2 * j + 1]);
+          }
+          sts128(stg + ((c ^ (lane & 7)) << 4), pack_act(o[0] * inv, o[1] * inv, p.fp16),
+                 pack_act(o[2] * inv, o[3] * inv, p.fp16), pack_act(o[4] * inv, o[5] * inv, p.fp16),
+                 pack_act(o[6] * inv, o[7] * inv, p.fp16));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, so, h * 64, b * p.q_batch_rows);
+          bulk_commit();
+        }
+      }
+      // x_sum / sV256 of this item are read by the quarter-0 warp before it joins the group's next first bar.sync
+    }
+    if (q == 0 && lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_cross_g2(const AttnDesc& a, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  const uint64_t w = (uint64_t)a.H * 64;
+  const uint64_t qrows = (uint64_t)(a.B - 1) * a.q_batch_rows + a.Lq;
+  const uint64_t krows = a.kv_rows_total > 0 ? (uint64_t)a.kv_rows_total : (uint64_t)(a.B - 1) * a.kv_batch_rows + 257;
+  SPRC_TRY(make_tmap_bf16(&tmQ, a.Q, w, qrows, 1, a.ldq, 0, 64, 32, 1, 2));
+  const uint64_t hstride = a.kv_head_stride > 0 ? (uint64_t)a.kv_head_stride : 64;
+  SPRC_TRY(make_tmap_bf16(&tmK, a.K, 64, krows, a.H, a.ldk, hstride, 64, XC_HALF, 1, 3));
+  SPRC_TRY(make_tmap_bf16(&tmV, a.V, 64, krows, a.H, a.ldv, hstride, 64, XC_HALF, 1, 3));
+  SPRC_TRY(make_tmap_bf16(&tmO, a.O, w, qrows, 1, a.ldo, 0, 64, 32, 1, 2));
+  CrossParams p;
+  p.B = a.B;
+  p.H = a.H;
+  p.q_batch_rows = a.q_batch_rows;
+  p.kv_batch_rows = a.kv_batch_rows;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.fp16 = act_fp16();
+  p.rev = next_sweep_reverse();
+  p.kv_idx0 = nullptr;
+  p.kv_idx1 = nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPRC_CUDA(cudaFuncSetAttribute(qf_cross_attention_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM));
+    attr_set = true;
+  }
+  const int items = a.B * a.H;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  prof_begin(st);
+  SPRC_CUDA(launch_pdl(qf_cross_attention_g2_kernel, dim3(grid), dim3(XG_THREADS), XG_SMEM, st, tmQ, tmK, tmV, tmO, p));
+  if (prof_enabled()) {
+    char tag[56];
+    snprintf(tag, sizeof(tag), "qf-cross-g2 B%d H%d Lq%d Lk%d", a.B, a.H, a.Lq, a.Lk);
+    prof_end(PROF_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * 64, 2.0 * a.B * a.H * 64 * (2.0 * a.Lq + 2.0 * a.Lk), st,
+             tag);
+  }
+  count_launch();
+  SPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int NSEG>
 int launch_cross2(const AttnDesc& a, cudaStream_t st) {
   constexpr int PBYTES = NSEG * 4 * 4096 + 12288;
@@ -405,7 +714,9 @@ bool attention_cross2_eligible(const AttnDesc& a) {
 }
 
 int attention_cross2(const AttnDesc& a, cudaStream_t st) {
-  return a.kv_idx0 ? launch_cross2<2>(a, st) : launch_cross2<1>(a, st);
+  if (a.kv_idx0) return launch_cross2<2>(a, st);
+  static const bool one_group = getenv("SPRC_CROSS_ATTN_1G") != nullptr;   // A/B switch: one softmax group
+  return one_group ? launch_cross2<1>(a, st) : launch_cross_g2(a, st);
 }
 
 }  // namespace sprc

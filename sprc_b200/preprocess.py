@@ -8,8 +8,11 @@ crop window) exactly as TargetPad / torchvision.transforms.functional.resize / c
 bicubic coefficient tables (libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc) in double precision
 with the same operation order; only the taps of the 224 columns / rows that survive the centre crop are emitted.
 
-Decoding (PNG/JPEG -> RGB uint8) stays on the host (PIL, thread pool); images must be mode "RGB" — the reference
-resizes before converting to RGB, which for other modes (palette, greyscale) is a different operation.
+Decoding stays on the host.  `PngBatchDecoder` (C++ workers behind `sprc_png_decode_files`, csrc/png.cpp) decodes a
+batch of PNG files — the format both datasets are stored in (data_utils.py:167-186,253-270) — into a pinned arena that
+the resize kernels consume after one copy; `PngIndexFeeder` chains decoder and preprocessor.  The reference resizes
+BEFORE converting to RGB, which equals convert-then-resize only for images Pillow opens as "RGB" or "L"; every other
+file (palette, alpha, 1-bit, 16-bit, interlaced, not a PNG) goes through the reference's own PIL chain on the host.
 """
 from __future__ import annotations
 
@@ -125,17 +128,32 @@ class TargetPadPreprocessor:
             if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
                 raise ValueError(f"expected uint8 [H,W,3], got {im.dtype} {im.shape}")
             arrs.append(np.ascontiguousarray(im))
-        n, dim = len(arrs), self.dim
+        if not arrs:
+            return torch.empty(0, 3, self.dim, self.dim, device=self.device)
+        pix = torch.from_numpy(np.concatenate([a.reshape(-1) for a in arrs])).pin_memory()
+        offs, o = [], 0
+        for a in arrs:
+            offs.append(o)
+            o += a.size
+        return self.run_packed(pix, [(a.shape[1], a.shape[0]) for a in arrs], offs)
+
+    @torch.no_grad()
+    def run_packed(self, pix: torch.Tensor, sizes: Sequence[Tuple[int, int]], offsets: Sequence[int]) -> torch.Tensor:
+        """`pix`: uint8 buffer (pinned host or device) holding image i as packed RGB at byte `offsets[i]`, `sizes[i]` =
+        (width, height).  One H2D copy of the used prefix, then the two kernels.  Returns fp32 [n,3,dim,dim]."""
+        n, dim = len(sizes), self.dim
         if n == 0:
             return torch.empty(0, 3, dim, dim, device=self.device)
         desc = np.zeros((n, _FIELDS), dtype=np.int64)
         tables: List[np.ndarray] = []
         table_off: Dict[Tuple[int, int], Tuple[int, int, int, int]] = {}
         t_len = 0
-        src_off = tmp_off = 0
+        tmp_off = 0
         max_rows = 0
-        for i, a in enumerate(arrs):
-            h, w = a.shape[:2]
+        end = 0
+        for i, (w, h) in enumerate(sizes):
+            src_off = int(offsets[i])
+            end = max(end, src_off + 3 * w * h)
             p = self.plan(w, h)
             if (w, h) not in table_off:   # images of one size share one set of tables
                 offs = []
@@ -147,12 +165,10 @@ class TargetPadPreprocessor:
             o = table_off[(w, h)]
             desc[i, :14] = (src_off, w, h, p["hp"], p["vp"], p["row0"], p["nrows"], p["hk"].shape[1], p["vk"].shape[1],
                             o[0], o[1], o[2], o[3], tmp_off)
-            src_off += a.size
             tmp_off += p["nrows"] * dim * 3
             max_rows = max(max_rows, p["nrows"])
-        pix = torch.from_numpy(np.concatenate([a.reshape(-1) for a in arrs])).pin_memory()
         dev = self.device
-        pix_d = pix.to(dev, non_blocking=True)
+        pix_d = pix[:end].to(dev, non_blocking=True)
         desc_d = torch.from_numpy(desc).to(dev, non_blocking=True)
         tab_d = torch.from_numpy(np.concatenate(tables).astype(np.int32)).to(dev, non_blocking=True)
         tmp = torch.empty(tmp_off, dtype=torch.uint8, device=dev)
@@ -162,3 +178,125 @@ class TargetPadPreprocessor:
                                                         L.ptr(tmp), self._mean, self._std, L.ptr(out),
                                                         L.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         return out
+
+
+PIL_MODES = ("RGB", "L", "1", "P", "LA", "RGBA")
+
+
+class PngBatch:
+    """Result of `PngBatchDecoder.decode`: `arena` (pinned uint8) holds image i as packed RGB at `offsets[i]`;
+    `wh[i]` = (width, height, Pillow mode code, index into PIL_MODES); `status[i]`: 0 decoded, 1 not taken (decode with
+    Pillow), 2 corrupt, 3 unreadable."""
+
+    def __init__(self, paths, arena, offsets, wh, status, slot=0):
+        self.paths, self.arena, self.offsets, self.wh, self.status, self.slot = paths, arena, offsets, wh, status, slot
+
+    def image(self, i: int) -> np.ndarray:
+        """uint8 [H,W,3] view of image i (status 0 only)."""
+        w, h = int(self.wh[i, 0]), int(self.wh[i, 1])
+        o = int(self.offsets[i])
+        return self.arena[o:o + 3 * w * h].numpy().reshape(h, w, 3)
+
+
+class PngBatchDecoder:
+    """Threaded PNG -> RGB8 decode into pinned arenas (sprc_png_decode_files).  Two arenas alternate so that batch i+1
+    can be decoded while batch i is still being copied to the device; `decode` grows an arena when a batch needs more."""
+
+    def __init__(self, threads: int = 0, arena_bytes: int = 64 << 20, pin: bool = True):
+        self._lib = L.load()
+        self.threads = int(threads)
+        self._pin = bool(pin) and torch.cuda.is_available()
+        self._arenas = [self._alloc(arena_bytes), self._alloc(arena_bytes)]
+        self._copied = [None, None]   # CUDA event per arena: the last H2D copy that read it
+        self._turn = 0
+
+    def mark_copied(self, batch: "PngBatch") -> None:
+        """Call after enqueuing the H2D copy of `batch`: its arena is not decoded into again before that copy ran."""
+        if torch.cuda.is_available():
+            ev = torch.cuda.Event()
+            ev.record()
+            self._copied[batch.slot] = ev
+
+    def _alloc(self, nbytes: int) -> torch.Tensor:
+        t = torch.empty(int(nbytes), dtype=torch.uint8)
+        return t.pin_memory() if self._pin else t
+
+    def decode(self, paths: Sequence[str]) -> PngBatch:
+        n = len(paths)
+        enc = [str(p).encode("utf-8") for p in paths]
+        poffs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=poffs[1:])
+        blob = b"".join(enc)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        wh = np.zeros((n, 3), dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        slot = self._turn
+        self._turn ^= 1
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()
+            self._copied[slot] = None
+        for _ in range(2):
+            arena = self._arenas[slot]
+            rc = self._lib.sprc_png_decode_files(blob, poffs.ctypes.data, n, self.threads, L.ptr(arena), arena.numel(),
+                                                 offs.ctypes.data, wh.ctypes.data, status.ctypes.data)
+            if rc != -34:
+                break
+            self._arenas[slot] = self._alloc(max(int(offs[n]), 2 * arena.numel()))   # grow once, decode again
+        L.check(rc)
+        return PngBatch(list(paths), self._arenas[slot], offs, wh, status, slot)
+
+
+class PngIndexFeeder:
+    """paths -> fp32 [m,3,dim,dim] on the device, the tensor `targetpad_transform` + default_collate would have produced
+    for the readable images of the batch, plus the indices that were kept.  Files Pillow opens as "RGB" / "L" take the
+    native decode + GPU resize; the rest run `fallback(PIL.Image.open(path))` — the reference's own transform — on the
+    host; files that raise there are dropped, as the reference's datasets + collate_fn do (data_utils.py:191-192,
+    utils.py:141-148)."""
+
+    def __init__(self, pre: TargetPadPreprocessor, fallback=None, threads: int = 0):
+        self.pre = pre
+        self.decoder = PngBatchDecoder(threads=threads)
+        self.fallback = fallback
+        self.n_native = self.n_fallback = self.n_dropped = 0
+
+    def decode(self, paths: Sequence[str]) -> PngBatch:
+        """Host half (safe to run on a helper thread while the GPU works on the previous batch)."""
+        return self.decoder.decode(paths)
+
+    @torch.no_grad()
+    def finish(self, batch: PngBatch):
+        import PIL.Image
+
+        n = len(batch.paths)
+        native = [i for i in range(n) if batch.status[i] == 0 and batch.wh[i, 2] in (0, 1)]
+        out_native = self.pre.run_packed(batch.arena, [(int(batch.wh[i, 0]), int(batch.wh[i, 1])) for i in native],
+                                         [int(batch.offsets[i]) for i in native])
+        self.decoder.mark_copied(batch)
+        host = {}
+        for i in range(n):
+            if i in native:
+                continue
+            try:
+                if self.fallback is None:
+                    raise NotImplementedError(f"{batch.paths[i]}: not an RGB / L PNG and no PIL fallback transform given")
+                host[i] = self.fallback(PIL.Image.open(batch.paths[i]))
+            except NotImplementedError:
+                raise
+            except Exception as e:  # noqa: BLE001  the reference prints and drops (data_utils.py:191-192)
+                print(f"Exception: {e}")
+        self.n_native += len(native)
+        self.n_fallback += len(host)
+        self.n_dropped += n - len(native) - len(host)
+        if not host:
+            return out_native, native
+        keep = sorted(native + list(host))
+        pos = {i: j for j, i in enumerate(keep)}
+        out = torch.empty(len(keep), 3, self.pre.dim, self.pre.dim, device=self.pre.device)
+        if native:
+            out[torch.tensor([pos[i] for i in native], device=out.device)] = out_native
+        for i, t in host.items():
+            out[pos[i]] = t.to(out.device, torch.float32)
+        return out, keep
+
+    def __call__(self, paths: Sequence[str]):
+        return self.finish(self.decode(paths))

@@ -87,17 +87,42 @@ def raw_rgb(image):
     return np.asarray(image)
 
 
+def image_path(image):
+    """`preprocess` callable for the reference's dataset classes that hands back the file NAME: `PIL.Image.open` is lazy
+    (only the header has been read when the dataset calls `preprocess`), so `build_index(..., png_feeder=...)` can decode
+    the whole batch with the native threaded decoder (csrc/png.cpp) instead of one PIL image per DataLoader worker."""
+    return image.filename
+
+
+def _path_batches(dataset, batch_size):
+    names, paths = [], []
+    for i in range(len(dataset)):
+        item = dataset[i]
+        if item is None:          # the reference's datasets return None for files that fail to open
+            continue
+        names.append(item[0])
+        paths.append(item[1])
+        if len(names) == batch_size:
+            yield names, paths
+            names, paths = [], []
+    if names:
+        yield names, paths
+
+
 def _collate_raw(batch):
     batch = [b for b in batch if b is not None]      # utils.py:141-148 drops unreadable images
     return [b[0] for b in batch], [b[1] for b in batch]
 
 
 def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, collate_fn=None,
-                keep_raws: bool = True, progress: bool = False, gpu_preprocess=None) -> GalleryIndex:
+                keep_raws: bool = True, progress: bool = False, gpu_preprocess=None, png_feeder=None) -> GalleryIndex:
     """Encode this rank's row shard of `dataset` ('classic' mode: items are (name, image)).
     gpu_preprocess: a `sprc_b200.preprocess.TargetPadPreprocessor`; the dataset must then be built with
     `preprocess=retrieval.raw_rgb` so that items are (name, uint8 [H,W,3]) and resize/crop/normalise run on the GPU
-     — workers only decode."""
+     — workers only decode.
+    png_feeder: a `sprc_b200.preprocess.PngIndexFeeder`; the dataset must then be built with
+    `preprocess=retrieval.image_path` so that items are (name, file name): no DataLoader workers at all — a helper
+    thread decodes batch i+1 natively (C++ workers, pinned arena) while the GPU resizes and encodes batch i."""
     from torch.utils.data import DataLoader, Subset
 
     if gpu_preprocess is not None:
@@ -107,16 +132,36 @@ def build_index(dataset, backend, batch_size: int = 64, num_workers: int = 2, co
     n = len(dataset)
     lo, hi = shard_range(n, rank, world)
     sub = Subset(dataset, range(lo, hi)) if world > 1 else dataset
-    loader = DataLoader(dataset=sub, batch_size=batch_size, num_workers=num_workers,
-                        pin_memory=gpu_preprocess is None, collate_fn=collate_fn)
     feats, raws, names = [], [], []
-    it = loader
+    if png_feeder is not None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def _fed():
+            with ThreadPoolExecutor(max_workers=1) as ex:
+                pending = None
+                for bn, bp in _path_batches(sub, batch_size):
+                    fut = ex.submit(png_feeder.decode, bp)
+                    if pending is not None:
+                        yield pending[0], pending[1].result()
+                    pending = (bn, fut)
+                if pending is not None:
+                    yield pending[0], pending[1].result()
+
+        it = _fed()
+    else:
+        it = DataLoader(dataset=sub, batch_size=batch_size, num_workers=num_workers,
+                        pin_memory=gpu_preprocess is None, collate_fn=collate_fn)
     if progress:
         from tqdm import tqdm
 
-        it = tqdm(loader)
+        it = tqdm(it)
     for batch_names, images in it:
-        if gpu_preprocess is not None:
+        if png_feeder is not None:
+            images, keep = png_feeder.finish(images)
+            batch_names = [batch_names[i] for i in keep]   # files Pillow refuses are dropped, as the reference does
+            if not batch_names:
+                continue
+        elif gpu_preprocess is not None:
             images = gpu_preprocess(images)
         o = backend.encode_gallery(images.to(backend.device, non_blocking=True), want_f32=False, want_bf16=True,
                                    want_raws_f32=False, want_raws_bf16=keep_raws)

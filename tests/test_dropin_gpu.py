@@ -311,3 +311,83 @@ def test_index_build_with_gpu_preprocess_equals_pil_path(staged_tree):
         sys.modules.pop("data_utils", None)
     assert a.names == b.names == staged_tree["names"]
     assert torch.equal(a.feats, b.feats) and torch.equal(a.raws, b.raws)
+
+
+def test_index_build_with_native_png_feeder_equals_pil_path(staged_tree, tmp_path):
+    """SURVEY §8f N2, input side: the index built from file NAMES (`preprocess=retrieval.image_path`: native threaded PNG
+    decode into a pinned arena + GPU resize, no DataLoader workers) is bit-identical to the one the reference's chain
+    builds (`PIL.Image.open` + `targetpad_transform` in DataLoader workers, utils.py:54-64, data_utils.py:91-105), on a
+    folder that mixes what the datasets hold (RGB of many sizes) with what they might (gray, palette, alpha, 16-bit, a
+    JPEG, a corrupt file: Pillow's own chain for those, dropped where it raises)."""
+    import importlib
+
+    import PIL.Image
+
+    from sprc_b200 import retrieval as R
+    from sprc_b200.model import Blip2QformerCirAlignPrompt
+    from sprc_b200.preprocess import PngIndexFeeder, TargetPadPreprocessor
+
+    rng = np.random.default_rng(11)
+    folder = tmp_path / "imgs"
+    folder.mkdir()
+    files = []
+    for i in range(70):
+        h, w = int(rng.integers(60, 420)), int(rng.integers(60, 520))
+        px = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        kind = ("RGB", "RGB", "RGB", "RGB", "L", "RGB", "P", "RGBA", "I16", "JPG")[i % 10]
+        p = str(folder / f"im{i:03d}.png")
+        if kind == "RGB":
+            PIL.Image.fromarray(px[..., :3], "RGB").save(p)
+        elif kind == "L":
+            PIL.Image.fromarray(px[..., 0], "L").save(p)
+        elif kind == "P":
+            PIL.Image.fromarray(px[..., :3], "RGB").quantize(64).save(p)
+        elif kind == "RGBA":
+            PIL.Image.fromarray(px, "RGBA").save(p)
+        elif kind == "I16":
+            PIL.Image.fromarray(rng.integers(0, 65535, (h, w)).astype(np.uint16)).save(p)
+        else:
+            PIL.Image.fromarray(px[..., :3], "RGB").save(p, format="JPEG")
+        files.append(p)
+    bad = str(folder / "im999.png")
+    data = bytearray(open(files[0], "rb").read())
+    data[data.index(b"IDAT") + 30] ^= 0x55
+    open(bad, "wb").write(bytes(data))
+    files.insert(17, bad)
+
+    class Folder:   # the datasets' classic-mode protocol (data_utils.py:253-270: name, preprocess(Image.open(path)); None on error)
+        def __init__(self, preprocess):
+            self.preprocess = preprocess
+
+        def __len__(self):
+            return len(files)
+
+        def __getitem__(self, i):
+            try:
+                return os.path.basename(files[i])[:-4], self.preprocess(PIL.Image.open(files[i]))
+            except Exception as e:  # noqa: BLE001
+                print(f"Exception: {e}")
+                return None
+
+    src = os.path.join(staged_tree["root"], "src")
+    sys.path.insert(0, src)
+    try:
+        du = importlib.import_module("data_utils")
+        importlib.reload(du)
+        ref_tf = du.targetpad_transform(1.25, 224)
+        model = Blip2QformerCirAlignPrompt(vit_model="clip_L", device="cuda:0", max_images=32, max_queries=8,
+                                           vit_depth=2, qf_layers=2)
+        model.load_state_dict(torch.load(staged_tree["ckpt"])["Blip2QformerCirAlignPrompt"])
+        from torch.utils.data.dataloader import default_collate
+
+        a = R.build_index(Folder(ref_tf), model, batch_size=16, num_workers=0,
+                          collate_fn=lambda b: default_collate([x for x in b if x is not None]))
+        feeder = PngIndexFeeder(TargetPadPreprocessor(1.25, 224, device="cuda:0"), fallback=ref_tf, threads=4)
+        b = R.build_index(Folder(R.image_path), model, batch_size=16, png_feeder=feeder)
+    finally:
+        sys.path.remove(src)
+        sys.modules.pop("data_utils", None)
+    print(f"\n[png feeder] native {feeder.n_native}, Pillow chain {feeder.n_fallback}, dropped {feeder.n_dropped}")
+    assert feeder.n_dropped == 1 and feeder.n_native == 42 and feeder.n_fallback == 28
+    assert a.names == b.names and "im999" not in a.names and len(a.names) == 70
+    assert torch.equal(a.feats, b.feats) and torch.equal(a.raws, b.raws)

@@ -53,8 +53,8 @@ if os.path.exists(f):
             d[1] += v
         tot = sum(v for _, v in agg.values())
         out = [f"ncu --metrics gpu__time_duration.sum --clock-control none --csv  python bench.py --steps 2 --warmup 3 "
-               f"--index-images 128 --no-cpu-baseline   (tools/gpu_round.sh {TAG})",
-               "one query step (592 composed queries, ViT-L Q-Former, gallery 50k -> top-50); per-launch times are "
+               f"--index-images 128 --no-cpu-baseline [...]   (tools/gpu_*.sh, tag {TAG})",
+               "one query step of bench.py's default batch (2368 composed queries since r01p; ViT-L Q-Former, gallery 50k -> top-50); per-launch times are "
                "cold-cache and serialised,", "so the SHARE of the step is the comparable figure "
                "(bench.py roofline.share_of_step reports the live CUDA-event share).", ""]
         for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
