@@ -681,6 +681,18 @@ def main():
     index_s = e0.elapsed_time(e1) / 1e3
     index_ips = n_index / index_s
     launches_index = int(lib.sprc_launch_count() - launches_index0)
+    # one more batch under the library profiler (per-launch CUDA events): what the tcgen05 GEMMs of an index batch reach
+    # on their own, next to the whole-pipeline images/s above
+    import ctypes as _ct
+
+    _pr = (_ct.c_double * 20)()
+    lib.sprc_profile(1)
+    L.check(lib.sprc_encode_gallery(h, L.ptr(img), min(IB, n_local), None, L.ptr(feats), None, L.ptr(raws), st()))
+    torch.cuda.synchronize()
+    L.check(lib.sprc_profile_read(_pr, 5))
+    lib.sprc_profile(0)
+    index_prof = {"gemm_ms": _pr[0], "gemm_tflops": (_pr[1] / (_pr[0] / 1e3) / 1e12) if _pr[0] > 0 else 0.0,
+                  "attention_ms": _pr[4], "layernorm_ms": _pr[8], "images": min(IB, n_local)}
 
     # ---- query pool (host pinned + device copies); reference rows come from the local shard ----
     pool = max(4, min(16, args.steps + args.warmup))
@@ -1036,7 +1048,17 @@ def main():
             "frac_of_qformer_gemm_roofline": value / world * FLOP_PER_QUERY[args.vit] / (pk["tf_sust"] * 1e12),
             "index_build": {"images_per_s_per_gpu": index_ips, "seconds": index_s,
                             "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (pk["tf_sust"] * 1e12),
-                            "images_encoded_per_gpu": n_index, "launches": launches_index},
+                            "images_encoded_per_gpu": n_index, "launches": launches_index,
+                            "gemm_kernels": {"achieved_tflops": index_prof["gemm_tflops"],
+                                             "frac_of_sustained_peak": index_prof["gemm_tflops"] / pk["tf_sust"],
+                                             "ms_per_batch": index_prof["gemm_ms"],
+                                             "attention_ms_per_batch": index_prof["attention_ms"],
+                                             "layernorm_ms_per_batch": index_prof["layernorm_ms"],
+                                             "batch_images": index_prof["images"],
+                                             "how": "one index batch under the library profiler: algorithmic 2*M*N*K of "
+                                                    "every tcgen05 GEMM launch / its CUDA-event time (the whole-pipeline "
+                                                    "fraction above also pays for attention, LayerNorm and the "
+                                                    "fp32-residual epilogues)"}},
             "cpu_baseline": cpu,
             "parity": parity,
             "rerank": rerank,

@@ -326,6 +326,19 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
                dtype);
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  // layout, not just the element count: a transposed [cols, rows] matrix has the right numel and the wrong meaning
+  // (leading singleton dimensions are ignored: cls_token [1,1,Dv], pos_embed [1,257,Dv], query_tokens [1,32,768])
+  {
+    int first = 0;
+    while (first < ndim - 1 && shape[first] == 1) ++first;
+    if (s.rows > 1 && ndim - first >= 2) {
+      int64_t inner = 1;
+      for (int i = first + 1; i < ndim; ++i) inner *= shape[i];
+      SPRC_REQUIRE(inner == s.cols && (s.flexible_rows || shape[first] == s.rows),
+                   "%s: expected a [%lld, %lld] matrix, got leading dimension %lld and %lld elements per row", name,
+                   (long long)s.rows, (long long)s.cols, (long long)shape[first], (long long)inner);
+    }
+  }
   int64_t rows = s.rows;
   if (s.flexible_rows) {
     SPRC_REQUIRE(numel % s.cols == 0 && numel / s.cols <= s.rows && numel > 0, "%s: bad shape (numel %lld)", name,
