@@ -250,6 +250,10 @@ int sprc_tokenize_host(const sprc_tokenizer* t, const char* texts, const int64_t
  * threads <= 0: one per core, at most 32. */
 int sprc_png_decode_files(const char* paths, const int64_t* path_offsets, int n, int threads, uint8_t* out,
                           int64_t out_capacity, int64_t* pixel_offsets, int32_t* wh, int32_t* status);
+/* The decoder's own DEFLATE / zlib inflater (csrc/inflate.h) alone, for tests and micro-benchmarks: 0 when `in` is a
+ * zlib stream that inflates to exactly out_bytes bytes with a matching Adler-32, a positive code otherwise (inside
+ * sprc_png_decode_files such streams are retried with zlib itself). */
+int sprc_op_inflate_zlib(const uint8_t* in, int64_t in_bytes, uint8_t* out, int64_t out_bytes);
 
 #ifdef __cplusplus
 }

@@ -121,6 +121,7 @@ SIGNATURES = {
          c_int64, c_int64, c_float, c_void_p],
     ),
     "sprc_png_decode_files": (c_int, [c_char_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sprc_op_inflate_zlib": (c_int, [c_char_p, c_int64, c_void_p, c_int64]),
     "sprc_tokenizer_create": (c_int, [c_char_p, c_int64, POINTER(c_void_p)]),
     "sprc_tokenizer_destroy": (None, [c_void_p]),
     "sprc_tokenize_host": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/sprc_b200.h"
+#include "inflate.h"
 
 namespace sprc { int set_error(int code, const char* fmt, ...); }  // runtime.cu
 
@@ -191,10 +192,14 @@ int32_t decode(const std::vector<uint8_t>& d, const PngInfo& o, uint8_t* out, st
   const size_t stride = (size_t(o.w) * bits + 7) / 8;
   const size_t bpp = std::max<size_t>(1, bits / 8);
   raw.resize((stride + 1) * o.h);
-  uLongf got = static_cast<uLongf>(raw.size());
-  const int zr = uncompress(raw.data(), &got, idat.data(), static_cast<uLong>(idat.size()));
-  // Z_BUF_ERROR with a full output buffer = trailing data after the last scanline, which Pillow tolerates
-  if (!(zr == Z_OK || (zr == Z_BUF_ERROR && got == raw.size())) || got != raw.size()) return PNG_CORRUPT;
+  // own DEFLATE decoder first (inflate.h: ~2x zlib on photo-like PNGs); whatever it refuses goes through zlib, so the
+  // set of accepted streams is zlib's
+  if (sprc_inflate::inflate_zlib_exact(idat.data(), idat.size(), raw.data(), raw.size()) != 0) {
+    uLongf got = static_cast<uLongf>(raw.size());
+    const int zr = uncompress(raw.data(), &got, idat.data(), static_cast<uLong>(idat.size()));
+    // Z_BUF_ERROR with a full output buffer = trailing data after the last scanline, which Pillow tolerates
+    if (!(zr == Z_OK || (zr == Z_BUF_ERROR && got == raw.size())) || got != raw.size()) return PNG_CORRUPT;
+  }
   const uint8_t* prev = nullptr;
   for (uint32_t y = 0; y < o.h; ++y) {
     uint8_t* line = raw.data() + size_t(y) * (stride + 1);
@@ -268,4 +273,11 @@ extern "C" int sprc_png_decode_files(const char* paths, const int64_t* path_offs
     std::vector<uint8_t>().swap(files[i]);
   });
   return 0;
+}
+
+// Test / micro-benchmark entry: the DEFLATE decoder of inflate.h alone (no zlib fallback).  Returns 0 when `in` is a
+// zlib stream that inflates to exactly out_bytes bytes with a matching Adler-32.
+extern "C" int sprc_op_inflate_zlib(const uint8_t* in, int64_t in_bytes, uint8_t* out, int64_t out_bytes) {
+  if (!in || !out || in_bytes < 0 || out_bytes < 0) return sprc::set_error(-22, "sprc_op_inflate_zlib: bad argument");
+  return sprc_inflate::inflate_zlib_exact(in, static_cast<size_t>(in_bytes), out, static_cast<size_t>(out_bytes));
 }

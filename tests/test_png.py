@@ -213,3 +213,87 @@ def test_large_batch_thread_counts_agree(tmp_path):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     for i, p in enumerate(paths):
         assert np.array_equal(b.image(i), _pil_rgb(p))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the decoder's own DEFLATE inflater (csrc/inflate.h) against zlib
+# ---------------------------------------------------------------------------------------------------
+def _inflate(lib, comp: bytes, n_out: int):
+    out = np.zeros(max(n_out, 1), dtype=np.uint8)
+    rc = lib.sprc_op_inflate_zlib(comp, len(comp), out.ctypes.data, n_out)
+    return rc, out[:n_out].tobytes()
+
+
+def _payloads(rng):
+    yield b""
+    yield b"a"
+    yield b"abc" * 5
+    yield bytes(1000)                                             # one long run (distance 1)
+    yield bytes(rng.integers(0, 256, 70000, dtype=np.uint8))      # incompressible: stored blocks at level 0, literals else
+    yield bytes(rng.integers(0, 4, 50000, dtype=np.uint8))        # tiny alphabet: short codes, many matches
+    yield (b"0123456789abcdef" * 5000)[:70001]                    # long matches at distance 16
+    yield bytes((np.arange(100000) % 251).astype(np.uint8))       # distance 251 matches of maximal length
+    text = (b"the quick brown fox jumps over the lazy dog; " * 300)
+    yield text
+    img = _smooth(rng, 120, 160, 3)                               # filtered photo-like scanlines (what a PNG holds)
+    yield bytes(np.diff(img.astype(np.int16), axis=1, prepend=0).astype(np.uint8).reshape(-1))
+    big = rng.integers(0, 256, 300000, dtype=np.uint8)
+    big[100000:200000] = big[0:100000]                            # matches at distance 100000 > 32768: not representable,
+    yield bytes(big)                                              # the compressor must fall back to literals
+    yield bytes(rng.choice(np.arange(256, dtype=np.uint8), 200000,
+                           p=np.r_[np.full(8, 0.1), np.full(248, 0.2 / 248)]))   # skewed: code lengths up to 15
+
+
+def test_inflate_equals_zlib_all_levels_and_strategies():
+    from sprc_b200 import _lib as L
+
+    lib = L.load()
+    rng = np.random.default_rng(5)
+    n = 0
+    for data in _payloads(rng):
+        for level in (0, 1, 3, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                for wbits in (15, 9):
+                    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, strategy)
+                    comp = c.compress(data) + c.flush()
+                    rc, out = _inflate(lib, comp, len(data))
+                    assert rc == 0, (len(data), level, strategy, wbits, rc)
+                    assert out == data, (len(data), level, strategy, wbits)
+                    n += 1
+        # several deflate blocks in one stream (Z_FULL_FLUSH emits an empty stored block between them)
+        c = zlib.compressobj(6)
+        third = len(data) // 3
+        comp = c.compress(data[:third]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(data[third:]) + c.flush()
+        rc, out = _inflate(lib, comp, len(data))
+        assert rc == 0 and out == data
+    assert n >= 500
+
+
+def test_inflate_refuses_what_it_must():
+    from sprc_b200 import _lib as L
+
+    lib = L.load()
+    rng = np.random.default_rng(6)
+    data = bytes(_smooth(rng, 64, 96, 3).reshape(-1))
+    comp = zlib.compress(data, 6)
+    assert _inflate(lib, comp, len(data))[0] == 0
+    assert _inflate(lib, comp, len(data) - 1)[0] != 0            # output longer than the buffer
+    assert _inflate(lib, comp, len(data) + 1)[0] != 0            # output shorter than the caller expects
+    assert _inflate(lib, comp[:-1], len(data))[0] != 0           # trailer cut
+    assert _inflate(lib, comp[:len(comp) // 2], len(data))[0] != 0
+    bad = bytearray(comp)
+    bad[-1] ^= 1
+    assert _inflate(lib, bytes(bad), len(data))[0] != 0          # Adler-32 mismatch
+    assert _inflate(lib, b"\x78\x9c" + b"\x07" + bytes(8), 0)[0] != 0   # reserved block type 3
+    assert _inflate(lib, comp + b"trailing", len(data))[0] == 0  # bytes after the trailer are tolerated
+    # random corruption anywhere in the stream: never a crash, and whenever the decoder says 0 the bytes are zlib's
+    n_ok = 0
+    for i in range(400):
+        b = bytearray(comp)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(2, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = _inflate(lib, bytes(b), len(data))
+        if rc == 0:
+            n_ok += 1
+            assert zlib.decompress(bytes(b)) == out
+    assert n_ok < 20
