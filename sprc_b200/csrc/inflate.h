@@ -77,7 +77,7 @@ inline bool build_table(const uint8_t* lens, int nsym, int kind, int primary_bit
       e.op = kDistExtra[sym];
     } else if (sym < 256) {
       e.base = static_cast<uint16_t>(sym);
-      e.op = OP_LITERAL;
+      e.op = OP_LITERAL | 1;   // low bits: number of literals this entry emits (pairs are formed below)
     } else if (sym == 256) {
       e.base = 0;
       e.op = OP_EOB;
@@ -131,6 +131,22 @@ inline bool build_table(const uint8_t* lens, int nsym, int kind, int primary_bit
       e.bits = static_cast<uint8_t>(l - primary_bits);
       const uint32_t start = table[pre].base;
       for (uint32_t i = rev >> primary_bits; i < (1u << sub_bits); i += 1u << (l - primary_bits)) table[start + i] = e;
+    }
+  }
+  if (kind == 0) {
+    // Two literals per lookup where both codes fit in the primary index: entry i = (first literal, second literal) when
+    // the bits left after the first code already determine a second literal code.  Photo-like PNG streams are mostly
+    // literals with 4..7-bit codes, and the decode loop is a serial chain (lookup -> shift -> lookup), so every pair
+    // saves one trip of that chain.
+    static thread_local Entry orig[1 << LL_BITS];
+    memcpy(orig, table, sizeof(Entry) * static_cast<size_t>(psize));
+    for (int i = 0; i < psize; ++i) {
+      const Entry e1 = orig[i];
+      if (e1.op != (OP_LITERAL | 1) || e1.bits >= primary_bits) continue;
+      const Entry e2 = orig[i >> e1.bits];
+      if (e2.op != (OP_LITERAL | 1) || e1.bits + e2.bits > primary_bits) continue;
+      table[i] = Entry{static_cast<uint16_t>(e1.base | (e2.base << 8)), static_cast<uint8_t>(e1.bits + e2.bits),
+                       static_cast<uint8_t>(OP_LITERAL | 2)};
     }
   }
   return true;
@@ -266,20 +282,23 @@ inline int inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t cap, si
         ip += (63 - bitcnt) >> 3;
         bitcnt |= 56;
         Entry e = ll[bitbuf & ((1u << LL_BITS) - 1)];
-        if (e.op & OP_LITERAL) {   // up to three literals per refill (3 x 15 bits < 56)
+        if (e.op & OP_LITERAL) {   // up to three lookups per refill (3 x 11 bits < 56), one or two literals each
           bitbuf >>= e.bits;
           bitcnt -= e.bits;
-          *op++ = static_cast<uint8_t>(e.base);
+          memcpy(op, &e.base, 2);   // the second byte is only kept when the entry holds a pair
+          op += e.op & 3;
           e = ll[bitbuf & ((1u << LL_BITS) - 1)];
           if (e.op & OP_LITERAL) {
             bitbuf >>= e.bits;
             bitcnt -= e.bits;
-            *op++ = static_cast<uint8_t>(e.base);
+            memcpy(op, &e.base, 2);
+            op += e.op & 3;
             e = ll[bitbuf & ((1u << LL_BITS) - 1)];
             if (e.op & OP_LITERAL) {
               bitbuf >>= e.bits;
               bitcnt -= e.bits;
-              *op++ = static_cast<uint8_t>(e.base);
+              memcpy(op, &e.base, 2);
+              op += e.op & 3;
               continue;
             }
           }
@@ -292,7 +311,7 @@ inline int inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t cap, si
           bitbuf >>= e.bits;
           bitcnt -= e.bits;
           e = ll[e.base + (bitbuf & ((1u << (e.op & OP_EXTRA_MASK)) - 1))];
-          if (e.op & OP_LITERAL) {
+          if (e.op & OP_LITERAL) {   // subtable entries are single literals
             bitbuf >>= e.bits;
             bitcnt -= e.bits;
             *op++ = static_cast<uint8_t>(e.base);
@@ -362,8 +381,10 @@ inline int inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t cap, si
         if (e.op & OP_INVALID) return 17;
         take(e.bits);
         if (e.op & OP_LITERAL) {
-          if (op >= out_end) return 18;
+          const int nl = e.op & 3;
+          if (out_end - op < nl) return 18;
           *op++ = static_cast<uint8_t>(e.base);
+          if (nl == 2) *op++ = static_cast<uint8_t>(e.base >> 8);
         } else if (e.op & OP_EOB) {
           done = true;
         } else {
