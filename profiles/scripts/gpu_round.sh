@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: GPU tests, default bench (+ reference arm), ncu launch list, ncu --set full captures.
-# usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+# usage: gpurun --timeout 1500 -- 'bash profiles/scripts/gpu_round.sh TAG'
 TAG=${1:-r01}
 O=gpurun_out
 mkdir -p $O

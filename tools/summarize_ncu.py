@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise the ncu outputs of tools/gpu_round.sh (gpurun_out/<TAG>_*) into profiles/:
+"""Summarise the ncu outputs of profiles/scripts/gpu_round.sh (gpurun_out/<TAG>_*) into profiles/:
   <TAG>_ncu_launch_summary.txt   per-kernel share of one query step (cold, serialised launch list)
   <TAG>_ncu_full_summary.txt     key metrics of the --set full captures
   ncu_traffic.json               dram bytes per launch (bench.py roofline.traffic)
@@ -88,7 +88,7 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("launch__cluster_size", "cluster"), ("launch__registers_per_thread", "regs/thread"),
         ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %")]
-out = [f"ncu --set full --clock-control none --import-source on (tools/gpu_round.sh {TAG}; one B200; cold caches)", ""]
+out = [f"ncu --set full --clock-control none --import-source on (profiles/scripts/gpu_round.sh {TAG}; one B200; cold caches)", ""]
 for name in ["gemm", "scan", "ln", "attnqf"]:
     f = os.path.join(O, f"{TAG}_full_{name}_raw.csv")
     if not os.path.exists(f):
