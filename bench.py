@@ -400,7 +400,7 @@ def eager_gpu_rows(args, sd, feats, dev):
     return rows
 
 
-def index_feed_rows(args, model, dev, n_files=384, w=640, h=480):
+def index_feed_rows(args, model, dev, n_files=1024, w=640, h=480):
     """SURVEY 8f N2, input side: gallery indexing FROM FILES.  `n_files` synthetic photo-like PNGs (640 x 480 RGB) on
     local disk, indexed (a) through the native feed - file names -> C++ PNG decode into a pinned arena (all host cores)
     -> one H2D copy -> GPU TargetPad / bicubic resize / normalise -> ViT + Q-Former; (b) through the reference's feed -

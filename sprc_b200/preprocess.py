@@ -208,14 +208,25 @@ class PngBatchDecoder:
         self._pin = bool(pin) and torch.cuda.is_available()
         self._arenas = [self._alloc(arena_bytes), self._alloc(arena_bytes)]
         self._copied = [None, None]   # CUDA event per arena: the last H2D copy that read it
+        self._copy_stream = None
         self._turn = 0
 
-    def mark_copied(self, batch: "PngBatch") -> None:
-        """Call after enqueuing the H2D copy of `batch`: its arena is not decoded into again before that copy ran."""
-        if torch.cuda.is_available():
+    def to_device(self, batch: "PngBatch", nbytes: int, device) -> torch.Tensor:
+        """The used prefix of the batch's arena on `device`, copied on a side stream (so the copy is not queued behind
+        the encoder work of earlier batches) and ordered before whatever the current stream does next.  The arena is
+        not decoded into again before that copy has run."""
+        dev = torch.device(device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._copy_stream):
+            pix_d = batch.arena[:nbytes].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record()
-            self._copied[batch.slot] = ev
+            ev.record(self._copy_stream)
+        cur.wait_event(ev)
+        pix_d.record_stream(cur)
+        self._copied[batch.slot] = ev
+        return pix_d
 
     def _alloc(self, nbytes: int) -> torch.Tensor:
         t = torch.empty(int(nbytes), dtype=torch.uint8)
@@ -269,9 +280,11 @@ class PngIndexFeeder:
 
         n = len(batch.paths)
         native = [i for i in range(n) if batch.status[i] == 0 and batch.wh[i, 2] in (0, 1)]
-        out_native = self.pre.run_packed(batch.arena, [(int(batch.wh[i, 0]), int(batch.wh[i, 1])) for i in native],
-                                         [int(batch.offsets[i]) for i in native])
-        self.decoder.mark_copied(batch)
+        sizes = [(int(batch.wh[i, 0]), int(batch.wh[i, 1])) for i in native]
+        offs = [int(batch.offsets[i]) for i in native]
+        end = max([o + 3 * w * h for o, (w, h) in zip(offs, sizes)], default=0)
+        pix = self.decoder.to_device(batch, end, self.pre.device) if end else batch.arena
+        out_native = self.pre.run_packed(pix, sizes, offs)
         host = {}
         for i in range(n):
             if i in native:
