@@ -23,7 +23,7 @@ def _case(name):
     return g, c, sd
 
 
-@pytest.mark.parametrize("name", ["tiny_L", "tiny_g", "full_L"])
+@pytest.mark.parametrize("name", ["tiny_L", "tiny_g", "full_L", "full_g"])
 def test_restatement_matches_reference_golden(name):
     g, c, sd = _case(name)
     images = synth.make_images(c["n_images"])
@@ -31,7 +31,7 @@ def test_restatement_matches_reference_golden(name):
         feats, raws = R.extract_target_features(sd, images)
         fusion = R.fusion_features(sd, raws[g["ref_rows"]], g["input_ids"], g["attention_mask"])
         sim = R.similarity(fusion, feats)
-    assert (raws[:, g["raw_rows"]] - g["raws_rows"]).abs().max().item() < 5e-5
+    assert (raws[:, g["raw_rows"]] - g["raws_rows"]).abs().max().item() < 5e-5   # ViT-g, 39 blocks: 7e-6 measured
     assert (feats - g["feats"]).abs().max().item() < 2e-6
     assert (fusion - g["fusion"]).abs().max().item() < 2e-6
     assert (sim - g["sim"]).abs().max().item() < 2e-6
@@ -51,8 +51,8 @@ def test_restatement_rerank_matches_reference_golden(name):
 
 
 def test_golden_full_g_is_self_consistent():
-    """ViT-g full depth is too slow to re-run on CPU in the unit suite; check the stored reference outputs'
-    invariants (unit-norm rows, sim == max-over-tokens of fusion . feats)."""
+    """Invariants of the stored reference outputs (unit-norm rows, sim == max-over-tokens of fusion . feats); the
+    restatement itself is re-derived against this golden above (3 images through all 39 ViT-g blocks: ~10 s)."""
     g = torch.load(os.path.join(GOLDEN, "full_g.pt"))
     assert (g["feats"].norm(dim=-1) - 1).abs().max().item() < 1e-5
     assert (g["fusion"].norm(dim=-1) - 1).abs().max().item() < 1e-5
