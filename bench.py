@@ -572,9 +572,8 @@ def vitg_rows(args, world, rank, dev, pk, dist):
                                           st()))
             else:
                 dist.all_gather_into_tensor(fusion_all, fusion)
-                for r in range(world):
-                    L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all[r * Bq:]), Bq, L.ptr(feats), n_rows, lo, k,
-                                              L.ptr(send[r, 0]), L.ptr(send[r, 1]), None, st()))
+                L.check(lib.sprc_sim_topk_grouped(h, L.ptr(fusion_all), world * Bq, L.ptr(feats), n_rows, lo, k,
+                                                  L.ptr(send[0, 0]), L.ptr(send[0, 1]), Bq, 2 * Bq * k, st()))
                 dist.all_to_all_single(recv, send)
                 L.check(lib.sprc_topk_merge_packed(h, L.ptr(recv), world, Bq, k, L.ptr(sc), L.ptr(ix), st()))
 
@@ -754,9 +753,10 @@ def main():
                                       st()))
         else:
             dist.all_gather_into_tensor(fusion_all, fusion)
-            for r in range(world):
-                L.check(lib.sprc_sim_topk(h, L.ptr(fusion_all[r * Bq:]), Bq, L.ptr(feats), n_local, lo, k,
-                                          L.ptr(cand_send[r, 0]), L.ptr(cand_send[r, 1]), None, st()))
+            # ONE scan launch for all world * Bq queries against this rank's shard; the [Bq, k] block of rank r's queries
+            # lands in slot r of the exchange buffer (sprc_sim_topk_grouped)
+            L.check(lib.sprc_sim_topk_grouped(h, L.ptr(fusion_all), world * Bq, L.ptr(feats), n_local, lo, k,
+                                              L.ptr(cand_send[0, 0]), L.ptr(cand_send[0, 1]), Bq, 2 * Bq * k, st()))
             dist.all_to_all_single(cand_recv, cand_send)
             L.check(lib.sprc_topk_merge_packed(h, L.ptr(cand_recv), world, Bq, k, L.ptr(msc), L.ptr(mix), st()))
 

@@ -107,6 +107,14 @@ int sprc_encode_query_lens(sprc_handle* h, const void* ref_raws, int ref_dtype, 
 int sprc_sim_topk(sprc_handle* h, const void* queries_bf16, int Q, const void* gallery_bf16, int64_t N,
                   int64_t row_offset, int k, float* out_score, int32_t* out_idx, float* out_full, void* stream);
 
+/* The same scan with a GROUPED output, for the multi-GPU step: Q = world * group_rows queries (all
+ * ranks' batches after the all-gather of query vectors) against this rank's shard in ONE launch; the [group_rows, k]
+ * block of query group g is written at out_score / out_idx + g * group_stride (elements), i.e. straight into the
+ * exchange buffer [dest rank][scores | rows][Bq][k] with group_stride = 2 * Bq * k and out_idx = out_score + Bq * k. */
+int sprc_sim_topk_grouped(sprc_handle* h, const void* queries_bf16, int Q, const void* gallery_bf16, int64_t N,
+                          int64_t row_offset, int k, float* out_score, int32_t* out_idx, int group_rows,
+                          int64_t group_stride, void* stream);
+
 /* Merge P candidate lists per query (the per-shard top-k after the NCCL all-gather):
  * cand_* are [P,Q,k]; output [Q,k] sorted by (score desc, idx asc). */
 int sprc_topk_merge(sprc_handle* h, const float* cand_score, const int32_t* cand_idx, int P, int Q, int k,
@@ -215,6 +223,37 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
 int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O, int B, int H, int ldq, int ldk, int ldv,
                             int ldo, int q_batch_rows, const int32_t* kv_idx0, const int32_t* kv_idx1,
                             int64_t kv_rows_total, int64_t kv_head_stride, float scale, void* stream);
+
+/* LayerNorm folded into the neighbouring GEMMs (csrc/gemm2_fold.cu, csrc/ln_fold.cu, csrc/common.h GemmFold;
+ * Qformer.py:291-295,373-381 post-LN sublayers, eva_vit.py:173-176 pre-LN blocks).  Row statistics: N / 64 (mean, M2)
+ * float pairs per row (12 for rows of 768).
+ * sprc_op_fold_weight: Wf = round16(W diag(gamma)), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n].
+ * sprc_op_gemm_fold, consumer (fold->st_in set): out_bf16 = act(rstd (A Wf^T - mean c) + d), bias = d;
+ * producer (fold->st_out set): out_f32 = A W^T + bias + LN(resid) (resid as is when st_res is null; may alias out_f32),
+ * fold->out16 = its raw 16-bit copy, fold->st_out = its row statistics.  Rows >= split take the *2 members. */
+typedef struct sprc_gemm_fold {
+  int32_t split;
+  float eps;
+  const void* st_in;
+  const void* st_in2;
+  const float* c;
+  const float* c2;
+  const float* resid;
+  const void* st_res;
+  const void* st_res2;
+  const float* res_g;
+  const float* res_b;
+  const float* res_g2;
+  const float* res_b2;
+  void* st_out;
+  void* st_out2;
+  void* out16;
+} sprc_gemm_fold;
+int sprc_op_fold_weight(const void* W_bf16, const float* gamma, const float* beta, const float* bias, int N, int K,
+                        void* Wf_bf16, float* c, float* d, void* stream);
+int sprc_op_gemm_fold(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
+                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
+                      const sprc_gemm_fold* fold, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side caption tokenizer (csrc/tokenizer.cpp; no CUDA).  Replaces the per-batch Python tokenizer call inside

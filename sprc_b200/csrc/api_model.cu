@@ -121,8 +121,27 @@ int sprc_encode_query_lens(sprc_handle* h, const void* ref_raws, int ref_dtype, 
                                   static_cast<bf16*>(fusion_bf16), S(stream));
 }
 
+static int sim_topk_api(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N, int64_t row_offset,
+                        int k, float* out_score, int32_t* out_idx, float* out_full, int group_rows,
+                        int64_t group_stride, void* stream);
+
 int sprc_sim_topk(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N, int64_t row_offset,
                   int k, float* out_score, int32_t* out_idx, float* out_full, void* stream) {
+  return sim_topk_api(h, queries, Q, gallery, N, row_offset, k, out_score, out_idx, out_full, 0, 0, stream);
+}
+
+int sprc_sim_topk_grouped(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N,
+                          int64_t row_offset, int k, float* out_score, int32_t* out_idx, int group_rows,
+                          int64_t group_stride, void* stream) {
+  if (!out_score || !out_idx || group_rows <= 0 || group_stride < (int64_t)group_rows * k)
+    return set_error(-22, "sprc_sim_topk_grouped: outputs, group_rows > 0 and group_stride >= group_rows * k needed");
+  return sim_topk_api(h, queries, Q, gallery, N, row_offset, k, out_score, out_idx, nullptr, group_rows, group_stride,
+                      stream);
+}
+
+static int sim_topk_api(sprc_handle* h, const void* queries, int Q, const void* gallery, int64_t N, int64_t row_offset,
+                        int k, float* out_score, int32_t* out_idx, float* out_full, int group_rows,
+                        int64_t group_stride, void* stream) {
   if (!queries || !gallery) return set_error(-22, "sprc_sim_topk: null argument");
   const bool want_topk = out_score || out_idx;
   void* ws = nullptr;
@@ -140,7 +159,7 @@ int sprc_sim_topk(sprc_handle* h, const void* queries, int Q, const void* galler
     }
   }
   return sim_topk(static_cast<const bf16*>(queries), Q, static_cast<const bf16*>(gallery), N, row_offset, k,
-                  out_score, out_idx, out_full, ws, ws_bytes, S(stream));
+                  out_score, out_idx, out_full, ws, ws_bytes, S(stream), group_rows, static_cast<size_t>(group_stride));
 }
 
 int sprc_topk_merge(sprc_handle*, const float* cand_score, const int32_t* cand_idx, int P, int Q, int k,

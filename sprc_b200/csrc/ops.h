@@ -73,6 +73,12 @@ int l2norm_rows256(const float* in, size_t in_row_stride, int rows, float* out_f
 int itm_head_prob(const float* h, int rows_per_pair, int pairs, const float* w, const float* b, float* p,
                   cudaStream_t st);
 
+// ---- ln_fold.cu ------------------------------------------------------------------------------
+// LayerNorm fold (GemmFold, common.h): Wf = round16(W diag(gamma)), c = row sums of Wf, d = W beta + bias
+bool ln_fold_enabled();
+int fold_weight(const bf16* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf,
+                float* c, float* d, cudaStream_t st);
+
 // ---- preprocess.cu ---------------------------------------------------------------------------
 // TargetPad + bicubic Resize + CenterCrop + ToTensor + Normalize (data_utils.py:52-72, 91-105) on decoded RGB uint8
 // images, bit-exact with PIL/torchvision; descriptors and coefficient tables come from sprc_b200/preprocess.py.
@@ -109,7 +115,7 @@ int attention(const AttnDesc& a, cudaStream_t st);
 // ---- scan.cu ---------------------------------------------------------------------------------
 int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t row_offset, int k,
              float* out_score, int32_t* out_idx, float* out_full, void* workspace, size_t workspace_bytes,
-             cudaStream_t st);
+             cudaStream_t st, int out_group_rows = 0, size_t out_group_stride = 0);
 size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full);
 int topk_merge(const float* cand_score, const int32_t* cand_idx, int P, int Q, int k, float* out_score,
                int32_t* out_idx, cudaStream_t st, size_t pstride = 0);   // pstride: elements between lists (0 = Q*k)

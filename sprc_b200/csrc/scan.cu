@@ -321,9 +321,14 @@ __device__ __forceinline__ void bitonic_sort_desc(u64* s, int n) {
 __global__ void __launch_bounds__(1024)
 topk_merge_kernel(const u64* __restrict__ cand_keys, size_t qpad, const float* __restrict__ cand_score,
                   const int32_t* __restrict__ cand_idx, size_t pstride, int P, int Q, int k, int npow2,
-                  float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+                  float* __restrict__ out_score, int32_t* __restrict__ out_idx, int group_rows, size_t group_stride) {
   extern __shared__ u64 skeys[];
   const int q = blockIdx.x;
+  // grouped output: queries [g * group_rows, (g + 1) * group_rows) write their [group_rows, k] block at g * group_stride
+  // (the multi-GPU exchange buffer [dest rank][scores | rows][Bq][k]); dense [Q, k] when group_rows == 0
+  const size_t ob = group_rows > 0 ? static_cast<size_t>(q / group_rows) * group_stride +
+                                         static_cast<size_t>(q % group_rows) * k
+                                   : static_cast<size_t>(q) * k;
   const int total = P * k;
   for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
     u64 key = 0;
@@ -344,8 +349,8 @@ topk_merge_kernel(const u64* __restrict__ cand_keys, size_t qpad, const float* _
     float sc;
     int32_t ix;
     decode_key(j < npow2 ? skeys[j] : 0, sc, ix);
-    if (out_score) out_score[static_cast<size_t>(q) * k + j] = sc;
-    if (out_idx) out_idx[static_cast<size_t>(q) * k + j] = ix;
+    if (out_score) out_score[ob + j] = sc;
+    if (out_idx) out_idx[ob + j] = ix;
   }
 }
 
@@ -372,7 +377,8 @@ static int next_pow2(int v) {
 }
 
 static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int32_t* ci, int P, int Q, int k,
-                        float* out_score, int32_t* out_idx, cudaStream_t st, size_t pstride = 0) {
+                        float* out_score, int32_t* out_idx, cudaStream_t st, size_t pstride = 0, int group_rows = 0,
+                        size_t group_stride = 0) {
   if (pstride == 0) pstride = static_cast<size_t>(Q) * k;
   const int np2 = next_pow2(P * k < 2 ? 2 : P * k);
   const size_t smem = static_cast<size_t>(np2) * 8;
@@ -383,7 +389,8 @@ static int launch_merge(const u64* keys, size_t qpad, const float* cs, const int
     configured = 200 * 1024;
   }
   prof_begin(st);
-  topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, pstride, P, Q, k, np2, out_score, out_idx);
+  topk_merge_kernel<<<Q, 1024, smem, st>>>(keys, qpad, cs, ci, pstride, P, Q, k, np2, out_score, out_idx, group_rows,
+                                           group_stride);
   prof_end(PROF_MERGE, 0.0, (double)P * k * Q * 8, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
@@ -415,7 +422,12 @@ static void scan_plan(int Q, long long N, int k, int& qtiles, int& splits, long 
 
 size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full) {
   const size_t qpad = static_cast<size_t>((Q + SQ - 1) / SQ) * SQ;
-  if (k <= KCAP) return static_cast<size_t>(device_sm_count() + 8) * KCAP * qpad * 8 + 256;
+  if (k <= KCAP) {   // splits * k candidate keys per (padded) query
+    int qtiles, splits;
+    long long ips;
+    scan_plan(Q, N, k, qtiles, splits, ips);
+    return static_cast<size_t>(splits) * k * qpad * 8 + 256;
+  }
   const size_t nseg = static_cast<size_t>((N + SEG - 1) / SEG);
   size_t need = ((nseg * k * qpad * 8 + 255) & ~size_t(255)) + 256;
   if (!caller_has_full) need += static_cast<size_t>(Q) * N * 4 + 256;
@@ -424,7 +436,9 @@ size_t sim_topk_workspace_bytes(int Q, int64_t N, int k, bool caller_has_full) {
 
 int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t row_offset, int k,
              float* out_score, int32_t* out_idx, float* out_full, void* workspace, size_t workspace_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, int out_group_rows, size_t out_group_stride) {
+  SPRC_REQUIRE(out_group_rows >= 0 && (out_group_rows == 0 || out_group_stride >= (size_t)out_group_rows * k),
+               "sim_topk: grouped output needs group_stride >= group_rows * k");
   SPRC_REQUIRE(Q > 0 && N > 0, "sim_topk: empty problem (Q=%d N=%lld)", Q, (long long)N);
   SPRC_REQUIRE(N * 32 < (1LL << 31), "sim_topk: gallery shard of %lld images exceeds the 2^31-token TMA coordinate "
                "range; shard it", (long long)N);
@@ -486,7 +500,9 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
   prof_end(PROF_SCAN, 2.0 * Q * (double)N * 32 * 256, (double)N * 32 * 256 * 2 + (double)Q * 512, st);
   count_launch();
   SPRC_CUDA(cudaGetLastError());
-  if (fused) return launch_merge(cand, qpad, nullptr, nullptr, splits, Q, k, out_score, out_idx, st);
+  if (fused)
+    return launch_merge(cand, qpad, nullptr, nullptr, splits, Q, k, out_score, out_idx, st, 0, out_group_rows,
+                        out_group_stride);
   if (want_topk) {
     const int nseg = static_cast<int>((N + SEG - 1) / SEG);
     SPRC_REQUIRE(static_cast<long long>(nseg) * k <= 16384 * 1, "sim_topk: N=%lld with k=%d exceeds the merge capacity",
@@ -495,7 +511,8 @@ int sim_topk(const bf16* queries, int Q, const bf16* gallery, int64_t N, int64_t
     row_topk_kernel<<<grid, 1024, 0, st>>>(full, N, row_offset, k, qpad, cand);
     count_launch();
     SPRC_CUDA(cudaGetLastError());
-    return launch_merge(cand, qpad, nullptr, nullptr, nseg, Q, k, out_score, out_idx, st);
+    return launch_merge(cand, qpad, nullptr, nullptr, nseg, Q, k, out_score, out_idx, st, 0, out_group_rows,
+                        out_group_stride);
   }
   return 0;
 }

@@ -188,3 +188,32 @@ def test_baseline_config_shapes_bit_exact(cfg, Q, N, k, P):
         ties += int((osc[:, :-1] == osc[:, 1:]).sum())
     assert ties > 0   # the grid produces real ties: the lower-row rule was exercised at this size
     print(f"\n[{cfg}] Q={Q} N={N} k={k} shards={P}: bit-exact, {ties} tied neighbours in the top-k lists")
+
+
+@pytest.mark.parametrize("world,Bq,N,k", [(2, 70, 1500, 50), (8, 160, 900, 50), (4, 128, 3000, 51), (3, 5, 64, 64),
+                                          (2, 33, 2000, 100)])
+def test_grouped_output_equals_per_group_scans_and_feeds_the_packed_merge(world, Bq, N, k):
+    """Multi-GPU step: ONE launch for all world * Bq queries against a shard writes, for every rank r, the
+    [Bq, k] scores and rows of r's queries into slot r of the exchange buffer [world][2][Bq][k] - exactly what `world`
+    separate scans wrote before - and `sprc_topk_merge_packed` reads that buffer in place."""
+    lib = L.load()
+    L.check(lib.sprc_set_act_dtype(0))
+    q = synth.make_dyadic((world * Bq, 256), seed=world * 13 + Bq).cuda().bfloat16()
+    g = synth.make_dyadic((N, 32, 256), seed=N + 1).cuda().bfloat16()
+    lo = 1000
+    buf = torch.full((world, 2, Bq, k), -7, device="cuda", dtype=torch.int32)
+    L.check(lib.sprc_sim_topk_grouped(None, L.ptr(q), world * Bq, L.ptr(g), N, lo, k, L.ptr(buf[0, 0]), L.ptr(buf[0, 1]),
+                                      Bq, 2 * Bq * k, L.cur_stream()))
+    torch.cuda.synchronize()
+    for r in range(world):
+        sc, ix, _ = sim_topk(q[r * Bq:(r + 1) * Bq], g, k, row_offset=lo)
+        assert torch.equal(buf[r, 0].view(torch.float32), sc) and torch.equal(buf[r, 1], ix), r
+    # the buffer as one rank's received candidates: P = world lists for Bq queries
+    msc = torch.empty(Bq, k, device="cuda")
+    mix = torch.empty(Bq, k, device="cuda", dtype=torch.int32)
+    L.check(lib.sprc_topk_merge_packed(None, L.ptr(buf), world, Bq, k, L.ptr(msc), L.ptr(mix), L.cur_stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(msc[:, 0]).all() and (mix[:, 0] >= lo).all()
+    # argument contract
+    assert lib.sprc_sim_topk_grouped(None, L.ptr(q), world * Bq, L.ptr(g), N, lo, k, L.ptr(buf[0, 0]), L.ptr(buf[0, 1]),
+                                     Bq, Bq * k - 1, L.cur_stream()) != 0
