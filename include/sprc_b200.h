@@ -226,7 +226,7 @@ int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O
 
 /* LayerNorm folded into the neighbouring GEMMs (csrc/gemm2_fold.cu, csrc/ln_fold.cu, csrc/common.h GemmFold;
  * Qformer.py:291-295,373-381 post-LN sublayers, eva_vit.py:173-176 pre-LN blocks).  Row statistics: N / 64 (mean, M2)
- * float pairs per row (12 for rows of 768).
+ * float pairs per row (12 for rows of 768), stored part-major.
  * sprc_op_fold_weight: Wf = round16(W diag(gamma)), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n].
  * sprc_op_gemm_fold, consumer (fold->st_in set): out_bf16 = act(rstd (A Wf^T - mean c) + d), bias = d;
  * producer (fold->st_out set): out_f32 = A W^T + bias + LN(resid) (resid as is when st_res is null; may alias out_f32),
@@ -234,6 +234,8 @@ int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O
 typedef struct sprc_gemm_fold {
   int32_t split;
   float eps;
+  int32_t st_stride; /* rows per statistics plane: st[part * st_stride + row] (part-major); 0 = M */
+  int32_t reserved;
   const void* st_in;
   const void* st_in2;
   const float* c;
@@ -249,6 +251,8 @@ typedef struct sprc_gemm_fold {
   void* st_out2;
   void* out16;
 } sprc_gemm_fold;
+/* 1 when the model runs the folded schedule in this process (environment SPRC_LN_FOLD, read once). */
+int sprc_ln_fold_enabled(void);
 int sprc_op_fold_weight(const void* W_bf16, const float* gamma, const float* beta, const float* bias, int N, int K,
                         void* Wf_bf16, float* c, float* d, void* stream);
 int sprc_op_gemm_fold(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,

@@ -146,6 +146,8 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
   return attention(a, static_cast<cudaStream_t>(stream));
 }
 
+int sprc_ln_fold_enabled(void) { return ln_fold_enabled() ? 1 : 0; }
+
 int sprc_op_fold_weight(const void* W, const float* gamma, const float* beta, const float* bias, int N, int K,
                         void* Wf, float* c, float* d, void* stream) {
   return fold_weight(static_cast<const bf16*>(W), gamma, beta, bias, N, K, static_cast<bf16*>(Wf), c, d,
@@ -159,6 +161,7 @@ int sprc_op_gemm_fold(const void* A, const void* W, const void* W2, int M, int m
   GemmFold f;
   f.split = fold->split;
   f.eps = fold->eps;
+  f.st_stride = fold->st_stride;
   f.st_in = static_cast<const float2*>(fold->st_in);
   f.st_in2 = static_cast<const float2*>(fold->st_in2);
   f.c = fold->c;

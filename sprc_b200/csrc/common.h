@@ -101,7 +101,8 @@ struct GemmDesc {
 // Post-LN sublayer  y = LN(s), s = dense(a) + x  (Qformer.py:291-295, 373-381) without a LayerNorm kernel: the
 // residual stream holds the PRE-LN sums s (fp32 + a raw 16-bit copy) and per-row statistics; LN is applied where
 // its output is consumed.  Row statistics are width / 64 partials (mean, M2) per row (12 for the Q-Former's 768) = one
-// per 64-column slice an epilogue thread owns, merged (Chan) by whoever reads them - deterministic, no atomics.
+// per 64-column slice an epilogue thread owns, stored PART-major ([part][M rows of the GEMM], so a warp's 32 rows are
+// contiguous) and merged (Chan) by whoever reads them - deterministic, no atomics.
 // The ViT's pre-LN blocks (eva_vit.py:173-176, clip_vit.py:132-139) use the same two forms with a raw residual.
 //   CONSUMER GEMM (st_in != null): A = raw 16-bit s, W = W * diag(gamma) (16-bit), GemmDesc::bias = d = W beta + b,
 //     c = row sums of the rounded folded weight:  out = act(rstd * (acc - mean * c) + d).
@@ -112,6 +113,7 @@ struct GemmDesc {
 // went through different LayerNorms (output_query / output) and may sit in different statistics buffers.
 struct GemmFold {
   int split = 0;
+  int st_stride = 0;   // rows per statistics plane (st[part * st_stride + row]); 0 = the M of the launch
   const float2* st_in = nullptr;
   const float2* st_in2 = nullptr;
   const float* c = nullptr;
@@ -128,6 +130,7 @@ struct GemmFold {
   bf16* out16 = nullptr;
   float eps = 1e-12f;
 };
+constexpr int kFoldParts = 12;   // statistics partials per Q-Former row of 768 (64 columns each)
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)
 int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st);     // CUDA-core checker used by tests only

@@ -33,7 +33,9 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 16;
-constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int STATS_WARP = 2 + EPI_WARPS;      // warp 18: per-row (mean, rstd) of the tile's 128 rows, one tile ahead
+constexpr int THREADS = (3 + EPI_WARPS) * 32;
+constexpr int STATS_BYTES = BM * 8;            // 128 (mean, rstd) pairs (one buffer: the ring leaves no room for two)
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
 constexpr int CHUNK_BYTES = 32 * 64;          // 32 rows x 16 fp32 (or x 32 16-bit values)
@@ -44,8 +46,9 @@ struct Cfg {
   static constexpr int EPI_PER_WARP = MODE == 2 ? 2 * CHUNK_BYTES : CHUNK_BYTES;
   static constexpr int RING_BYTES = STAGES * (A_BYTES + B_BYTES);
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_PER_WARP;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
-  static constexpr int SMEM_TOTAL = RING_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + (MODE == 2 ? 2 * EPI_WARPS : 0) + 2) * 8 + 16;
+  static_assert(RING_BYTES + EPI_BYTES + STATS_BYTES + BAR_BYTES + 1024 <= 227 * 1024, "shared memory budget");
+  static constexpr int SMEM_TOTAL = RING_BYTES + EPI_BYTES + STATS_BYTES + BAR_BYTES + 1024;
 };
 
 struct FoldParams {
@@ -60,21 +63,58 @@ struct FoldParams {
   GemmFold f;
 };
 
-__device__ __forceinline__ void fold_row_stats(const float2* __restrict__ st, int parts, float eps, float& mean,
-                                               float& rstd) {
-  float m = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < parts; ++i) m += __ldg(st + i).x;
-  m /= static_cast<float>(parts);
-  float m2 = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < parts; ++i) {
-    const float2 pt = __ldg(st + i);
-    const float dlt = pt.x - m;
-    m2 += pt.y + 64.0f * dlt * dlt;
+// Statistics partials are stored PART-major, st[part * M + row]: the 32 lanes of an epilogue warp (= 32 consecutive rows)
+// read and write 256 contiguous bytes per partial.  (Row-major partials, as in the first version, cost 32 cache lines
+// per load instruction and made the consumer 0.6-0.8x the plain GEMM: profiles/r02v_fold_probe.log.)
+// One pass, Chan's merge of (mean, M2) over equal-sized slices of 64 columns.
+// Per-row (mean, rstd) from the (mean, M2) partials of the row's 64-column slices (Chan's merge, equal slice sizes).
+// Partials are stored PART-major, st[part * M + row]: the 32 lanes of a warp (= 32 consecutive rows) read and write
+// 256 contiguous bytes per partial.  ONE warp per CTA does this for the 128 rows of a tile, one tile ahead of the
+// epilogue, and hands the result over through shared memory: when each of the 16 epilogue warps merged the partials of
+// its own rows (r02v-r02x), the epilogue's instruction count doubled (ncu r02y: 140 M against 67.5 M warp instructions,
+// tensor pipe 58 % against 90 %) and the epilogue, not the MMA, paced the kernel.
+// Lane l owns rows l, l + 32, l + 64, l + 96 of the tile; four partials of all four rows are loaded per batch.
+__device__ __forceinline__ void tile_row_stats(const float2* __restrict__ st_lo, const float2* __restrict__ st_hi,
+                                               int split, int m0, int lane, int M, int stride, int parts,
+                                               float eps, float2* __restrict__ out) {
+  float m[4], m2[4];
+  const float2* base[4];
+  bool ok[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = m0 + r * 32 + lane;
+    ok[r] = row < M;
+    const float2* st = (split > 0 && m0 + r * 32 >= split) ? st_hi : st_lo;
+    base[r] = st + (ok[r] ? row : 0);
+    m[r] = 0.f;
+    m2[r] = 0.f;
   }
-  mean = m;
-  rstd = rsqrtf(m2 / (64.0f * static_cast<float>(parts)) + eps);
+  for (int i0 = 0; i0 < parts; i0 += 4) {
+    float2 pt[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        pt[j][r] = (i0 + j < parts) ? __ldg(base[r] + static_cast<size_t>(i0 + j) * stride) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j;
+      if (i < parts) {
+        const float inv = __frcp_rn(static_cast<float>(i + 1));
+        const float w = 64.0f * static_cast<float>(i) * inv;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float dlt = pt[j][r].x - m[r];
+          m[r] += dlt * inv;
+          m2[r] += pt[j][r].y + dlt * dlt * w;
+        }
+      }
+    }
+  }
+  const float invn = 1.0f / (64.0f * static_cast<float>(parts));
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    out[r * 32 + lane] = ok[r] ? make_float2(m[r], rsqrtf(m2[r] * invn + eps)) : make_float2(0.f, 1.f);
 }
 
 template <int MODE>
@@ -90,12 +130,15 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sEpi = smem + RING_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + EPI_BYTES);   // used in the leader only
+  float2* sStats = reinterpret_cast<float2*>(smem + RING_BYTES + EPI_BYTES);          // [2][BM] (mean, rstd)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + EPI_BYTES + STATS_BYTES);   // leader only
   uint64_t* empty_bar = full_bar + STAGES;                                          // one per CTA
   uint64_t* tfull_bar = empty_bar + STAGES;                                         // one per CTA
   uint64_t* tempty_bar = tfull_bar + 2;                                             // used in the leader only
   uint64_t* res_bar = tempty_bar + 2;                                               // [EPI_WARPS][2] residual chunk landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+  uint64_t* sfull_bar = res_bar + (MODE == 2 ? 2 * EPI_WARPS : 0);                   // statistics of a tile are in sStats
+  uint64_t* sempty_bar = sfull_bar + 1;                                              // all epilogue warps have read them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,7 +162,10 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
     }
-    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+    if (MODE == 2)
+      for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+    mbar_init(sfull_bar, 1);
+    mbar_init(sempty_bar, EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, 2 * BN);
@@ -191,6 +237,23 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
+  } else if (warp == STATS_WARP) {
+    // ===================== row statistics of the tile's 128 rows, one tile ahead of the epilogue =====================
+    const float2* st_lo = MODE == 1 ? f.st_in : f.st_res;
+    const float2* st_hi = MODE == 1 ? f.st_in2 : f.st_res2;
+    if (st_lo != nullptr) {
+      const int parts = (MODE == 1 ? p.K : p.N) >> 6;
+      uint32_t sph = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int tile = p.rev ? num_tiles - 1 - t : t;
+        const int m0 = (tile / p.num_n_blocks) * (2 * BM) + static_cast<int>(crank) * BM;
+        mbar_wait(sempty_bar, sph ^ 1);   // every epilogue warp has read the previous tile's statistics
+        tile_row_stats(st_lo, st_hi ? st_hi : st_lo, f.split, m0, lane, p.M, f.st_stride, parts, f.eps, sStats);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfull_bar);
+        sph ^= 1;
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..17): 32 rows x 64 columns per warp and tile =====================
     const int q = warp & 3;
@@ -202,6 +265,7 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int as = 0;
     uint32_t aphase = 0;
 
+    uint32_t sph = 0;   // statistics phase (consumer: always; producer: when the residual is normalised)
     if constexpr (MODE == 1) {
       // ---------------- consumer: 16-bit output, two 32-column chunks ----------------
       const uint32_t srow = stile + lane * 64;
@@ -212,13 +276,12 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool w2 = p.m_split > 0 && m0 >= p.m_split;
         const float* bias = w2 ? p.bias2 : p.bias;
         const float* f_c = w2 ? f.c2 : f.c;
-        const int row = m0 + lane;
-        float f_mu = 0.f, f_rs = 1.f;
-        {
-          const bool hi = f.split > 0 && m0 >= f.split;
-          const int parts = p.K >> 6;
-          if (row < p.M) fold_row_stats((hi ? f.st_in2 : f.st_in) + (size_t)row * parts, parts, f.eps, f_mu, f_rs);
-        }
+        mbar_wait(sfull_bar, sph);
+        const float2 ms = sStats[q * 32 + lane];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar);
+        sph ^= 1;
+        const float f_mu = ms.x, f_rs = ms.y;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -315,7 +378,15 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const float* rb = hi ? f.res_b2 : f.res_b;
         float rmu = 0.f, rrs = 1.f;
         const int oparts = p.N >> 6;
-        if (norm && rowok) fold_row_stats(sr + (size_t)row * oparts, oparts, f.eps, rmu, rrs);
+        if (f.st_res != nullptr) {   // uniform over the kernel: the statistics warp runs exactly then
+          mbar_wait(sfull_bar, sph);
+          const float2 ms = sStats[q * 32 + lane];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sempty_bar);
+          sph ^= 1;
+          rmu = ms.x;
+          rrs = ms.y;
+        }
         float s_mean = 0.f, s_m2 = 0.f;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
@@ -394,7 +465,7 @@ gemm_fold_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                   pack_act(v[12], v[13], p.fp16), pack_act(v[14], v[15], p.fp16));
               if (cc == 3) {
                 float2* so = hi ? f.st_out2 : f.st_out;
-                so[(size_t)row * oparts + (n0 >> 6)] = make_float2(s_mean, s_m2);
+                so[(size_t)(n0 >> 6) * f.st_stride + row] = make_float2(s_mean, s_m2);
               }
             }
             fence_proxy_async();
@@ -436,6 +507,8 @@ int launch_gemm_2cta_fold(const GemmDesc& d, cudaStream_t st) {
   const GemmFold& f = *d.fold;
   const bool prod = f.st_out != nullptr, cons = f.st_in != nullptr;
   SPRC_REQUIRE(prod != cons, "gemm fold: exactly one of st_in (consumer) / st_out (producer) must be set");
+  SPRC_REQUIRE(!prod || f.split == 0 || ((f.st_res != nullptr) == (f.st_res2 != nullptr)),
+               "gemm fold producer: with a split either both row ranges carry a normalised residual or neither");
   SPRC_REQUIRE(d.grp_rows == 0 && !d.out_col_block && d.N % 64 == 0 && f.split % 32 == 0 && d.K % 64 == 0,
                "gemm fold: dense rows, N %% 64 == 0, K %% 64 == 0 and split %% 32 == 0 needed (N=%d K=%d split=%d)", d.N,
                d.K, f.split);
@@ -472,6 +545,8 @@ int launch_gemm_2cta_fold(const GemmDesc& d, cudaStream_t st) {
   p.rev = next_sweep_reverse();
   p.m_split = d.W2 ? d.m_split : 0;
   p.f = f;
+  if (p.f.st_stride <= 0) p.f.st_stride = d.M;
+  SPRC_REQUIRE(p.f.st_stride >= d.M, "gemm fold: statistics plane stride %d < M %d", p.f.st_stride, d.M);
 
   const int tiles = p.num_m_pairs * p.num_n_blocks;
   int npairs = device_sm_count() / 2;

@@ -18,11 +18,11 @@ dev = torch.device("cuda:0")
 h16 = torch.float16
 
 
-def stats(x):   # [M, N] fp32 -> [M, N/64, 2] (mean, M2) partials
+def stats(x):   # [M, N] fp32 -> [N/64, M, 2] (mean, M2) partials, part-major
     M, N = x.shape
     xs = x.view(M, N // 64, 64)
     m = xs.mean(-1)
-    return torch.stack([m, ((xs - m[..., None]) ** 2).sum(-1)], -1).contiguous()
+    return torch.stack([m, ((xs - m[..., None]) ** 2).sum(-1)], -1).permute(1, 0, 2).contiguous()
 
 
 def fold_struct(**kw):
@@ -67,7 +67,7 @@ def check_and_time(M, N, K, normed, name):
     # ---- correctness (first 4096 rows in fp32 on the device) ----
     x = x0.clone()
     out16 = torch.zeros(M, N, device=dev, dtype=h16)
-    st_out = torch.full((M, N // 64, 2), float("nan"), device=dev)
+    st_out = torch.full((N // 64, M, 2), float("nan"), device=dev)
     f, keep = fold_struct(resid=x, out16=out16, st_out=st_out, st_res=st_res if normed else None,
                           res_g=ga if normed else None, res_b=be if normed else None)
     L.check(lib.sprc_op_gemm_fold(L.ptr(A), L.ptr(W), None, M, 0, N, K, L.ptr(b), None, 0, L.ptr(x), None, f,
@@ -80,8 +80,9 @@ def check_and_time(M, N, K, normed, name):
         ref = A[sl].float() @ W.float().T + b + r
         e32 = (x[sl] - ref).abs().max().item()
         e16 = (out16[sl].float() - ref).abs().max().item()
-        m = st_out[sl, :, 0].mean(-1)
-        var = (st_out[sl, :, 1].sum(-1) + 64 * ((st_out[sl, :, 0] - m[:, None]) ** 2).sum(-1)) / N
+        so = st_out[:, sl].permute(1, 0, 2)
+        m = so[:, :, 0].mean(-1)
+        var = (so[:, :, 1].sum(-1) + 64 * ((so[:, :, 0] - m[:, None]) ** 2).sum(-1)) / N
         em = (m - ref.mean(-1)).abs().max().item()
         ev = ((var - ref.var(-1, unbiased=False)) / ref.var(-1, unbiased=False)).abs().max().item()
         assert e32 < 2e-3 and e16 < 2e-2 and em < 1e-4 and ev < 1e-3, (name, lo, e32, e16, em, ev)
