@@ -224,41 +224,6 @@ int sprc_op_attention_pairs(const void* Q, const void* K, const void* V, void* O
                             int ldo, int q_batch_rows, const int32_t* kv_idx0, const int32_t* kv_idx1,
                             int64_t kv_rows_total, int64_t kv_head_stride, float scale, void* stream);
 
-/* LayerNorm folded into the neighbouring GEMMs (csrc/gemm2_fold.cu, csrc/ln_fold.cu, csrc/common.h GemmFold;
- * Qformer.py:291-295,373-381 post-LN sublayers, eva_vit.py:173-176 pre-LN blocks).  Row statistics: N / 64 (mean, M2)
- * float pairs per row (12 for rows of 768), stored part-major.
- * sprc_op_fold_weight: Wf = round16(W diag(gamma)), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n].
- * sprc_op_gemm_fold, consumer (fold->st_in set): out_bf16 = act(rstd (A Wf^T - mean c) + d), bias = d;
- * producer (fold->st_out set): out_f32 = A W^T + bias + LN(resid) (resid as is when st_res is null; may alias out_f32),
- * fold->out16 = its raw 16-bit copy, fold->st_out = its row statistics.  Rows >= split take the *2 members. */
-typedef struct sprc_gemm_fold {
-  int32_t split;
-  float eps;
-  int32_t st_stride; /* rows per statistics plane: st[part * st_stride + row] (part-major); 0 = M */
-  int32_t reserved;
-  const void* st_in;
-  const void* st_in2;
-  const float* c;
-  const float* c2;
-  const float* resid;
-  const void* st_res;
-  const void* st_res2;
-  const float* res_g;
-  const float* res_b;
-  const float* res_g2;
-  const float* res_b2;
-  void* st_out;
-  void* st_out2;
-  void* out16;
-} sprc_gemm_fold;
-/* 1 when the model runs the folded schedule in this process (environment SPRC_LN_FOLD, read once). */
-int sprc_ln_fold_enabled(void);
-int sprc_op_fold_weight(const void* W_bf16, const float* gamma, const float* beta, const float* bias, int N, int K,
-                        void* Wf_bf16, float* c, float* d, void* stream);
-int sprc_op_gemm_fold(const void* A_bf16, const void* W_bf16, const void* W2_bf16, int M, int m_split, int N, int K,
-                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
-                      const sprc_gemm_fold* fold, void* stream);
-
 /* ---------------------------------------------------------------------------------------------------
  * Host-side caption tokenizer (csrc/tokenizer.cpp; no CUDA).  Replaces the per-batch Python tokenizer call inside
  * `inference` (blip2_qformer_cir_align_prompt.py:323-329: `self.tokenizer(text, padding="max_length",

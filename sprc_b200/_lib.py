@@ -41,14 +41,6 @@ class SprcTensorDesc(ctypes.Structure):
     ]
 
 
-class SprcGemmFold(ctypes.Structure):
-    """include/sprc_b200.h sprc_gemm_fold (LayerNorm fold descriptor of sprc_op_gemm_fold)."""
-    _fields_ = [("split", ctypes.c_int32), ("eps", c_float), ("st_stride", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)] + [
-        (n, c_void_p) for n in ("st_in", "st_in2", "c", "c2", "resid", "st_res", "st_res2", "res_g", "res_b",
-                                "res_g2", "res_b2", "st_out", "st_out2", "out16")]
-
-
 F32, F16, BF16, I64, I32 = 0, 1, 2, 3, 4
 VIT_EVA_G, VIT_CLIP_L = 0, 1
 ACT_NONE, ACT_GELU, ACT_QUICKGELU = 0, 1, 2
@@ -138,14 +130,6 @@ SIGNATURES = {
     "sprc_tokenizer_destroy": (None, [c_void_p]),
     "sprc_tokenize_host": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
-    "sprc_ln_fold_enabled": (c_int, []),
-    "sprc_op_fold_weight": (
-        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "sprc_op_gemm_fold": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-         POINTER(SprcGemmFold), c_void_p],
-    ),
     "sprc_op_attention_ragged": (
         c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
     "sprc_op_layernorm": (

@@ -146,51 +146,4 @@ int sprc_op_attention(const void* Q, const void* K, const void* V, void* O, int 
   return attention(a, static_cast<cudaStream_t>(stream));
 }
 
-int sprc_ln_fold_enabled(void) { return ln_fold_enabled() ? 1 : 0; }
-
-int sprc_op_fold_weight(const void* W, const float* gamma, const float* beta, const float* bias, int N, int K,
-                        void* Wf, float* c, float* d, void* stream) {
-  return fold_weight(static_cast<const bf16*>(W), gamma, beta, bias, N, K, static_cast<bf16*>(Wf), c, d,
-                     static_cast<cudaStream_t>(stream));
-}
-
-int sprc_op_gemm_fold(const void* A, const void* W, const void* W2, int M, int m_split, int N, int K,
-                      const float* bias, const float* bias2, int act, float* out_f32, void* out_bf16,
-                      const sprc_gemm_fold* fold, void* stream) {
-  if (!A || !W || !fold) return set_error(-22, "sprc_op_gemm_fold: null argument");
-  GemmFold f;
-  f.split = fold->split;
-  f.eps = fold->eps;
-  f.st_stride = fold->st_stride;
-  f.st_in = static_cast<const float2*>(fold->st_in);
-  f.st_in2 = static_cast<const float2*>(fold->st_in2);
-  f.c = fold->c;
-  f.c2 = fold->c2;
-  f.resid = fold->resid;
-  f.st_res = static_cast<const float2*>(fold->st_res);
-  f.st_res2 = static_cast<const float2*>(fold->st_res2);
-  f.res_g = fold->res_g;
-  f.res_b = fold->res_b;
-  f.res_g2 = fold->res_g2;
-  f.res_b2 = fold->res_b2;
-  f.st_out = static_cast<float2*>(fold->st_out);
-  f.st_out2 = static_cast<float2*>(fold->st_out2);
-  f.out16 = static_cast<bf16*>(fold->out16);
-  GemmDesc d;
-  d.A = static_cast<const bf16*>(A);
-  d.W = static_cast<const bf16*>(W);
-  d.W2 = static_cast<const bf16*>(W2);
-  d.M = M;
-  d.m_split = m_split;
-  d.N = d.ldc = N;
-  d.K = d.lda = d.ldw = K;
-  d.bias = bias;
-  d.bias2 = bias2;
-  d.act = act;
-  d.out_f32 = out_f32;
-  d.out_bf16 = static_cast<bf16*>(out_bf16);
-  d.fold = &f;
-  return gemm_bf16_tcgen05(d, static_cast<cudaStream_t>(stream));
-}
-
 }  // extern "C"

@@ -66,8 +66,6 @@ void set_act_fp16(int on);
 // ------------------------------------------------------------------------------------------------
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICKGELU = 2 };
 
-struct GemmFold;
-
 struct GemmDesc {
   const bf16* A = nullptr;
   const bf16* W = nullptr;
@@ -94,43 +92,8 @@ struct GemmDesc {
   const bf16* W2 = nullptr;
   const float* bias2 = nullptr;
   int m_split = 0;
-  // LayerNorm folded into the neighbouring GEMMs (gemm2_fold.cu; see GemmFold below)
-  const GemmFold* fold = nullptr;
 };
 
-// Post-LN sublayer  y = LN(s), s = dense(a) + x  (Qformer.py:291-295, 373-381) without a LayerNorm kernel: the
-// residual stream holds the PRE-LN sums s (fp32 + a raw 16-bit copy) and per-row statistics; LN is applied where
-// its output is consumed.  Row statistics are width / 64 partials (mean, M2) per row (12 for the Q-Former's 768) = one
-// per 64-column slice an epilogue thread owns, stored PART-major ([part][M rows of the GEMM], so a warp's 32 rows are
-// contiguous) and merged (Chan) by whoever reads them - deterministic, no atomics.
-// The ViT's pre-LN blocks (eva_vit.py:173-176, clip_vit.py:132-139) use the same two forms with a raw residual.
-//   CONSUMER GEMM (st_in != null): A = raw 16-bit s, W = W * diag(gamma) (16-bit), GemmDesc::bias = d = W beta + b,
-//     c = row sums of the rounded folded weight:  out = act(rstd * (acc - mean * c) + d).
-//   PRODUCER GEMM (st_out != null; ldc == N, fp32 out, GemmDesc::residual must be null): s' = acc + bias + r with
-//     r = resid (already normalised, st_res == null) or (resid - mean) * rstd * res_g + res_b; writes s' (fp32,
-//     may alias resid), its raw 16-bit copy out16 and the statistics of s'.
-// Rows >= split (a multiple of 32; 0 = one range) take the *2 members: the fusion pass's query rows and text rows
-// went through different LayerNorms (output_query / output) and may sit in different statistics buffers.
-struct GemmFold {
-  int split = 0;
-  int st_stride = 0;   // rows per statistics plane (st[part * st_stride + row]); 0 = the M of the launch
-  const float2* st_in = nullptr;
-  const float2* st_in2 = nullptr;
-  const float* c = nullptr;
-  const float* c2 = nullptr;
-  const float* resid = nullptr;
-  const float2* st_res = nullptr;
-  const float2* st_res2 = nullptr;
-  const float* res_g = nullptr;
-  const float* res_b = nullptr;
-  const float* res_g2 = nullptr;
-  const float* res_b2 = nullptr;
-  float2* st_out = nullptr;
-  float2* st_out2 = nullptr;
-  bf16* out16 = nullptr;
-  float eps = 1e-12f;
-};
-constexpr int kFoldParts = 12;   // statistics partials per Q-Former row of 768 (64 columns each)
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st);  // the product path (UTCHMMA + TMA)
 int gemm_bf16_simt(const GemmDesc& d, cudaStream_t st);     // CUDA-core checker used by tests only

@@ -429,8 +429,7 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
 }
 
 bool gemm_2cta_enabled();
-int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st);        // gemm2.cu
-int launch_gemm_2cta_fold(const GemmDesc& d, cudaStream_t st);   // gemm2_fold.cu
+int launch_gemm_2cta(const GemmDesc& d, cudaStream_t st);   // gemm2.cu
 
 int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
   SPRC_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem %dx%dx%d", d.M, d.N, d.K);
@@ -449,8 +448,6 @@ int gemm_bf16_tcgen05(const GemmDesc& d, cudaStream_t st) {
                  "gemm: two weight sets need dense rows and 0 < m_split (%d) < M (%d), m_split %% 256 == 0", d.m_split,
                  d.M);
   }
-  // LayerNorm fold (GemmFold): its epilogues live in their own CTA-pair kernels (gemm2_fold.cu), whatever the size
-  if (d.fold) return launch_gemm_2cta_fold(d, st);
   const long long tiles256 = (long long)((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
   // CTA pairs (256 x 256 tiles) whenever every pair gets work; the single-CTA kernels cover ragged N and small problems
   // (a ragged last N block - ViT-g's 1408 = 5.5 x 256, 4224 = 16.5 x 256 - runs as a half-empty 256-column tile: its

@@ -387,7 +387,6 @@ int Model::load_tensor(const char* name, int dtype, int ndim, const int64_t* sha
   SPRC_CUDA(cudaGetLastError());
   SPRC_CUDA(cudaDeviceSynchronize());
   s.loaded = true;
-  fold_ready = vit_fold_ready = false;   // folded weights (ln_fold.cu) are derived from the loaded ones
   return 0;
 }
 
@@ -425,9 +424,10 @@ static int linear(const bf16* A, int M, int K, int lda, const bf16* W, int N, co
 
 // dense + residual + LayerNorm of a post-LN Q-Former sublayer (Qformer.py:291-295, 373-381): x (fp32, in place) and
 // xb (16-bit copy) <- LayerNorm(A W^T + bias + x): GEMM with TMA reduce-add into x, then the LayerNorm kernel.
-// Two fused forms were built and measured slower on B200, then removed (profiles/r01c_gemm_ln_*, profiles/r02a_*:
-// a 3-CTA cluster kernel exchanging row statistics through DSMEM, and LayerNorm folded algebraically into the
-// neighbouring GEMMs' epilogues - LayerNorm 7.3 -> 0.8 ms per step but GEMMs 43.7 -> 61.2 ms).
+// Fused forms were built, measured on B200 and removed: a 3-CTA cluster kernel exchanging row
+// statistics through DSMEM (profiles/r01c_gemm_ln_*), and LayerNorm folded algebraically into the neighbouring GEMMs'
+// epilogues, twice (profiles/r02a_*: LayerNorm 7.3 -> 0.8 ms per step but GEMMs 43.7 -> 61.2 ms; profiles/r03a_*, commit
+// 649ae55, with a TMA-prefetched producer epilogue and a statistics warp: GEMMs 44.3 -> 50.5 ms, 37.3k vs 37.2k q/s).
 static bool dual_ffn_enabled() {
   static const bool on = [] {
     const char* e = getenv("SPRC_DUAL_FFN");   // SPRC_DUAL_FFN=0: separate launches for query-row and text-row FFNs
@@ -450,9 +450,7 @@ int Model::vit_forward(const float* images, int B, float* raws_f32, bf16* raws_b
   SPRC_TRY(vit_assemble_tokens(patch_out, cls, pos, B, Dv, x, st));
   if (vit_kind == SPRC_VIT_CLIP_L) SPRC_TRY(layernorm(x, T, Dv, ln_pre_g, ln_pre_b, 1e-5f, 0, 0, x, nullptr, st));
   const float scale = 1.0f / sqrtf((float)dh);
-  const bool fold = vit_fold_usable();   // SPRC_LN_FOLD=1: norm1 / norm2 folded into the GEMMs (ln_fold.cu)
-  if (fold) SPRC_TRY(vit_blocks_fold(B, st));
-  for (int i = fold ? depth : 0; i < depth; ++i) {
+  for (int i = 0; i < depth; ++i) {
     const VitBlock& b = blocks[i];
     SPRC_TRY(layernorm(x, T, Dv, b.ln1_g, b.ln1_b, vit_eps, 0, 0, nullptr, xn, st));
     SPRC_TRY(linear(xn, T, Dv, Dv, b.qkv_w, 3 * Dv, b.qkv_b, ACT_NONE, nullptr, nullptr, qkv, 3 * Dv, 0, 0, st));
@@ -510,13 +508,7 @@ int Model::qformer_layers(int B, int S, bool with_enc, int Lk, const int32_t* kv
   const int g = (S == 64) ? 32 : 0;  // row grouping for "first/last 32 rows of each 64-row sample"
   const int gs = (S == 64) ? 64 : 0;
   const int ldkv = n_cross * 1536;
-  int first_layer = 0;
-  if (S == 32 && with_enc && !kv_idx0 && !key_mask && kv_rows > 0 && fold_usable(B, 0)) {
-    // gallery pass with SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu), then the last layer here
-    SPRC_TRY(qformer_layers_ragged_fold(B, 0, true, Lk, nullptr, nullptr, st));
-    first_layer = qf_layers - 1;
-  }
-  for (int l = first_layer; l < qf_layers; ++l) {
+  for (int l = 0; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     // Rows whose output nobody reads are not computed in the LAST layer (their keys/values still are): the
     // fusion pass is consumed through its 32 query rows only (align_prompt.py:343 `fusion_output[:, :32]`,
@@ -684,12 +676,7 @@ int Model::qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int
   float* x_cls = qt;
   bf16* ctx_cls = qcq;
   bf16* x_cls_b = qcq + (size_t)B * 768;
-  int first_layer = 0;
-  if (fold_usable(B, T8)) {   // SPRC_LN_FOLD=1: layers 0 .. L-2 without LayerNorm kernels (ln_fold.cu)
-    SPRC_TRY(qformer_layers_ragged_fold(B, T8, with_enc, Lk, kv_idx0, kv_idx1, st));
-    first_layer = qf_layers - 1;
-  }
-  for (int l = first_layer; l < qf_layers; ++l) {
+  for (int l = 0; l < qf_layers; ++l) {
     const QfLayer& L = layers[l];
     const bool last = l == qf_layers - 1;
     SPRC_TRY(linear(qhb, rows_all, 768, 768, L.qkv_w, 2304, L.qkv_b, ACT_NONE, nullptr, nullptr, qqkv, 2304, 0, 0, st));

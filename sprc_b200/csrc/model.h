@@ -44,24 +44,6 @@ struct QfLayer {
   float *qi_b, *qo_b, *qo_g, *qo_beta;
 };
 
-// LayerNorm folded into a consuming GEMM (ln_fold.cu): w = W diag(gamma) in the 16-bit operand format,
-// c[n] = sum_k w[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n]
-struct FoldedLinear {
-  bf16* w = nullptr;
-  float* c = nullptr;
-  float* d = nullptr;
-};
-struct QfFold {
-  FoldedLinear qkv_q, qkv_t;  // self-attention q/k/v after the previous layer's output_query / output LayerNorm
-  FoldedLinear cq;            // crossattention.self.query after attention.output.LayerNorm
-  FoldedLinear qi;            // intermediate_query after crossattention.output (cross layers) / attention.output LN
-  FoldedLinear ti;            // intermediate after attention.output.LayerNorm
-};
-
-struct VitFold {
-  FoldedLinear qkv, fc1;
-};
-
 struct Model {
   // ---- dimensions ----
   int vit_kind = 0, Dv = 0, depth = 0, heads = 16, dh = 0, mlp = 0;
@@ -90,13 +72,6 @@ struct Model {
   float *vproj_b = nullptr, *tproj_b = nullptr, *itm_w = nullptr, *itm_b = nullptr;
   void* staging = nullptr;
   size_t staging_bytes = 0;
-  // LayerNorm fold (opt-in, ln_fold.cu): folded weights per layer, two row-statistics buffers [12][qf_rows] (mean, M2)
-  std::vector<QfFold> folds;
-  bool fold_ready = false;
-  float2* fold_st[2] = {nullptr, nullptr};
-  std::vector<VitFold> vit_folds;   // ViT blocks: qkv after norm1 (blocks >= 1), fc1 after norm2
-  bool vit_fold_ready = false;
-  float2* vit_st[2] = {nullptr, nullptr};   // [Dv / 64][vit_cap * 257] (mean, M2)
 
   // ---- workspace ----
   int vit_cap = 0;   // images
@@ -167,16 +142,6 @@ struct Model {
   // kv_idx0 / kv_idx1 (rerank): two-segment keys cat(ref, target) through sample index tables over plain K/V rows
   int qformer_layers_ragged(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
                             cudaStream_t st);
-  // LayerNorm fold (ln_fold.cu): layers 0 .. L-2 of a ragged pass without LayerNorm kernels
-  int fold_one(FoldedLinear* f, const bf16* W, const float* bias, const float* gamma, const float* beta, int N,
-               cudaStream_t st, int K = 768);
-  int prepare_vit_fold(cudaStream_t st);
-  bool vit_fold_usable() const;
-  int vit_blocks_fold(int B, cudaStream_t st);   // all ViT blocks without norm1 / norm2 kernels (block 0's norm1 kept)
-  int prepare_fold(cudaStream_t st);
-  bool fold_usable(int B, int T8) const;
-  int qformer_layers_ragged_fold(int B, int T8, bool with_enc, int Lk, const int32_t* kv_idx0, const int32_t* kv_idx1,
-                                 cudaStream_t st);
   // row tables of the ragged layout for B samples; sample b has lens_host[b / repeat] live text tokens
   int build_ragged_meta(const int32_t* lens_host, int repeat, int B, int* T8_out, cudaStream_t st);
   // text_len_host (optional, host int32 [R]): caption lengths -> ragged rows (live text tokens only)

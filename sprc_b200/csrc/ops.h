@@ -73,12 +73,6 @@ int l2norm_rows256(const float* in, size_t in_row_stride, int rows, float* out_f
 int itm_head_prob(const float* h, int rows_per_pair, int pairs, const float* w, const float* b, float* p,
                   cudaStream_t st);
 
-// ---- ln_fold.cu ------------------------------------------------------------------------------
-// LayerNorm fold (GemmFold, common.h): Wf = round16(W diag(gamma)), c = row sums of Wf, d = W beta + bias
-bool ln_fold_enabled();
-int fold_weight(const bf16* W, const float* gamma, const float* beta, const float* bias, int N, int K, bf16* Wf,
-                float* c, float* d, cudaStream_t st);
-
 // ---- preprocess.cu ---------------------------------------------------------------------------
 // TargetPad + bicubic Resize + CenterCrop + ToTensor + Normalize (data_utils.py:52-72, 91-105) on decoded RGB uint8
 // images, bit-exact with PIL/torchvision; descriptors and coefficient tables come from sprc_b200/preprocess.py.

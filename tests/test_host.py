@@ -303,7 +303,6 @@ def test_c_abi_argument_validation_without_a_gpu():
     refused(lib.sprc_encode_query_lens(z, z, 0, z, z, z, 1, z, z, z), "null")
     refused(lib.sprc_sim_topk(z, z, 1, z, 1, 0, 1, z, z, z, z), "null")
     refused(lib.sprc_sim_topk_grouped(z, z, 1, z, 1, 0, 1, z, z, 1, 1, z), "group")
-    refused(lib.sprc_op_gemm_fold(z, z, z, 1, 0, 64, 64, z, z, 0, z, z, None, z), "null")
     refused(lib.sprc_topk_merge(z, z, z, 1, 1, 1, z, z, z), "null")
     refused(lib.sprc_gather_scores(z, z, 1, z, 1, z, 1, z, z), "null")
     refused(lib.sprc_rerank(z, z, z, z, z, z, 1, 1, z, z), "null")
