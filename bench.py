@@ -767,6 +767,14 @@ def main():
     # busy time per batch and the idle gaps between consecutive batches)
     e2e_diag = {"submit_s": 0.0, "wait_s": 0.0, "ev": []}
 
+    from concurrent.futures import ThreadPoolExecutor
+
+    tok_pool = ThreadPoolExecutor(max_workers=1)
+    tok_ahead = {}
+
+    def tokenize_step(j):
+        model.tokenizer.tokenize_into(caps_pool[j % pool], ids_stage[j & 1], mask_stage[j & 1], lens_stage[j & 1])
+
     def step_host(i):
         p_ = i % pool
         if world == 1 and not e2e_from_ids:
@@ -792,8 +800,13 @@ def main():
         else:
             # strings in on every rank: C++ tokenizer into pinned staging, H2D, the device step (all-gather of query
             # vectors, local scans, all-to-all of candidates, merge of this rank's queries), D2H of its top-k
+            # The tokenizer works one batch ahead on a helper thread (C++ workers, no interpreter lock): batch i + 1 is
+            # tokenised while the GPU runs batch i, as in the single-GPU submit / wait pair.
             s_ = i & 1
-            model.tokenizer.tokenize_into(caps_pool[p_], ids_stage[s_], mask_stage[s_], lens_stage[s_])
+            if tok_ahead.get("step") != i:
+                tok_ahead["fut"] = tok_pool.submit(tokenize_step, i)
+            tok_ahead["fut"].result()
+            tok_ahead["step"], tok_ahead["fut"] = i + 1, tok_pool.submit(tokenize_step, i + 1)
             ids_dev_stage.copy_(ids_stage[s_], non_blocking=True)
             if not ragged:
                 mask_dev_stage.copy_(mask_stage[s_], non_blocking=True)
@@ -812,6 +825,9 @@ def main():
         while inflight[0] > 0:
             L.check(lib.sprc_query_topk_host_wait(h))
             inflight[0] -= 1
+        if tok_ahead.get("fut") is not None:   # the batch tokenised ahead of the last step is not used
+            tok_ahead["fut"].result()
+            tok_ahead.clear()
 
     def timed(fn, steps, warmup, drain=None):
         for i in range(warmup):
@@ -1016,7 +1032,7 @@ def main():
                    "and enqueued while the GPU works on batch i")
     else:
         h2d_bytes = world * (Bq * (32 * 8 * (1 if ragged else 2) + 4))
-        e2e_api = ("caption STRINGS -> C++ tokenizer -> pinned ids -> device step (all-gather of query vectors, local "
+        e2e_api = ("caption STRINGS -> C++ tokenizer (one batch ahead, helper thread) -> pinned ids -> device step (all-gather of query vectors, local "
                    "scans, ONE all-to-all of candidates, merge of this rank's queries) -> top-k rows of this rank on host")
     if rank == 0:
         line = {
