@@ -239,8 +239,9 @@ int sprc_query_topk_host_submit(sprc_handle* h, const void* raws_bf16, const voi
   SPRC_TRY(sprc_sim_topk(h, m.d_fusion, Bq, gallery_bf16, N, 0, k, m.d_topk_score, m.d_topk_idx, nullptr, stream));
   SPRC_CUDA(cudaMemcpyAsync(out_score_host, m.d_topk_score, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
   SPRC_CUDA(cudaMemcpyAsync(out_idx_host, m.d_topk_idx, (size_t)Bq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (!h->done[0])
+    for (cudaEvent_t& e : h->done) SPRC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   cudaEvent_t& ev = h->done[h->submitted % sprc_handle::kInflight];
-  if (!ev) SPRC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   SPRC_CUDA(cudaEventRecord(ev, st));
   ++h->submitted;
   return 0;
@@ -258,9 +259,11 @@ int sprc_query_topk_strings_submit(sprc_handle* h, const sprc_tokenizer* tok, co
   Model& m = h->m;
   SPRC_REQUIRE(Bq > 0 && Bq <= m.max_queries, "sprc_query_topk_strings: Bq=%d outside (0, %d]", Bq, m.max_queries);
   // the slot's previous batch (submitted - kInflight) has been awaited, so its H2D copies are done
-  int64_t*& stage = h->tok_stage[h->submitted % sprc_handle::kInflight];
   const size_t row = (size_t)m.max_queries * 32;
-  if (!stage) SPRC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&stage), (2 * row + m.max_queries) * 8, cudaHostAllocDefault));
+  if (!h->tok_stage[0])   // all slots at the first call (page-locked allocation synchronises the device)
+    for (int64_t*& p : h->tok_stage)
+      SPRC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), (2 * row + m.max_queries) * 8, cudaHostAllocDefault));
+  int64_t*& stage = h->tok_stage[h->submitted % sprc_handle::kInflight];
   int64_t* ids = stage;
   int64_t* mask = stage + row;
   int32_t* rows = reinterpret_cast<int32_t*>(stage + 2 * row);

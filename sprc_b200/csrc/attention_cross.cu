@@ -362,7 +362,7 @@ constexpr int XG_THREADS = 10 * 32;
 constexpr int XG_PGROUP = 4 * 4096;                 // P of one group: four 64-key blocks 4 KB apart
 constexpr int XG_PBYTES = 2 * XG_PGROUP + 12288;    // + the rows 32..127 the last block's MMA also reads
 constexpr int XG_XCH = 3 * 128 * 4;                 // per group: max[4][32], part[4][32], sum[4][32]
-constexpr int XG_SMEM = XG_PBYTES + 2 * XC_STAGE + 2 * XC_OBYTES + 256 + 128 + 2 * XG_XCH + 1024;
+constexpr int XG_SMEM = XG_PBYTES + 2 * XC_STAGE + 2 * XC_OBYTES + 256 + 160 + 2 * XG_XCH + 1024;
 
 __global__ void __launch_bounds__(XG_THREADS, 1)
 qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -375,14 +375,19 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   uint8_t* sO = stages + 2 * XC_STAGE;              // [2][XC_OBYTES]
   uint8_t* sV256 = sO + 2 * XC_OBYTES;              // [2][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV256 + 256);
-  uint64_t* full = bars;         // [2] stage g loaded
-  uint64_t* empty = bars + 2;    // [2] stage g free
+  // The K half of a stage (Q replicas + K) is free again as soon as the scores are out and the softmax warps have read
+  // their key-256 operands; the V half only after P V.  Separate barriers let K of the group's NEXT item stream in under
+  // this item's softmax and P V (with one barrier per stage the load sat in series with the chain).
+  uint64_t* fullk = bars;        // [2] Q + K of group g's item loaded
+  uint64_t* emptyk = bars + 2;   // [2] Q + K half of stage g free
   uint64_t* s_full = bars + 4;   // [2] scores of group g's item are in region g
   uint64_t* rfree = bars + 6;    // [2] region g may take new scores
   uint64_t* p_full = bars + 8;   // [2] P of group g's item is in shared memory
   uint64_t* o_full = bars + 10;  // [2] O of group g's item is complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  const uint32_t xch0 = smem_u32(bars + 16);
+  uint64_t* fullv = bars + 12;   // [2] V of group g's item loaded
+  uint64_t* emptyv = bars + 14;  // [2] V half of stage g free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t xch0 = smem_u32(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.B * p.H;
@@ -396,8 +401,10 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&fullk[s], 1);
+      mbar_init(&emptyk[s], 1);
+      mbar_init(&fullv[s], 1);
+      mbar_init(&emptyv[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&rfree[s], 1);
       mbar_init(&p_full[s], 4);
@@ -414,24 +421,39 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   griddep_launch();
 
   if (warp == 0) {
-    // ===================== TMA producer: item `it` -> stage it & 1 =====================
+    // ===================== TMA producer: item `it` -> stage it & 1, K half and V half on their own barriers =====
     if (elect_one()) {
-      for (int it = 0; it < n_my; ++it) {
-        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-        const int itm = p.rev ? n_items - 1 - item : item;
-        const int b = itm / p.H, h = itm % p.H;
-        const int st = it & 1;
-        uint8_t* sb = stages + st * XC_STAGE;
-        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&full[st], XC_STAGE);
+      int next_k[2] = {0, 1}, next_v[2] = {0, 1};
+      while (next_v[0] < n_my || next_v[1] < n_my) {
 #pragma unroll
-        for (int rep = 0; rep < 4; ++rep)
-          tma_load_2d(&tmQ, &full[st], sb + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
-        const int kr = b * p.kv_batch_rows;
-        tma_load_3d(&tmK, &full[st], sb + XC_QBYTES, 0, kr, h, kEvictFirst);
-        tma_load_3d(&tmK, &full[st], sb + XC_QBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
-        tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES, 0, kr, h, kEvictFirst);
-        tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* sb = stages + g * XC_STAGE;
+          int it = next_k[g];
+          if (it < n_my && mbar_test(&emptyk[g], ((it >> 1) & 1) ^ 1)) {
+            const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int itm = p.rev ? n_items - 1 - item : item;
+            const int b = itm / p.H, h = itm % p.H;
+            const int kr = b * p.kv_batch_rows;
+            mbar_expect_tx(&fullk[g], XC_QBYTES + XC_KBYTES);
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep)
+              tma_load_2d(&tmQ, &fullk[g], sb + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
+            tma_load_3d(&tmK, &fullk[g], sb + XC_QBYTES, 0, kr, h, kEvictFirst);
+            tma_load_3d(&tmK, &fullk[g], sb + XC_QBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+            next_k[g] = it + 2;
+          }
+          it = next_v[g];
+          if (it < n_my && it < next_k[g] && mbar_test(&emptyv[g], ((it >> 1) & 1) ^ 1)) {
+            const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int itm = p.rev ? n_items - 1 - item : item;
+            const int b = itm / p.H, h = itm % p.H;
+            const int kr = b * p.kv_batch_rows;
+            mbar_expect_tx(&fullv[g], XC_KBYTES);
+            tma_load_3d(&tmV, &fullv[g], sb + XC_QBYTES + XC_KBYTES, 0, kr, h, kEvictFirst);
+            tma_load_3d(&tmV, &fullv[g], sb + XC_QBYTES + XC_KBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+            next_v[g] = it + 2;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -447,7 +469,7 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
           int it = s_next[g];
           if (it < n_my) {
             const uint32_t n = (it >> 1) & 1;
-            if (mbar_test(&full[g], n) && mbar_test(&rfree[g], n ^ 1)) {
+            if (mbar_test(&fullk[g], n) && mbar_test(&rfree[g], n ^ 1)) {
               tc_fence_after();
               const uint64_t da = umma_desc_k_sw128(smem_u32(sb));
               const uint64_t db = umma_desc_k_sw128(smem_u32(sb + XC_QBYTES));
@@ -459,7 +481,8 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
             }
           }
           it = pv_next[g];
-          if (it < n_my && it < s_next[g] && mbar_test(&p_full[g], (it >> 1) & 1)) {
+          if (it < n_my && it < s_next[g] && mbar_test(&p_full[g], (it >> 1) & 1) &&
+              mbar_test(&fullv[g], (it >> 1) & 1)) {
             tc_fence_after();
             const uint32_t sv = smem_u32(sb + XC_QBYTES + XC_KBYTES);
 #pragma unroll
@@ -469,7 +492,7 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
               umma_bf16(tmem_base + g * XC_REGION, da, db, idesc_pv, ks != 0 ? 1u : 0u);
             }
             umma_commit(&o_full[g]);
-            umma_commit(&empty[g]);
+            umma_commit(&emptyv[g]);
             pv_next[g] = it + 2;
           }
         }
@@ -493,7 +516,7 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       const int itm = p.rev ? n_items - 1 - item : item;
       const int b = itm / p.H, h = itm % p.H;
       uint32_t sr[64];
-      mbar_wait(&s_full[g], par);   // the stage is loaded too (the MMA has read it)
+      mbar_wait(&s_full[g], par);   // Q + K are loaded too (the MMA has read them)
       tc_fence_after();
       {
         uint32_t(&a0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
@@ -522,6 +545,7 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       else
         asm volatile("bar.sync 2, 128;" ::: "memory");
       tc_fence_after();
+      if (q == 0 && lane == 0) mbar_arrive(&emptyk[g]);   // scores are out, every warp has read Q / K row 256
       float mx = fmaxf(fmaxf(lds32f(x_max + lane * 4), lds32f(x_max + (32 + lane) * 4)),
                        fmaxf(lds32f(x_max + (64 + lane) * 4), lds32f(x_max + (96 + lane) * 4)));
       const float s256 = (lds32f(x_part + lane * 4) + lds32f(x_part + (32 + lane) * 4)) +
@@ -546,10 +570,13 @@ qf_cross_attention_g2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       const float p256 = ex2_approx(fmaf(s256, p.scale_log2, -moff));
       if (q == 0) sum += p256;
       sts32f(x_sum + (q * 32 + lane) * 4, sum);
-      if (q == 0 && lane < 8) {
-        // value row 256 -> side buffer (the stage is recycled before the epilogue runs)
-        const uint4 v = lds128(sb + XC_QBYTES + XC_KBYTES + 256 * 128 + (lane << 4));
-        sts128(sv256 + (lane << 4), v.x, v.y, v.z, v.w);
+      if (q == 0) {
+        // value row 256 -> side buffer (the V half is recycled before the epilogue runs)
+        mbar_wait(&fullv[g], par);
+        if (lane < 8) {
+          const uint4 v = lds128(sb + XC_QBYTES + XC_KBYTES + 256 * 128 + (lane << 4));
+          sts128(sv256 + (lane << 4), v.x, v.y, v.z, v.w);
+        }
       }
       fence_proxy_async();   // P (generic-proxy writes) -> tcgen05.mma (async proxy)
       if (g == 0)
