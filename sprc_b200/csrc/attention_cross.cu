@@ -80,14 +80,18 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   uint8_t* sO = stages + 2 * XC_STAGE;
   uint8_t* sV256 = sO + XC_OBYTES;                  // [NSEG][128 B] value rows 256
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV256 + 256);
-  uint64_t* full = bars;         // [2] stage loaded
-  uint64_t* empty = bars + 2;    // [2] stage free
+  // the Q + K half of a stage is free once its scores are out and the softmax warps have read their key-256 operands,
+  // the V half only after P V: separate barriers, so the next segment's Q + K stream in under this item's softmax
+  uint64_t* full = bars;         // [2] Q + K of the stage loaded
+  uint64_t* empty = bars + 2;    // [2] Q + K half free
   uint64_t* s_full = bars + 4;   // [2] scores of the segment in region r
   uint64_t* rfree = bars + 6;    // [2] region r may take new scores
   uint64_t* p_full = bars + 8;   // P of the item is in shared memory
   uint64_t* o_full = bars + 9;   // O of the item is complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  const uint32_t xch = smem_u32(bars + 12);   // max[NSEG][4][32], part[NSEG][4][32], sum[4][32]
+  uint64_t* fullv = bars + 10;   // [2] V of the stage loaded
+  uint64_t* emptyv = bars + 12;  // [2] V half free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const uint32_t xch = smem_u32(bars + 16);   // max[NSEG][4][32], part[NSEG][4][32], sum[4][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.B * p.H;
@@ -103,6 +107,8 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     for (int s = 0; s < 2; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&fullv[s], 1);
+      mbar_init(&emptyv[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&rfree[s], 1);
     }
@@ -126,22 +132,31 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         const int itm = p.rev ? n_items - 1 - item : item;
         const int b = itm / p.H, h = itm % p.H;
 #pragma unroll
-        for (int sg = 0; sg < NSEG; ++sg) {
-          const int u = it * NSEG + sg;
-          const int st = u & 1;
-          uint8_t* sb = stages + st * XC_STAGE;
-          mbar_wait(&empty[st], ((u >> 1) & 1) ^ 1);
-          mbar_expect_tx(&full[st], XC_STAGE);
+        for (int half = 0; half < 2; ++half) {   // Q + K of every segment of the item first, then the V halves
 #pragma unroll
-          for (int rep = 0; rep < 4; ++rep)
-            tma_load_2d(&tmQ, &full[st], sb + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
-          const int img = NSEG == 1 ? b : (sg == 0 ? __ldg(p.kv_idx0 + b) : __ldg(p.kv_idx1 + b));
-          const int kr = img * p.kv_batch_rows;
-          // K/V maps are (d, row, head): heads are column slices of wide rows or contiguous [rows, 64] blocks
-          tma_load_3d(&tmK, &full[st], sb + XC_QBYTES, 0, kr, h, kEvictFirst);
-          tma_load_3d(&tmK, &full[st], sb + XC_QBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
-          tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES, 0, kr, h, kEvictFirst);
-          tma_load_3d(&tmV, &full[st], sb + XC_QBYTES + XC_KBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+          for (int sg = 0; sg < NSEG; ++sg) {
+            const int u = it * NSEG + sg;
+            const int st = u & 1;
+            const uint32_t par = ((u >> 1) & 1) ^ 1;
+            uint8_t* sb = stages + st * XC_STAGE;
+            const int img = NSEG == 1 ? b : (sg == 0 ? __ldg(p.kv_idx0 + b) : __ldg(p.kv_idx1 + b));
+            const int kr = img * p.kv_batch_rows;
+            // K/V maps are (d, row, head): heads are column slices of wide rows or contiguous [rows, 64] blocks
+            if (half == 0) {
+              mbar_wait(&empty[st], par);
+              mbar_expect_tx(&full[st], XC_QBYTES + XC_KBYTES);
+#pragma unroll
+              for (int rep = 0; rep < 4; ++rep)
+                tma_load_2d(&tmQ, &full[st], sb + rep * 4096, h * 64, b * p.q_batch_rows, kEvictNormal);
+              tma_load_3d(&tmK, &full[st], sb + XC_QBYTES, 0, kr, h, kEvictFirst);
+              tma_load_3d(&tmK, &full[st], sb + XC_QBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+            } else {
+              mbar_wait(&emptyv[st], par);
+              mbar_expect_tx(&fullv[st], XC_KBYTES);
+              tma_load_3d(&tmV, &fullv[st], sb + XC_QBYTES + XC_KBYTES, 0, kr, h, kEvictFirst);
+              tma_load_3d(&tmV, &fullv[st], sb + XC_QBYTES + XC_KBYTES + XC_HALF * 128, 0, kr + XC_HALF, h, kEvictFirst);
+            }
+          }
         }
       }
     }
@@ -174,6 +189,8 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     for (int it = 0; it < n_my; ++it) {
       if (NSEG == 1 && it + 1 < n_my) issue_scores(it + 1);   // the other region: runs under this item's softmax
       mbar_wait(p_full, it & 1);   // P of this item is in shared memory, its scores are consumed
+#pragma unroll
+      for (int sg = 0; sg < NSEG; ++sg) mbar_wait(&fullv[(it * NSEG + sg) & 1], ((it * NSEG + sg) >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t o_addr = tmem_base + (NSEG == 1 ? (it & 1) * XC_REGION : 0);
@@ -190,7 +207,7 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
         umma_commit(o_full);
 #pragma unroll
-        for (int sg = 0; sg < NSEG; ++sg) umma_commit(&empty[(it * NSEG + sg) & 1]);
+        for (int sg = 0; sg < NSEG; ++sg) umma_commit(&emptyv[(it * NSEG + sg) & 1]);
       }
       __syncwarp();
       if (NSEG == 2 && it + 1 < n_my) issue_scores(it + 1);
@@ -241,6 +258,10 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       asm volatile("bar.sync 1, 128;" ::: "memory");   // every score of the item has been read
       tc_fence_after();
       if (NSEG == 2 && q == 0 && lane == 0) mbar_arrive(&rfree[1]);   // region 1 only ever holds scores
+      if (q == 0 && lane == 0) {   // scores are out, every warp has read Q / K row 256: the Q + K halves are free
+#pragma unroll
+        for (int sg = 0; sg < NSEG; ++sg) mbar_arrive(&empty[(it * NSEG + sg) & 1]);
+      }
       float s256[NSEG];
       float mx = fmaxf(fmaxf(lds32f(x_max + lane * 4), lds32f(x_max + (32 + lane) * 4)),
                        fmaxf(lds32f(x_max + (64 + lane) * 4), lds32f(x_max + (96 + lane) * 4)));
@@ -273,13 +294,17 @@ qf_cross_attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         if (q == 0) sum += p256[sg];
       }
       sts32f(x_sum + (q * 32 + lane) * 4, sum);
-      if (q == 0 && lane < 8) {
-        // value rows 256 of the item's segments -> side buffer (the stages are recycled before the epilogue runs)
+      if (q == 0) {
+        // value rows 256 of the item's segments -> side buffer (the V halves are recycled before the epilogue runs)
 #pragma unroll
         for (int sg = 0; sg < NSEG; ++sg) {
-          const uint32_t sb = smem_u32(stages + ((it * NSEG + sg) & 1) * XC_STAGE);
-          const uint4 v = lds128(sb + XC_QBYTES + XC_KBYTES + 256 * 128 + (lane << 4));
-          sts128(smem_u32(sV256) + sg * 128 + (lane << 4), v.x, v.y, v.z, v.w);
+          const int u = it * NSEG + sg;
+          mbar_wait(&fullv[u & 1], (u >> 1) & 1);
+          if (lane < 8) {
+            const uint32_t sb = smem_u32(stages + (u & 1) * XC_STAGE);
+            const uint4 v = lds128(sb + XC_QBYTES + XC_KBYTES + 256 * 128 + (lane << 4));
+            sts128(smem_u32(sV256) + sg * 128 + (lane << 4), v.x, v.y, v.z, v.w);
+          }
         }
       }
       fence_proxy_async();   // P (generic-proxy writes) -> tcgen05.mma (async proxy)
@@ -687,7 +712,7 @@ int launch_cross_g2(const AttnDesc& a, cudaStream_t st) {
 template <int NSEG>
 int launch_cross2(const AttnDesc& a, cudaStream_t st) {
   constexpr int PBYTES = NSEG * 4 * 4096 + 12288;
-  const size_t smem = PBYTES + 2 * XC_STAGE + XC_OBYTES + 256 + 12 * 8 + (2 * NSEG + 1) * 128 * 4 + 1024;
+  const size_t smem = PBYTES + 2 * XC_STAGE + XC_OBYTES + 256 + 16 * 8 + (2 * NSEG + 1) * 128 * 4 + 1024;
   CUtensorMap tmQ, tmK, tmV, tmO;
   const uint64_t w = (uint64_t)a.H * 64;
   const uint64_t qrows = (uint64_t)(a.B - 1) * a.q_batch_rows + a.Lq;
