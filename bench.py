@@ -979,6 +979,17 @@ def main():
     cat = lambda c: dict(ms=prof[c * 4], flops=prof[c * 4 + 1], bytes=prof[c * 4 + 2], n=prof[c * 4 + 3])  # noqa: E731
     gemm, attn, lnorm, scan, merge = (cat(c) for c in range(5))
     prof_total = sum(x["ms"] for x in (gemm, attn, lnorm, scan, merge))
+    # N > 1: the step is two collectives long in lockstep, so it is paced by the slowest rank; show every rank's own
+    # kernel time per step and SM clock under load (boards of one box differ under their power caps)
+    rank_skew = None
+    if world > 1:
+        mine = torch.tensor([prof_total / max(K, 1), float(clk.get("sm_mhz") or 0.0)], device=dev)
+        allr = torch.empty(world, 2, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        rank_skew = {"kernel_ms_per_step": [round(v, 2) for v in allr[:, 0].tolist()],
+                     "sm_mhz": [round(v) for v in allr[:, 1].tolist()],
+                     "note": "per rank: sum of its own kernels' CUDA-event times per step (profiling pass) and its median "
+                             "SM clock in the timed loop; ms_per_step above is the lockstep step (max over ranks)"}
     gemm_tf = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
     scan_gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9 if scan["ms"] > 0 else 0.0
     scan_tf = scan["flops"] / (scan["ms"] / 1e3) / 1e12 if scan["ms"] > 0 else 0.0
@@ -1143,6 +1154,7 @@ def main():
             "eager_gpu": eager,
             "index_feed": index_feed,
             "sharded_equals_single": sharded_equals_single,
+            "rank_skew": rank_skew,
             "roofline_vit": {args.vit: {"images_per_s_per_gpu": index_ips,
                                         "frac_of_vit_gemm_roofline": index_ips * FLOP_PER_IMAGE[args.vit] / (
                                             pk["tf_sust"] * 1e12)},
