@@ -796,21 +796,64 @@ def main():
     cand_recv = torch.empty(world, 2, Bq, k, device=dev, dtype=torch.int32)
     msc = torch.empty(Bq, k, device=dev)
     mix = torch.empty(Bq, k, device=dev, dtype=torch.int32)
+    # N > 1, two streams: the fusion of batch i + 1 (main stream) runs while batch i is exchanged, scanned and merged on
+    # a second stream, so the two collectives - and the wait for the slowest rank they imply - leave the critical path.
+    # Two buffers of everything a batch owns; SPRC_BENCH_LOCKSTEP=1 selects the one-stream lockstep step.
+    pipelined = world > 1 and os.environ.get("SPRC_BENCH_LOCKSTEP", "0") != "1"
+    pipe_allowed = pipelined
+    pipe = None
+    if pipelined:
+        pipe = {"n": 0, "s_ex": torch.cuda.Stream(device=dev),
+                "fusion": [fusion, torch.empty_like(fusion)], "fusion_all": [fusion_all, torch.empty_like(fusion_all)],
+                "send": [cand_send, torch.empty_like(cand_send)], "recv": [cand_recv, torch.empty_like(cand_recv)],
+                "msc": [msc, torch.empty_like(msc)], "mix": [mix, torch.empty_like(mix)],
+                "ev_enc": [torch.cuda.Event(), torch.cuda.Event()], "ev_gath": [torch.cuda.Event(), torch.cuda.Event()],
+                "ev_done": [torch.cuda.Event(), torch.cuda.Event()], "last": 0}
 
-    def step_device(i, ids_src=None, lens_src=None, mask_src=None):
+    pipe_state = {"on": pipelined}   # the profiling pass switches to the one-stream step (per-kernel times undisturbed)
+
+    def step_device(i, ids_src=None, lens_src=None, mask_src=None, host_out=None):
         p_ = i % pool
         ids_ = ids_d[p_] if ids_src is None else ids_src
+        fus = fusion
+        if pipe_state["on"]:
+            b_ = pipe["n"] & 1
+            pipe["n"] += 1
+            pipe["slot"] = b_
+            fus = pipe["fusion"][b_]
+            if pipe["n"] > 2:   # the all-gather of the batch that last used this buffer has read it
+                torch.cuda.current_stream(dev).wait_event(pipe["ev_gath"][b_])
         if ragged:
             L.check(lib.sprc_encode_query_lens(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_),
                                                L.ptr(lens_h[p_] if lens_src is None else lens_src), Bq, None,
-                                               L.ptr(fusion), st()))
+                                               L.ptr(fus), st()))
         else:
             L.check(lib.sprc_encode_query(h, L.ptr(raws), L.BF16, L.ptr(rows_d[p_]), L.ptr(ids_),
-                                          L.ptr(mask_d[p_] if mask_src is None else mask_src), Bq, None, L.ptr(fusion),
+                                          L.ptr(mask_d[p_] if mask_src is None else mask_src), Bq, None, L.ptr(fus),
                                           st()))
         if world == 1:
             L.check(lib.sprc_sim_topk(h, L.ptr(fusion), Bq, L.ptr(feats), n_local, 0, k, L.ptr(sc), L.ptr(ix), None,
                                       st()))
+        elif pipe_state["on"]:
+            b_ = pipe["slot"]
+            s_enc, s_ex = torch.cuda.current_stream(dev), pipe["s_ex"]
+            pipe["ev_enc"][b_].record(s_enc)
+            with torch.cuda.stream(s_ex):
+                s_ex.wait_event(pipe["ev_enc"][b_])
+                dist.all_gather_into_tensor(pipe["fusion_all"][b_], pipe["fusion"][b_])
+                pipe["ev_gath"][b_].record(s_ex)     # fusion[b_] may be overwritten by the encode two batches on
+                sx = L.c_void_p(s_ex.cuda_stream)
+                snd, rcv = pipe["send"][b_], pipe["recv"][b_]
+                L.check(lib.sprc_sim_topk_grouped(h, L.ptr(pipe["fusion_all"][b_]), world * Bq, L.ptr(feats), n_local, lo,
+                                                  k, L.ptr(snd[0, 0]), L.ptr(snd[0, 1]), Bq, 2 * Bq * k, sx))
+                dist.all_to_all_single(rcv, snd)
+                L.check(lib.sprc_topk_merge_packed(h, L.ptr(rcv), world, Bq, k, L.ptr(pipe["msc"][b_]),
+                                                   L.ptr(pipe["mix"][b_]), sx))
+                if host_out is not None:
+                    host_out[0].copy_(pipe["msc"][b_], non_blocking=True)
+                    host_out[1].copy_(pipe["mix"][b_], non_blocking=True)
+                pipe["ev_done"][b_].record(s_ex)
+            pipe["last"] = b_
         else:
             dist.all_gather_into_tensor(fusion_all, fusion)
             # ONE scan launch for all world * Bq queries against this rank's shard; the [Bq, k] block of rank r's queries
@@ -832,7 +875,11 @@ def main():
     tok_pool = ThreadPoolExecutor(max_workers=1)
     tok_ahead = {}
 
+    h2d_ev = [None, None]   # pinned staging slot -> the H2D copy that last read it
+
     def tokenize_step(j):
+        if h2d_ev[j & 1] is not None:
+            h2d_ev[j & 1].synchronize()
         model.tokenizer.tokenize_into(caps_pool[j % pool], ids_stage[j & 1], mask_stage[j & 1], lens_stage[j & 1])
 
     def step_host(i):
@@ -871,17 +918,32 @@ def main():
             if not ragged:
                 mask_dev_stage.copy_(mask_stage[s_], non_blocking=True)
             rows_d[p_].copy_(rows_h[p_], non_blocking=True)
-            step_device(i, ids_src=ids_dev_stage, lens_src=lens_stage[s_], mask_src=mask_dev_stage)
-            out_sc_h.copy_(msc, non_blocking=True)
-            out_ix_h.copy_(mix, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
+            h2d_ev[s_] = torch.cuda.Event()
+            h2d_ev[s_].record()
+            if pipe_state["on"]:
+                # results of batch i land in the host buffers of its slot on the exchange stream; the host waits for
+                # batch i - 1 (two batches in flight, as on one GPU), the drain waits for the last one
+                step_device(i, ids_src=ids_dev_stage, lens_src=lens_stage[s_], mask_src=mask_dev_stage,
+                            host_out=(out_sc_h2[pipe["n"] & 1], out_ix_h2[pipe["n"] & 1]))
+                if pipe["n"] > 1:
+                    pipe["ev_done"][pipe["last"] ^ 1].synchronize()
+            else:
+                step_device(i, ids_src=ids_dev_stage, lens_src=lens_stage[s_], mask_src=mask_dev_stage)
+                out_sc_h.copy_(msc, non_blocking=True)
+                out_ix_h.copy_(mix, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def drain_pipe():
+        if pipe_state["on"]:   # the exchange stream's last batch is part of the timed work
+            torch.cuda.current_stream(dev).wait_stream(pipe["s_ex"])
+
     def drain_host():
+        drain_pipe()
         while inflight[0] > 0:
             L.check(lib.sprc_query_topk_host_wait(h))
             inflight[0] -= 1
@@ -916,7 +978,7 @@ def main():
     clocks = ClockSampler(local)
     time.sleep(0.25)
     l0 = lib.sprc_launch_count()
-    ms, tw0, tw1 = timed(step_device, K, W)
+    ms, tw0, tw1 = timed(step_device, K, W, drain=drain_pipe)
     launches = (lib.sprc_launch_count() - l0) * K // (K + W)
     clk = clocks.window(tw0, tw1)
     value = world * Bq * K / (ms / 1e3)
@@ -938,21 +1000,26 @@ def main():
                             "(tokenizer + enqueue) and wait"}
     # the device-resident loop once more AFTER the e2e loop: the GPU is power-capped in this workload, and how much of
     # the value/e2e gap is the host path and how much the power state of a longer run shows in this repeat
-    ms_rep, _, _ = timed(step_device, K, W)
+    ms_rep, _, _ = timed(step_device, K, W, drain=drain_pipe)
     value_repeat = world * Bq * K / (ms_rep / 1e3)
 
     # ---- N > 1: the sharded pipeline must give what ONE GPU gives on the whole gallery (bit-exact, query sample) ----
     sharded_equals_single = None
     if world > 1 and N % world == 0:
         step_device(0)
+        drain_pipe()
+        torch.cuda.synchronize()
+        fus_l = pipe["fusion"][pipe["last"]] if pipe_state["on"] else fusion
+        mix_l = pipe["mix"][pipe["last"]] if pipe_state["on"] else mix
+        msc_l = pipe["msc"][pipe["last"]] if pipe_state["on"] else msc
         whole = torch.empty(N, 32, 256, device=dev, dtype=adt)
         dist.all_gather_into_tensor(whole, feats)
         nq = min(256, Bq)
         sc1 = torch.empty(nq, k, device=dev)
         ix1 = torch.empty(nq, k, device=dev, dtype=torch.int32)
-        L.check(lib.sprc_sim_topk(h, L.ptr(fusion), nq, L.ptr(whole), N, 0, k, L.ptr(sc1), L.ptr(ix1), None, st()))
+        L.check(lib.sprc_sim_topk(h, L.ptr(fus_l), nq, L.ptr(whole), N, 0, k, L.ptr(sc1), L.ptr(ix1), None, st()))
         torch.cuda.synchronize()
-        ok = torch.tensor([int(torch.equal(ix1, mix[:nq]) and torch.equal(sc1, msc[:nq]))], device=dev)
+        ok = torch.tensor([int(torch.equal(ix1, mix_l[:nq]) and torch.equal(sc1, msc_l[:nq]))], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         sharded_equals_single = bool(ok.item())
         assert sharded_equals_single, "sharded scan + all-to-all + merge differs from the single-GPU scan"
@@ -963,11 +1030,14 @@ def main():
     import ctypes
 
     prof = (ctypes.c_double * 20)()
+    drain_pipe()
     barrier()
+    pipe_state["on"] = False   # one stream: a kernel's CUDA-event time is its own
     lib.sprc_profile(1)
     for i in range(K):
         step_device(W + i)
     torch.cuda.synchronize()
+    pipe_state["on"] = pipe_allowed
     L.check(lib.sprc_profile_read(prof, 5))
     if args.profile_dump and rank == 0:
         L.check(lib.sprc_profile_dump((args.profile_dump + ".query.csv").encode()))
@@ -1106,7 +1176,9 @@ def main():
     else:
         h2d_bytes = world * (Bq * (32 * 8 * (1 if ragged else 2) + 4))
         e2e_api = ("caption STRINGS -> C++ tokenizer (one batch ahead, helper thread) -> pinned ids -> device step (all-gather of query vectors, local "
-                   "scans, ONE all-to-all of candidates, merge of this rank's queries) -> top-k rows of this rank on host")
+                   "scan in ONE grouped launch, ONE all-to-all of candidates, merge of this rank's queries) -> top-k rows "
+                   "of this rank on host; two batches in flight (the fusion of batch i + 1 on the main stream while batch i "
+                   "is exchanged, scanned and merged on a second stream)" + ("" if pipelined else " - disabled: lockstep"))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -1116,7 +1188,9 @@ def main():
                        "queries_per_step_per_gpu": Bq, "k": k, "gallery_rows_per_gpu": n_local,
                        "l2": "inputs_exceed_l2 (gallery %.0f MB + weights; query batches rotate)" % (
                            n_local * 32 * 256 * 2 / 1e6),
-                       "parallelism": "gallery rows sharded x%d, queries data-parallel" % world,
+                       "parallelism": "gallery rows sharded x%d, queries data-parallel" % world + (
+                           "; two-stream step (fusion of batch i + 1 overlaps the exchange / scan / merge of batch i)"
+                           if pipelined else ""),
                        "weights": "synthetic seed 0, full depth (sprc_b200/synth.py)",
                        "captions": "32-token rows, %.1f live tokens on average (SURVEY 8d: L~U{3..20} + [CLS],[SEP]); "
                                    "%s" % (float(lens_h.float().mean()),
