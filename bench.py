@@ -4,12 +4,16 @@
 One "step" = one batch of Bq (default 2368 = 16 x 148 SMs) composed queries (reference image row + 32-token caption) through the
 hot path: Q-Former fusion (two passes) -> similarity scan over the whole gallery -> top-50.
 Workload at N=1: BASELINE.json configs[1] model (ViT-L BLIP-2, full depth, synthetic weights) with the
-gallery enlarged to the 50k rows the metric is quoted on; the gallery index (bf16 features + bf16 raw
-embeds) is built by our own ViT/Q-Former from synthetic images before the timed region.
+gallery enlarged to the 50k rows the metric is quoted on; the gallery index (16-bit features + 16-bit raw
+embeds) is built by our own ViT/Q-Former from synthetic images before the timed region.  `e2e` starts from caption
+STRINGS (C++ tokenizer inside the timed region).  Extra keys: roofline (+ ours-vs-cuBLAS points on the path's shapes),
+roofline_scan(_hbm), parity (in-process check against the reference's golden), cpu_baseline (the unmodified reference on
+the host cores), eager_gpu, rerank (C5), vit_g (C3 / C4), index_build, index_feed (indexing from PNG files), rank_skew.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-  (N > 1: launched by torch.distributed.run, one rank per GPU; gallery rows sharded, per-shard top-k
-   all-gathered over NCCL and merged; per-GPU query work is fixed => weak scaling)
+  (N > 1: launched by torch.distributed.run, one rank per GPU; gallery rows sharded; per batch one all-gather of the
+   query vectors, ONE scan launch of the shard for all ranks' queries, one all-to-all of the per-shard top-k and a merge
+   of each rank's own queries over NCCL; per-GPU query work is fixed => weak scaling)
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on
 both sides, max over ranks; inputs of consecutive steps differ and the gallery (819 MB) + weights exceed
