@@ -257,6 +257,23 @@ class Blip2QformerCirAlignPrompt:
                                             L.ptr(full), self._stream()))
         return sc, ix, full
 
+    def sim_topk_grouped(self, queries_bf16: torch.Tensor, gallery_bf16: torch.Tensor, k: int, row_offset: int,
+                         exchange: torch.Tensor):
+        """The scan of this rank's shard for ALL ranks' queries in one launch, written straight into the packed exchange
+        buffer `exchange` int32 [P, 2, c, k] (sprc_sim_topk_grouped): query q goes to slot q // c, row q % c; rows the
+        scan does not write (P * c > Q) keep what the caller put there."""
+        q = queries_bf16.to(self._device, self.act_torch_dtype).contiguous()
+        g = gallery_bf16
+        assert g.dtype == self.act_torch_dtype and g.is_contiguous() and g.device == self._device
+        P, two, c, kk = exchange.shape
+        assert two == 2 and kk == k and exchange.dtype == torch.int32 and exchange.is_contiguous()
+        assert q.shape[0] <= P * c
+        with torch.cuda.device(self._device):
+            L.check(self._lib.sprc_sim_topk_grouped(self._h, L.ptr(q), q.shape[0], L.ptr(g), g.shape[0], row_offset, k,
+                                                    L.ptr(exchange[0, 0]), L.ptr(exchange[0, 1]), c, 2 * c * k,
+                                                    self._stream()))
+        return exchange
+
     def gather_scores(self, queries_bf16, gallery_bf16, rows: torch.Tensor) -> torch.Tensor:
         q = queries_bf16.to(self._device, self.act_torch_dtype).contiguous()
         rows = rows.to(self._device, torch.int32).contiguous()

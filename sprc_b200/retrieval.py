@@ -214,10 +214,16 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
             fusion32[sel.to(dev)] = f.float()
         dist.all_reduce(fusion32)  # exactly one rank contributes each row: x + 0 + ... is exact
         fusion = fusion32.to(index.feats.dtype)
+    send = None
     if index.feats.shape[0] == 0:
         # empty shard (fewer images than ranks): no candidates from this rank
         sc = torch.full((Q, k), float("-inf"), dtype=torch.float32, device=dev)
         ix = torch.full((Q, k), -1, dtype=torch.int32, device=dev)
+    elif world > 1 and hasattr(backend, "sim_topk_grouped"):
+        # one launch writes every destination rank's [c, k] block straight into the exchange buffer
+        send = _exchange_buffer(Q, k, world, dev)
+        backend.sim_topk_grouped(fusion, index.feats, k, index.lo, send)
+        sc = ix = None
     else:
         sc, ix, _ = backend.sim_topk(fusion, index.feats, k=k, row_offset=index.lo)
     sub = None
@@ -228,29 +234,40 @@ def query_topk(backend, index: GalleryIndex, ref_rows: torch.Tensor, input_ids: 
         local = torch.where((subset_rows >= index.lo) & (subset_rows < index.hi), local, torch.full_like(local, -1))
         sub = backend.gather_scores(fusion, index.feats, local.to(torch.int32))
     if world > 1:
-        sc, ix = exchange_and_merge(backend, sc, ix, dist, rank, world)
+        sc, ix = exchange_and_merge(backend, sc, ix, dist, rank, world, send=send, Q=Q)
         if sub is not None:
             dist.all_reduce(sub, op=dist.ReduceOp.MAX)  # non-owners hold -inf
     return sc, ix, sub
 
 
-def exchange_and_merge(backend, sc: torch.Tensor, ix: torch.Tensor, dist, rank: int, world: int):
+def _exchange_buffer(Q: int, k: int, world: int, dev) -> torch.Tensor:
+    """int32 [world, 2, c, k] (c = ceil(Q / world)) pre-filled with the padding candidate (-inf, -1)."""
+    c = (Q + world - 1) // world
+    send = torch.empty(world, 2, c, k, dtype=torch.int32, device=dev)
+    send[:, 0] = torch.tensor(float("-inf")).view(torch.int32).item()
+    send[:, 1] = -1
+    return send
+
+
+def exchange_and_merge(backend, sc, ix, dist, rank: int, world: int, send=None, Q=None):
     """Per-shard candidates (sc fp32 / ix int32 [Q,k], identical query order on every rank) -> merged [Q,k] on every
     rank.  ONE all-to-all of one packed buffer delivers to rank r only the candidates of ITS slice of the queries
     (c = ceil(Q / world) queries, P lists of k), rank r merges those c queries, and one all-gather of the merged
     [c, 2k] block makes the (small) result identical everywhere: bytes received per rank 2 * Q * k * 8, flat in the
     number of ranks (an all-gather of all candidates + a replicated merge would be world * Q * k * 8 and Q merges)."""
-    Q, k = sc.shape
-    dev = sc.device
-    c = (Q + world - 1) // world
-    send = torch.empty(world, 2, c, k, dtype=torch.int32, device=dev)
-    send[:, 0] = torch.tensor(float("-inf")).view(torch.int32).item()      # padding queries: (-inf, -1)
-    send[:, 1] = -1
-    flat_s, flat_i = send[:, 0].reshape(world * c, k), send[:, 1].reshape(world * c, k)   # copies when strided
-    flat_s[:Q] = sc.contiguous().view(torch.int32)
-    flat_i[:Q] = ix
-    send[:, 0] = flat_s.view(world, c, k)
-    send[:, 1] = flat_i.view(world, c, k)
+    if send is None:   # candidates as [Q, k] tensors: pack them into the exchange buffer here
+        Q, k = sc.shape
+        dev = sc.device
+        c = (Q + world - 1) // world
+        send = _exchange_buffer(Q, k, world, dev)
+        flat_s, flat_i = send[:, 0].reshape(world * c, k), send[:, 1].reshape(world * c, k)   # copies when strided
+        flat_s[:Q] = sc.contiguous().view(torch.int32)
+        flat_i[:Q] = ix
+        send[:, 0] = flat_s.view(world, c, k)
+        send[:, 1] = flat_i.view(world, c, k)
+    else:              # the scan already wrote it (Model.sim_topk_grouped)
+        _, _, c, k = send.shape
+        dev = send.device
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send)                                       # recv[p] = rank p's lists for MY queries
     if hasattr(backend, "topk_merge_packed"):
