@@ -1155,6 +1155,18 @@ def main():
                              f"same {N}-row gallery (our index as fp32) for >= 12 s after one warm-up "
                              f"({time.perf_counter() - t_cpu0:.1f} s in all incl. model construction), torch CPU "
                              f"eager on {cores} host threads, {sec:.2f} s per batch"}
+            # the indexing half of the path on the same host cores: the unmodified reference's
+            # extract_target_features (ViT + Q-Former gallery pass, fp32) on one batch of 8 synthetic images
+            try:
+                imgs = synth.make_images(8)
+                t_i0 = time.perf_counter()
+                with torch.no_grad():
+                    ref_model.extract_target_features(imgs, mode="mean")
+                cpu["index_images_per_s"] = 8 / (time.perf_counter() - t_i0)
+                cpu["index_sample"] = ("ONE batch of 8 synthetic images through the unmodified reference "
+                                       "extract_target_features (no warm-up), same host threads")
+            except Exception as e:  # informative
+                cpu["index_error"] = f"{type(e).__name__}: {e}"[:200]
             del ref_model
         else:
             qps, sec = cpu_query_sample(args.vit, args.cpu_sample, gal_cpu, sd, steps=1, warmup=1, min_seconds=12.0)
